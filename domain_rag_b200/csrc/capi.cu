@@ -1,0 +1,225 @@
+// extern "C" surface of libdomainrag_b200.so (declared in include/domainrag_b200.h).
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/domainrag_b200.h"
+#include "common.cuh"
+#include "index.cuh"
+
+namespace drag {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+int device_sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return n;
+}
+
+}  // namespace drag
+
+using namespace drag;
+
+extern "C" {
+
+const char* drag_last_error(void) { return g_last_error.c_str(); }
+int drag_version(void) { return 100; }
+
+int drag_device_count(int* count) {
+    DRAG_REQUIRE(count, "drag_device_count: null pointer");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(DRAG_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    return DRAG_OK;
+}
+
+int drag_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len) {
+    cudaDeviceProp p;
+    DRAG_CUDA(cudaGetDeviceProperties(&p, device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (name && name_len > 0) {
+        strncpy(name, p.name, name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    return DRAG_OK;
+}
+
+// ------------------------------------------------------------------------------------ index
+int drag_index_create(int d, int device, drag_index_t** out) {
+    DRAG_REQUIRE(out, "drag_index_create: null out pointer");
+    DRAG_REQUIRE(d >= 1 && d <= 16384, "drag_index_create: need 1 <= d <= 16384");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(DRAG_ERR_NO_DEVICE, "drag_index_create: no CUDA device (this library has no CPU path)");
+    DRAG_REQUIRE(device >= 0 && device < ndev, "drag_index_create: bad device ordinal");
+    Index* ix = new Index();
+    ix->d = d;
+    ix->device = device;
+    DRAG_CUDA(cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, device));
+    *out = reinterpret_cast<drag_index_t*>(ix);
+    return DRAG_OK;
+}
+
+int drag_index_reset(drag_index_t* h) {
+    DRAG_REQUIRE(h, "drag_index_reset: null index");
+    Index* ix = reinterpret_cast<Index*>(h);
+    DRAG_CUDA(cudaSetDevice(ix->device));
+    for (Segment& s : ix->segs)
+        if (s.owned && s.X) DRAG_CUDA(cudaFree(s.X));
+    ix->segs.clear();
+    ix->ntotal = 0;
+    ix->seg_tab_n = -1;
+    return DRAG_OK;
+}
+
+int drag_index_destroy(drag_index_t* h) {
+    if (!h) return DRAG_OK;
+    Index* ix = reinterpret_cast<Index*>(h);
+    int rc = drag_index_reset(h);
+    if (ix->partial) cudaFree(ix->partial);
+    if (ix->qdev) cudaFree(ix->qdev);
+    if (ix->Ddev) cudaFree(ix->Ddev);
+    if (ix->Idev) cudaFree(ix->Idev);
+    if (ix->seg_start) cudaFree(ix->seg_start);
+    if (ix->seg_base) cudaFree(ix->seg_base);
+    if (ix->ev0) cudaEventDestroy(ix->ev0);
+    if (ix->ev1) cudaEventDestroy(ix->ev1);
+    delete ix;
+    return rc;
+}
+
+int drag_index_add(drag_index_t* h, const float* X, int64_t N, int64_t base_id, int x_on_device, void* stream) {
+    DRAG_REQUIRE(h, "drag_index_add: null index");
+    DRAG_REQUIRE(N >= 0, "drag_index_add: negative row count");
+    if (N == 0) return DRAG_OK;
+    DRAG_REQUIRE(X, "drag_index_add: null data pointer");
+    Index* ix = reinterpret_cast<Index*>(h);
+    DRAG_REQUIRE(ix->ntotal + N < 0xFFFFFFFFll, "drag_index_add: more than 2^32-1 rows on one device");
+    DRAG_CUDA(cudaSetDevice(ix->device));
+    Segment s;
+    s.N = N;
+    s.base_id = base_id;
+    s.owned = true;
+    const size_t bytes = static_cast<size_t>(N) * ix->d * sizeof(float);
+    DRAG_CUDA(cudaMalloc(&s.X, bytes));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemcpyAsync(s.X, X, bytes, x_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && !x_on_device) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cudaFree(s.X);
+        return fail(DRAG_ERR_CUDA, std::string("drag_index_add copy: ") + cudaGetErrorString(e));
+    }
+    ix->segs.push_back(s);
+    ix->ntotal += N;
+    ix->seg_tab_n = -1;
+    return DRAG_OK;
+}
+
+int drag_index_adopt(drag_index_t* h, const float* X_dev, int64_t N, int64_t base_id) {
+    DRAG_REQUIRE(h, "drag_index_adopt: null index");
+    DRAG_REQUIRE(N >= 0, "drag_index_adopt: negative row count");
+    if (N == 0) return DRAG_OK;
+    DRAG_REQUIRE(X_dev, "drag_index_adopt: null data pointer");
+    Index* ix = reinterpret_cast<Index*>(h);
+    DRAG_REQUIRE(ix->ntotal + N < 0xFFFFFFFFll, "drag_index_adopt: more than 2^32-1 rows on one device");
+    Segment s;
+    s.X = const_cast<float*>(X_dev);
+    s.N = N;
+    s.base_id = base_id;
+    s.owned = false;
+    ix->segs.push_back(s);
+    ix->ntotal += N;
+    ix->seg_tab_n = -1;
+    return DRAG_OK;
+}
+
+int drag_index_ntotal(drag_index_t* h, int64_t* ntotal) {
+    DRAG_REQUIRE(h && ntotal, "drag_index_ntotal: null pointer");
+    *ntotal = reinterpret_cast<Index*>(h)->ntotal;
+    return DRAG_OK;
+}
+
+int drag_index_search_device(drag_index_t* h, const float* q_dev, int nq, int k, float* D_dev, int64_t* I_dev,
+                             void* stream) {
+    return index_search_device(reinterpret_cast<Index*>(h), q_dev, nq, k, D_dev, I_dev,
+                               reinterpret_cast<cudaStream_t>(stream));
+}
+
+int drag_index_search(drag_index_t* h, const float* q_host, int nq, int k, float* D_host, int64_t* I_host) {
+    DRAG_REQUIRE(h, "drag_index_search: null index");
+    DRAG_REQUIRE(nq >= 0 && k >= 1, "drag_index_search: bad nq/k");
+    if (nq == 0) return DRAG_OK;
+    DRAG_REQUIRE(q_host && D_host && I_host, "drag_index_search: null pointer");
+    Index* ix = reinterpret_cast<Index*>(h);
+    DRAG_CUDA(cudaSetDevice(ix->device));
+    int rc = index_ensure_io(ix, nq, k);
+    if (rc) return rc;
+    cudaStream_t st = 0;
+    DRAG_CUDA(cudaMemcpyAsync(ix->qdev, q_host, static_cast<size_t>(nq) * ix->d * sizeof(float),
+                              cudaMemcpyHostToDevice, st));
+    rc = index_search_device(ix, ix->qdev, nq, k, ix->Ddev, ix->Idev, st);
+    if (rc) return rc;
+    DRAG_CUDA(cudaMemcpyAsync(D_host, ix->Ddev, static_cast<size_t>(nq) * k * sizeof(float),
+                              cudaMemcpyDeviceToHost, st));
+    DRAG_CUDA(cudaMemcpyAsync(I_host, ix->Idev, static_cast<size_t>(nq) * k * sizeof(int64_t),
+                              cudaMemcpyDeviceToHost, st));
+    DRAG_CUDA(cudaStreamSynchronize(st));
+    return DRAG_OK;
+}
+
+int drag_index_last_launch(drag_index_t* h, int* grid, int* stages, int* rows_per_stage, int* nq_batch) {
+    DRAG_REQUIRE(h, "drag_index_last_launch: null index");
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (grid) *grid = ix->last_grid;
+    if (stages) *stages = ix->last_stages;
+    if (rows_per_stage) *rows_per_stage = ix->last_rps;
+    if (nq_batch) *nq_batch = ix->last_nqb;
+    return DRAG_OK;
+}
+
+int drag_index_set_timing(drag_index_t* h, int enable) {
+    DRAG_REQUIRE(h, "drag_index_set_timing: null index");
+    Index* ix = reinterpret_cast<Index*>(h);
+    DRAG_CUDA(cudaSetDevice(ix->device));
+    if (enable && !ix->ev0) {
+        DRAG_CUDA(cudaEventCreate(&ix->ev0));
+        DRAG_CUDA(cudaEventCreate(&ix->ev1));
+    }
+    ix->timing = enable != 0;
+    return DRAG_OK;
+}
+
+int drag_index_last_scan_ms(drag_index_t* h, float* ms) {
+    DRAG_REQUIRE(h && ms, "drag_index_last_scan_ms: null pointer");
+    Index* ix = reinterpret_cast<Index*>(h);
+    DRAG_REQUIRE(ix->timing && ix->ev0, "drag_index_last_scan_ms: timing not enabled");
+    DRAG_CUDA(cudaEventSynchronize(ix->ev1));
+    DRAG_CUDA(cudaEventElapsedTime(ms, ix->ev0, ix->ev1));
+    return DRAG_OK;
+}
+
+int drag_topk_merge_device(const float* scores, const int64_t* ids, int nq, int lists, int k_in, int k_out,
+                           float* D_dev, int64_t* I_dev, void* stream) {
+    return merge_pairs_device(scores, ids, nq, lists, k_in, k_out, D_dev, I_dev,
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------ stem
+int drag_stem_stats(const float* img_dev, int B, int H, int W, const float* w_fold_dev, const float* b_fold_dev,
+                    float eps, float* out_dev, void* stream) {
+    return stem_stats_device(img_dev, B, H, W, w_fold_dev, b_fold_dev, eps, out_dev,
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

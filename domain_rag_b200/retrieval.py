@@ -1,0 +1,144 @@
+"""Host-side mirror of the reference's two-stage retrieval functions
+(retrieval/clip100_resnet_style_all_shots.py), same names / argument meaning / return records,
+with the third-party calls served by libdomainrag_b200.so:
+
+  clip_first_stage_retrieval  :396-451  faiss.IndexFlatIP add/search -> IndexFlatIP (HBM resident,
+                                        cached across queries instead of rebuilt per query)
+  compute_resnet_features     :180-203  cv2 read/resize -> fused stem+stats kernel
+  resnet_second_stage_rerank  :454-497  101 batch-1 launches -> ONE batched launch; distance /
+                                        stable sort / 1/(1+d) on the host exactly as the reference
+Error convention is the reference's: print + return []/None/first-stage results and continue.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .index import IndexFlatIP
+
+_INDEX_CACHE: dict = {}
+
+
+def clean_image_path(path):
+    """reference :77-86 - strip the stray "pipeline/" prefix some caches carry."""
+    if isinstance(path, str):
+        return path.replace("../../pipeline/datasets", "../../datasets")
+    return path
+
+
+def _cached_index(dataset_features: Dict[str, np.ndarray], d: int, device: int) -> IndexFlatIP:
+    """One resident index per (set of feature arrays); the reference re-adds N*d floats per query."""
+    key = (device, d) + tuple((name, id(f), len(f)) for name, f in dataset_features.items()
+                              if f is not None and len(f) > 0)
+    ix = _INDEX_CACHE.get(key)
+    if ix is None:
+        _INDEX_CACHE.clear()  # keep a single corpus resident
+        ix = IndexFlatIP(d, device)
+        for name, f in dataset_features.items():
+            if f is not None and len(f) > 0:
+                ix.add(np.asarray(f, dtype=np.float32))  # dict order == reference vstack order (:406-419)
+        _INDEX_CACHE[key] = ix
+    return ix
+
+
+def clip_first_stage_retrieval(query_feature, dataset_features, dataset_paths, top_k=100, device: int = 0):
+    """Stage A: exact inner-product top-k over every source dataset; returns the reference records
+    {similarity, image_path, source_dataset, index} in descending score."""
+    all_paths: List[str] = []
+    all_sources: List[str] = []
+    n_total = 0
+    for name, feats in dataset_features.items():
+        if feats is not None and len(feats) > 0:
+            paths = dataset_paths[name]
+            print(f"将从{name}数据集({len(feats)}张图像)中检索")
+            all_paths.extend(paths)
+            all_sources.extend([name] * len(paths))
+            n_total += len(feats)
+    if n_total == 0:
+        print("错误：没有可用的数据集特征")
+        return []
+    print(f"总共使用 {n_total} 张图像进行检索")
+    try:
+        q = np.asarray([query_feature], dtype=np.float32)
+        ix = _cached_index(dataset_features, q.shape[1], device)
+        D, I = ix.search(q, min(top_k, n_total))
+        results = []
+        for i, idx in enumerate(I[0]):
+            if 0 <= idx < len(all_paths):
+                results.append({"similarity": float(D[0][i]), "image_path": all_paths[idx],
+                                "source_dataset": all_sources[idx], "index": int(idx)})
+        return results
+    except Exception as e:  # reference :449-451
+        print(f"CLIP检索时出错: {e}")
+        return []
+
+
+def load_style_input(image_path: str):
+    """reference :186-193: cv2.imread -> RGB -> resize(256,256) -> float /255 -> CHW (host tensor)."""
+    import cv2
+    import torch
+    img = cv2.imread(clean_image_path(image_path))
+    if img is None:
+        print(f"警告：无法读取图像 {image_path}")
+        return None
+    img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+    img = cv2.resize(img, (256, 256))
+    return torch.tensor(img).float().permute(2, 0, 1) / 255.0
+
+
+def compute_resnet_features(image_path, model, device):
+    """reference :180-203 - one image -> float32 [128] = cat(mean, std), or None on failure."""
+    try:
+        x = load_style_input(image_path)
+        if x is None:
+            return None
+        return model.style_features(x.unsqueeze(0).to(device))[0].cpu().numpy()
+    except Exception as e:
+        print(f"计算ResNet特征时出错: {e}, 图像: {image_path}")
+        return None
+
+
+def compute_resnet_features_batch(image_paths: Sequence[str], model, device) -> List[Optional[np.ndarray]]:
+    """All candidates of a query in ONE kernel launch (the reference does 101 batch-1 launches)."""
+    import torch
+    xs, slots = [], []
+    for i, p in enumerate(image_paths):
+        x = load_style_input(p)
+        if x is not None:
+            xs.append(x)
+            slots.append(i)
+    out: List[Optional[np.ndarray]] = [None] * len(image_paths)
+    if xs:
+        batch = torch.stack(xs).pin_memory().to(device, non_blocking=True)
+        feats = model.style_features(batch).cpu().numpy()
+        for j, i in enumerate(slots):
+            out[i] = feats[j]
+    return out
+
+
+def rerank_by_style(query_feat, cand_feats, first_stage_results):
+    """Distance / stable sort / similarity of reference :474-495 on precomputed 128-d features."""
+    rerank_results = []
+    for result, f in zip(first_stage_results, cand_feats):
+        if f is None:
+            continue  # reference :472 silently drops unreadable candidates
+        distance = np.linalg.norm(np.asarray(query_feat, np.float32) - np.asarray(f, np.float32))
+        rerank_results.append({"clip_similarity": result["similarity"], "resnet_distance": float(distance),
+                               "image_path": clean_image_path(result["image_path"]),
+                               "source_dataset": result.get("source_dataset", "unknown")})
+    rerank_results.sort(key=lambda x: x["resnet_distance"])
+    return [{"rank": i + 1, "similarity": float(1.0 / (1.0 + r["resnet_distance"])),
+             "image_path": r["image_path"], "source_dataset": r["source_dataset"]}
+            for i, r in enumerate(rerank_results)]
+
+
+def resnet_second_stage_rerank(query_image_path, first_stage_results, resnet_model, device):
+    """Stage B: re-rank the CLIP candidates by L2 distance of stem style statistics."""
+    query_image_path = clean_image_path(query_image_path)
+    paths = [query_image_path] + [clean_image_path(r["image_path"]) for r in first_stage_results]
+    feats = compute_resnet_features_batch(paths, resnet_model, device)
+    if feats[0] is None:
+        print(f"警告：无法计算查询图像的ResNet特征: {query_image_path}")
+        return first_stage_results
+    return rerank_by_style(feats[0], feats[1:], first_stage_results)

@@ -1,0 +1,79 @@
+/*
+ * libdomainrag_b200.so - C ABI of the B200-native Domain-RAG retrieve-then-compose hot path.
+ *
+ * Every entry point returns an int status (0 = ok); the message for the last failure on the calling
+ * thread is available from drag_last_error(). Unless a function says "host", every pointer is a
+ * DEVICE pointer valid on the handle's device, and work is enqueued on `stream` (a cudaStream_t
+ * passed as void*; NULL = the legacy default stream) without synchronising. The library never
+ * frees caller memory.  No torch types cross this boundary.
+ *
+ * The reference (LiYu0524/Domain-RAG) has no FFI of its own: its hot path is seven calls into
+ * third-party Python packages. Each group below names the call site it replaces
+ * (paths relative to the reference root). INTEGRATION.md shows the ctypes binding.
+ */
+#ifndef DOMAINRAG_B200_H
+#define DOMAINRAG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRAG_OK 0
+#define DRAG_ERR_INVALID 1
+#define DRAG_ERR_CUDA 2
+#define DRAG_ERR_UNSUPPORTED 3
+#define DRAG_ERR_NO_DEVICE 4
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* drag_last_error(void);
+int drag_version(void);
+/* Number of visible CUDA devices and the SM count / name of one of them. */
+int drag_device_count(int* count);
+int drag_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len);
+
+/* ---- exact inner-product index ---------------------------------------------------------------
+ * Replaces faiss.IndexFlatIP(d) / index.add(X) / index.search(q, k) at
+ * retrieval/clip100_resnet_style_all_shots.py:425-434 (clip_first_stage_retrieval).
+ * The corpus stays resident in HBM across queries (the reference rebuilds the index per query).
+ * Results: scores descending; equal scores -> lower id first; missing slots -> (-FLT_MAX, -1).
+ * Limits: 1 <= k <= 1024; fewer than 2^32-1 rows per device. */
+typedef struct drag_index drag_index_t;
+int drag_index_create(int d, int device, drag_index_t** out);
+int drag_index_destroy(drag_index_t* h);
+/* Copy N rows of fp32 [N][d] into index-owned device memory; ids are base_id .. base_id+N-1.
+ * x_on_device = 0: X is a host pointer (the faiss contract), 1: X is a device pointer. */
+int drag_index_add(drag_index_t* h, const float* X, int64_t N, int64_t base_id, int x_on_device, void* stream);
+/* Zero-copy variant: the index scans caller-owned device memory (must outlive the index). */
+int drag_index_adopt(drag_index_t* h, const float* X_dev, int64_t N, int64_t base_id);
+int drag_index_reset(drag_index_t* h);
+int drag_index_ntotal(drag_index_t* h, int64_t* ntotal);
+/* HOST buffers, synchronous - the drop-in for index.search(): q [nq][d] -> D [nq][k], I [nq][k]. */
+int drag_index_search(drag_index_t* h, const float* q_host, int nq, int k, float* D_host, int64_t* I_host);
+/* DEVICE buffers, asynchronous on `stream`. */
+int drag_index_search_device(drag_index_t* h, const float* q_dev, int nq, int k, float* D_dev, int64_t* I_dev, void* stream);
+/* Geometry of the most recent scan launch (for roofline arithmetic in bench.py). */
+int drag_index_last_launch(drag_index_t* h, int* grid, int* stages, int* rows_per_stage, int* nq_batch);
+/* Optional CUDA-event bracket around the scan kernel launches of the next searches (the merge
+ * kernel is outside it); drag_index_last_scan_ms synchronises on the closing event. */
+int drag_index_set_timing(drag_index_t* h, int enable);
+int drag_index_last_scan_ms(drag_index_t* h, float* ms);
+/* Merge `lists` per-shard top-k_in lists per query (after the all-gather of per-shard results,
+ * SURVEY 8e) into the global top-k_out: scores/ids [nq][lists][k_in] -> D/I [nq][k_out].
+ * ids < 0 mark empty slots. lists*k_in <= 8192. */
+int drag_topk_merge_device(const float* scores, const int64_t* ids, int nq, int lists, int k_in, int k_out,
+                           float* D_dev, int64_t* I_dev, void* stream);
+
+/* ---- ResNet-50 stem + style statistics --------------------------------------------------------
+ * Replaces ResNetEncoder()(x) + calc_mean_std (retrieval/clip100_resnet_style_all_shots.py:51-74,
+ * 197-200): img fp32 [B][3][256][256] in [0,1] -> out fp32 [B][128] = cat(mean[64], std[64]),
+ * std = sqrt(unbiased var + eps). w_fold [64][3][7][7] / b_fold [64] are conv1 with eval-mode bn1
+ * folded in. */
+int drag_stem_stats(const float* img_dev, int B, int H, int W, const float* w_fold_dev, const float* b_fold_dev,
+                    float eps, float* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOMAINRAG_B200_H */

@@ -1,0 +1,77 @@
+"""GPU parity: fused ResNet-50 stem + style statistics vs the oracle and the reference golden."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ip_topk as O
+from oracle import stem as S
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4   # stem stats rel-err <= 1e-4 (fp32 path)
+
+
+@pytest.fixture(scope="module")
+def enc(lib):
+    from domain_rag_b200.resnet import ResNetEncoder
+    return ResNetEncoder(seed=2000).to("cuda").eval()
+
+
+def test_matches_reference_golden(enc, golden_dir):
+    g = np.load(golden_dir / "stem_stats.npz")
+    x = torch.rand(4, 3, 256, 256, generator=torch.Generator().manual_seed(int(g["input_seed"])))
+    got = enc.style_features(x.cuda()).cpu().numpy()
+    np.testing.assert_allclose(got, g["stats"], rtol=RTOL, atol=1e-6)
+
+
+def test_reference_call_pattern(enc):
+    """features = model(img); mean, std = calc_mean_std(features); cat([mean.squeeze(), std.squeeze()])"""
+    from domain_rag_b200.resnet import calc_mean_std
+    x = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(5))
+    feats = enc(x.cuda())
+    mean, std = calc_mean_std(feats)
+    assert mean.shape == (1, 64, 1, 1) and std.shape == (1, 64, 1, 1)
+    got = torch.cat([mean.squeeze(), std.squeeze()]).cpu()
+    want = S.style_features(x, enc.state)[0]
+    torch.testing.assert_close(got, want, rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.parametrize("b,kind", [(1, "rand"), (7, "rand"), (101, "rand"), (3, "zeros"), (2, "ones"),
+                                    (2, "sparse")])
+def test_matches_oracle(enc, b, kind):
+    g = torch.Generator().manual_seed(100 + b)
+    if kind == "rand":
+        x = torch.rand(b, 3, 256, 256, generator=g)
+    elif kind == "zeros":
+        x = torch.zeros(b, 3, 256, 256)
+    elif kind == "ones":
+        x = torch.ones(b, 3, 256, 256)
+    else:
+        x = (torch.rand(b, 3, 256, 256, generator=g) > 0.97).float()
+    got = enc.style_features(x.cuda()).cpu()
+    want = S.style_features(x, enc.state)
+    torch.testing.assert_close(got, want, rtol=RTOL, atol=2e-6)
+
+
+def test_rerank_order_matches_reference_golden(enc, golden_dir):
+    """Second-stage re-rank (reference :454-497) with GPU features reproduces the reference's order."""
+    import cv2
+    from domain_rag_b200.retrieval import rerank_by_style
+    g = json.load(open(golden_dir / "rerank.json"))
+
+    def load(name):
+        img = cv2.imread(str(golden_dir / "images" / name))
+        if img is None:
+            return None
+        img = cv2.resize(cv2.cvtColor(img, cv2.COLOR_BGR2RGB), (256, 256))
+        return torch.tensor(img).float().permute(2, 0, 1) / 255.0
+
+    qf = enc.style_features(load(g["query"])[None].cuda())[0].cpu().numpy()
+    cands = [load(r["image_path"]) for r in g["first_stage"]]
+    feats = [None if c is None else enc.style_features(c[None].cuda())[0].cpu().numpy() for c in cands]
+    got = rerank_by_style(qf, feats, g["first_stage"])
+    assert [r["image_path"] for r in got] == [r["image_path"] for r in g["reranked"]]
+    np.testing.assert_allclose([r["similarity"] for r in got], [r["similarity"] for r in g["reranked"]],
+                               rtol=1e-4)
+    assert got == O.rerank_by_style(qf, feats, g["first_stage"])
