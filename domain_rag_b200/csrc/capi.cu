@@ -6,6 +6,7 @@
 
 #include "../../include/domainrag_b200.h"
 #include "common.cuh"
+#include "gemm.cuh"
 #include "index.cuh"
 
 namespace drag {
@@ -220,6 +221,50 @@ int drag_stem_stats(const float* img_dev, int B, int H, int W, const float* w_fo
                     float eps, float* out_dev, void* stream) {
     return stem_stats_device(img_dev, B, H, W, w_fold_dev, b_fold_dev, eps, out_dev,
                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------ gemm
+int drag_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epi_mode,
+                   const void* bias, void* out, int ldo, const void* resid, int ldr, const void* gate,
+                   int gate_ld, int rows_per_batch, void* stream) {
+    DRAG_REQUIRE(epi_mode >= 0 && epi_mode <= 6 && epi_mode != EPI_QKV_ROPE, "drag_gemm_bf16: bad epi_mode");
+    GemmEpi e;
+    e.mode = epi_mode;
+    e.bias = static_cast<const __nv_bfloat16*>(bias);
+    if (epi_mode == EPI_BIAS_F32) e.out_f32 = static_cast<float*>(out);
+    else e.out = static_cast<__nv_bfloat16*>(out);
+    e.ldo = ldo;
+    e.resid = static_cast<const __nv_bfloat16*>(resid);
+    e.ldr = ldr;
+    e.gate = static_cast<const __nv_bfloat16*>(gate);
+    e.gate_ld = gate_ld;
+    e.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : (1 << 30);
+    if (epi_mode == EPI_GATE_RESID) DRAG_REQUIRE(resid, "drag_gemm_bf16: gated residual needs resid");
+    return gemm_bf16(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(W), ldw, M, N, K,
+                     e, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int drag_gemm_qkv_rope(const void* A, int lda, const void* W, int ldw, int M, int K, int heads, const void* bias,
+                       void* q_out, void* k_out, void* v_out, const void* q_norm_w, const void* k_norm_w,
+                       const float* rope_cos, const float* rope_sin, int s_total, int tok_offset,
+                       int rows_per_batch, float rms_eps, void* stream) {
+    GemmEpi e;
+    e.mode = EPI_QKV_ROPE;
+    e.bias = static_cast<const __nv_bfloat16*>(bias);
+    e.q_out = static_cast<__nv_bfloat16*>(q_out);
+    e.k_out = static_cast<__nv_bfloat16*>(k_out);
+    e.v_out = static_cast<__nv_bfloat16*>(v_out);
+    e.q_norm_w = static_cast<const __nv_bfloat16*>(q_norm_w);
+    e.k_norm_w = static_cast<const __nv_bfloat16*>(k_norm_w);
+    e.rope_cos = rope_cos;
+    e.rope_sin = rope_sin;
+    e.heads = heads;
+    e.s_total = s_total;
+    e.tok_offset = tok_offset;
+    e.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : (1 << 30);
+    e.rms_eps = rms_eps;
+    return gemm_bf16(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(W), ldw, M,
+                     3 * heads * 128, K, e, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,48 @@
+// Host/device interface of the tcgen05 GEMM core (gemm_tcgen05.cu).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace drag {
+
+enum GemmEpiMode : int {
+    EPI_BIAS = 0,        // out = acc + bias                        (bf16)
+    EPI_GELU_TANH = 1,   // out = gelu_tanh(acc + bias)             (Flux MLP)
+    EPI_QUICK_GELU = 2,  // out = x * sigmoid(1.702 x)              (OpenAI CLIP MLP)
+    EPI_SILU = 3,        // out = x * sigmoid(x)                    (time/guidance/pooled MLPs, Redux)
+    EPI_GATE_RESID = 4,  // out = resid + gate[b][n] * (acc + bias) (gate == null: plain residual)
+    EPI_QKV_ROPE = 5,    // per-head RMSNorm(q,k) + RoPE, scatter to [B][H][S][128]
+    EPI_BIAS_F32 = 6,    // out_f32 = acc + bias
+};
+
+struct GemmEpi {
+    int mode = EPI_BIAS;
+    const __nv_bfloat16* bias = nullptr;  // [N] or null
+    __nv_bfloat16* out = nullptr;         // row-major, leading dimension ldo (elements)
+    float* out_f32 = nullptr;
+    int ldo = 0;
+    // EPI_GATE_RESID
+    const __nv_bfloat16* resid = nullptr;
+    int ldr = 0;
+    const __nv_bfloat16* gate = nullptr;  // [B][gate_ld]
+    int gate_ld = 0;
+    int rows_per_batch = 1 << 30;         // batch index of a row = row / rows_per_batch
+    // EPI_QKV_ROPE: N == 3 * heads * 128, columns [0,H*128) = q, then k, then v
+    __nv_bfloat16* q_out = nullptr;       // [B][H][S_total][128]
+    __nv_bfloat16* k_out = nullptr;
+    __nv_bfloat16* v_out = nullptr;
+    const __nv_bfloat16* q_norm_w = nullptr;  // [128]
+    const __nv_bfloat16* k_norm_w = nullptr;  // [128]
+    const float* rope_cos = nullptr;      // [S_total][64]
+    const float* rope_sin = nullptr;      // [S_total][64]
+    int heads = 0, s_total = 0, tok_offset = 0;
+    float rms_eps = 1e-6f;
+};
+
+// C[M,N] = A[M,K] (bf16 row-major, lda) x W[N,K]^T (bf16 row-major, ldw), fp32 accumulate in TMEM.
+// Requirements: K % 8 == 0, lda % 8 == 0, ldw % 8 == 0, A and W 16-byte aligned.
+int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
+              const GemmEpi& epi, cudaStream_t st);
+
+}  // namespace drag

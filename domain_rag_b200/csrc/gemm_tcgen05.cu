@@ -1,0 +1,409 @@
+// bf16 GEMM core on 5th-gen tensor cores: C[M,N] = A[M,K] * W[N,K]^T with fused epilogues.
+//
+// Persistent, warp-specialised, one CTA per SM (grid = min(tiles, #SM)):
+//   warp 0 (1 lane)  TMA producer: A/W tiles (128 x 64 and BN x 64 bf16, SWIZZLE_128B) into a
+//                    STAGES-deep shared-memory ring, completion by mbarrier transaction bytes;
+//   warp 1 (1 lane)  MMA issuer: tcgen05.mma cta_group::1 kind::f16, UMMA 128 x BN x 16, fp32
+//                    accumulators in TMEM (2 accumulator stages x BN columns), tcgen05.commit
+//                    releases ring slots and publishes finished accumulators;
+//   warps 2..5       epilogue: tcgen05.ld (32 lanes x 32 columns per instruction), fused
+//                    bias / activation / gate*x+residual / per-head RMSNorm+RoPE, bf16 stores.
+// The epilogue of tile i overlaps the MMAs of tile i+1 through the double-buffered accumulator.
+// Tile order is M-fastest so that concurrently running CTAs share the same W tile in L2.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace drag {
+
+constexpr int G_BM = 128;
+constexpr int G_BK = 64;
+constexpr int G_THREADS = 192;
+constexpr int G_EPI_WARP0 = 2;
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int A_BYTES = G_BM * G_BK * 2;
+    static constexpr int B_BYTES = BN * G_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator stages
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmShape {
+    int M, N, K;
+    int num_m, num_n, num_k;
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+    const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+    const float t = 1.f - 2.f / (__expf(2.f * u) + 1.f);
+    return 0.5f * x * (1.f + t);
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]);
+    __nv_bfloat162 p3 = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&p0);
+    u.y = *reinterpret_cast<uint32_t*>(&p1);
+    u.z = *reinterpret_cast<uint32_t*>(&p2);
+    u.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(dst) = u;
+}
+
+__device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* src, float* v) {
+    uint4 u = *reinterpret_cast<const uint4*>(src);
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(p[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+
+// Generic epilogue on one 32-column chunk held in registers (this thread = one row).
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, float (&v)[32], int row, int col0, int N) {
+    if (e.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            float b[8];
+            load_bf16x8(e.bias + col0 + j, b);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[j + t] += b[t];
+        }
+    }
+    if (e.mode == EPI_GELU_TANH) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+    } else if (e.mode == EPI_QUICK_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] * sigmoid_f(1.702f * v[j]);
+    } else if (e.mode == EPI_SILU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] * sigmoid_f(v[j]);
+    } else if (e.mode == EPI_GATE_RESID) {
+        const int b = row / e.rows_per_batch;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            float r[8];
+            load_bf16x8(e.resid + static_cast<size_t>(row) * e.ldr + col0 + j, r);
+            if (e.gate) {
+                float g[8];
+                load_bf16x8(e.gate + static_cast<size_t>(b) * e.gate_ld + col0 + j, g);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[j + t] = r[t] + g[t] * bf16_round(v[j + t]);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[j + t] = r[t] + bf16_round(v[j + t]);
+            }
+        }
+    }
+    if (e.mode == EPI_BIAS_F32) {
+        float* dst = e.out_f32 + static_cast<size_t>(row) * e.ldo + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+        __nv_bfloat16* dst = e.out + static_cast<size_t>(row) * e.ldo + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) store_bf16x8(dst + j, &v[j]);
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(G_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         GemmShape sh, GemmEpi epi) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);   // SWIZZLE_128B tiles: 1024-B aligned
+    uint8_t* tiles = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty = full + Cfg::STAGES;
+    uint64_t* tmem_full = empty + Cfg::STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = sh.num_m * sh.num_n;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < Cfg::STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);   // one arrival per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        int stage = 0, phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int m_blk = t % sh.num_m, n_blk = t / sh.num_m;
+            for (int kb = 0; kb < sh.num_k; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* a_dst = tiles + stage * Cfg::STAGE_BYTES;
+                uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+                mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                tma_load_2d(a_dst, &tmA, kb * G_BK, m_blk * G_BM, &full[stage]);
+                tma_load_2d(b_dst, &tmB, kb * G_BK, n_blk * BN, &full[stage]);
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = umma_idesc_bf16(G_BM, BN);
+        int stage = 0, phase = 0;
+        int acc = 0, acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < sh.num_k; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
+                const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+                const uint64_t a_desc = umma_desc_k_sw128(a_addr);
+                const uint64_t b_desc = umma_desc_k_sw128(b_addr);
+#pragma unroll
+                for (int k = 0; k < G_BK / 16; ++k) {
+                    // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the addr>>4 field
+                    tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                }
+                tc_commit(&empty[stage]);          // slot reusable once these MMAs have read it
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(&tmem_full[acc]);            // accumulator complete
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= G_EPI_WARP0) {
+        // ------------------------------------------------------------------ epilogue
+        const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+        int acc = 0, acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int m_blk = t % sh.num_m, n_blk = t / sh.num_m;
+            const int row = m_blk * G_BM + quarter * 32 + lane;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+            if (epi.mode == EPI_QKV_ROPE) {
+                // BN covers BN/128 whole heads; columns [0,H*128) q, [H*128, 2H*128) k, rest v
+                const int hd = 128;
+                const int b = row / epi.rows_per_batch;
+                const int pos = epi.tok_offset + (row - b * epi.rows_per_batch);
+#pragma unroll 1
+                for (int h0 = 0; h0 < BN; h0 += hd) {
+                    const int col_h = n_blk * BN + h0;
+                    const int which = col_h / (epi.heads * hd);          // 0 q, 1 k, 2 v
+                    const int head = (col_h - which * epi.heads * hd) / hd;
+                    __nv_bfloat16* dst_base = (which == 0 ? epi.q_out : (which == 1 ? epi.k_out : epi.v_out));
+                    float inv_rms = 1.f;
+                    if (which < 2) {   // pass 1: sum of squares of the bf16-rounded projection
+                        float ss = 0.f;
+#pragma unroll 1
+                        for (int c = 0; c < hd; c += 32) {
+                            uint32_t r[32];
+                            tmem_ld_32x32(t_addr + h0 + c, r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                float bb[8];
+                                if (epi.bias) load_bf16x8(epi.bias + col_h + c + j, bb);
+#pragma unroll
+                                for (int tt = 0; tt < 8; ++tt) {
+                                    float x = __uint_as_float(r[j + tt]) + (epi.bias ? bb[tt] : 0.f);
+                                    x = bf16_round(x);
+                                    ss = fmaf(x, x, ss);
+                                }
+                            }
+                        }
+                        inv_rms = rsqrtf(ss * (1.f / hd) + epi.rms_eps);
+                    }
+                    const __nv_bfloat16* nw = (which == 0) ? epi.q_norm_w : epi.k_norm_w;
+#pragma unroll 1
+                    for (int c = 0; c < hd; c += 32) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(t_addr + h0 + c, r);
+                        tmem_ld_wait();
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            float bb[8];
+                            if (epi.bias) load_bf16x8(epi.bias + col_h + c + j, bb);
+#pragma unroll
+                            for (int tt = 0; tt < 8; ++tt)
+                                v[j + tt] = bf16_round(__uint_as_float(r[j + tt]) + (epi.bias ? bb[tt] : 0.f));
+                        }
+                        if (which < 2 && row < sh.M) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                float w[8];
+                                load_bf16x8(nw + c + j, w);
+#pragma unroll
+                                for (int tt = 0; tt < 8; ++tt)
+                                    v[j + tt] = bf16_round(bf16_round(v[j + tt] * inv_rms) * w[tt]);
+                            }
+                            const float* cs = epi.rope_cos + static_cast<size_t>(pos) * (hd / 2) + c / 2;
+                            const float* sn = epi.rope_sin + static_cast<size_t>(pos) * (hd / 2) + c / 2;
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 c4 = *reinterpret_cast<const float4*>(cs + j);
+                                const float4 s4 = *reinterpret_cast<const float4*>(sn + j);
+                                const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+                                const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                                for (int tt = 0; tt < 4; ++tt) {
+                                    const float x0 = v[2 * (j + tt)], x1 = v[2 * (j + tt) + 1];
+                                    v[2 * (j + tt)] = x0 * cc[tt] - x1 * sv[tt];
+                                    v[2 * (j + tt) + 1] = x1 * cc[tt] + x0 * sv[tt];
+                                }
+                            }
+                        }
+                        if (row < sh.M) {
+                            __nv_bfloat16* dst = dst_base +
+                                ((static_cast<size_t>(b) * epi.heads + head) * epi.s_total + pos) * hd + c;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) store_bf16x8(dst + j, &v[j]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_addr + c, r);
+                    tmem_ld_wait();
+                    const int col0 = n_blk * BN + c;
+                    if (row < sh.M && col0 < sh.N) {
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        epilogue_chunk(epi, v, row, col0, sh.N);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------- host
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static void load_encode() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+        g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+}
+
+// 2-D bf16 row-major [rows][cols] with leading dimension ld (elements); box = 64 cols x box_rows.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows) {
+    std::call_once(g_encode_once, load_encode);
+    if (!g_encode) return fail(DRAG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DRAG_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(r));
+    return DRAG_OK;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& sh, const GemmEpi& epi,
+                       cudaStream_t st) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DRAG_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM));
+        attr_set = true;
+    }
+    int sms = device_sm_count();
+    if (sms <= 0) sms = 148;
+    int tiles = sh.num_m * sh.num_n;
+    int grid = tiles < sms ? tiles : sms;
+    gemm_bf16_tcgen05_kernel<BN><<<grid, G_THREADS, Cfg::SMEM, st>>>(tmA, tmB, sh, epi);
+    DRAG_CUDA(cudaGetLastError());
+    return DRAG_OK;
+}
+
+int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
+              const GemmEpi& epi, cudaStream_t st) {
+    DRAG_REQUIRE(A && W, "gemm: null operand");
+    DRAG_REQUIRE(M >= 1 && N >= 1 && K >= 1, "gemm: empty problem");
+    DRAG_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K, lda, ldw must be multiples of 8");
+    DRAG_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+                 "gemm: operands must be 16-byte aligned");
+    DRAG_REQUIRE(N % 32 == 0, "gemm: N must be a multiple of 32");
+    int bn = 256;
+    if (epi.mode == EPI_QKV_ROPE) {
+        DRAG_REQUIRE(N == 3 * epi.heads * 128, "gemm qkv epilogue: N must be 3*heads*128");
+        DRAG_REQUIRE(epi.q_out && epi.k_out && epi.v_out && epi.rope_cos && epi.rope_sin && epi.q_norm_w &&
+                         epi.k_norm_w, "gemm qkv epilogue: null pointer");
+        bn = (N % 256 == 0) ? 256 : 128;
+    } else {
+        DRAG_REQUIRE(epi.out || epi.out_f32, "gemm: null output");
+        if (N % 256 != 0 || N <= 256) bn = (N % 128 == 0 && N > 128) ? 128 : 64;
+        if (N % bn != 0 && N > bn) bn = 64;   // N % 32 == 0: tail columns masked per 32-column chunk
+    }
+    GemmShape sh;
+    sh.M = M; sh.N = N; sh.K = K;
+    sh.num_m = ceil_div(M, G_BM);
+    sh.num_n = ceil_div(N, bn);
+    sh.num_k = ceil_div(K, G_BK);
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap_bf16_2d(&tmA, A, M, K, lda, G_BM);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tmB, W, N, K, ldw, bn);
+    if (rc) return rc;
+    switch (bn) {
+        case 256: return launch_gemm<256>(tmA, tmB, sh, epi, st);
+        case 128: return launch_gemm<128>(tmA, tmB, sh, epi, st);
+        default:  return launch_gemm<64>(tmA, tmB, sh, epi, st);
+    }
+}
+
+}  // namespace drag

@@ -103,7 +103,6 @@ stem_stats_kernel(const float* __restrict__ img, const float* __restrict__ w_fol
         if (cy & 1) {
             __syncthreads();
             // pooled row py = (cy-1)/2 covers conv rows cy-2 (if >= 0), cy-1, cy
-            float s1 = 0.f, s2 = 0.f;
             for (int i = 0; i < 16; ++i) {
                 const int px = pg * 16 + i;
                 float m = 0.f;  // post-ReLU values are >= 0 and every window holds a valid element
@@ -117,11 +116,10 @@ stem_stats_kernel(const float* __restrict__ img, const float* __restrict__ w_fol
                         m = fmaxf(m, rr[rx * ST_C + pc]);
                     }
                 }
-                s1 += m;
-                s2 = fmaf(m, m, s2);
+                const double md = static_cast<double>(m);
+                acc_sum += md;
+                acc_sq = fma(md, md, acc_sq);
             }
-            acc_sum += static_cast<double>(s1);
-            acc_sq += static_cast<double>(s2);
         }
     }
     red_sum[pg][pc] = acc_sum;

@@ -26,9 +26,10 @@ namespace drag {
 
 constexpr int SCAN_CW = 12;                      // consumer warps per CTA
 constexpr int SCAN_THREADS = 32 * (SCAN_CW + 1); // + producer warp
-constexpr int SCAN_WB = 32;                      // pending candidates per (warp, query)
+constexpr int SCAN_WB = 64;                      // capacity of the pending buffer per (warp, query)
+constexpr int SCAN_WB_FLUSH = 32;                // merge into the CTA list once this many are pending
 constexpr int SCAN_STAGE_TARGET = 16384;         // bytes per ring stage
-constexpr int SCAN_MAX_STAGES = 16;
+constexpr int SCAN_MAX_STAGES = 24;
 constexpr int SCAN_SMEM_BUDGET = 227 * 1024;
 constexpr int TOPK_KMAX = 1024;
 
@@ -46,38 +47,29 @@ __device__ __forceinline__ uint64_t make_key(float score, uint32_t ordinal) {
     return (static_cast<uint64_t>(order_f32(score)) << 32) | (0xFFFFFFFFu - ordinal);
 }
 
-// One warp sorts n (power of two) u64 keys in shared memory, descending.
-__device__ __forceinline__ void warp_bitonic_desc(volatile uint64_t* a, int n, int lane) {
-    for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = lane; t < (n >> 1); t += 32) {
-                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                int l = i | j;
-                bool desc = ((i & k) == 0);
-                uint64_t x = a[i], y = a[l];
-                bool swap = desc ? (x < y) : (x > y);
-                if (swap) {
-                    a[i] = y;
-                    a[l] = x;
-                }
-            }
-            __syncwarp();
-        }
-    }
-}
-
 struct ScanSmem {
     float* q;              // [nq][D]
-    uint64_t* lists;       // [nq][lcap]   sorted desc in [0,k)
+    uint64_t* lists;       // [nq][2][k]   ping-pong, current copy sorted descending, zero padded
     uint64_t* thr;         // [nq]         current k-th key (0 = list not full)
     uint64_t* wbuf;        // [CW][nq][WB]
     int* wcnt;             // [CW][nq]
     int* locks;            // [nq]
-    int nq, k, lcap;
+    int* cur;              // [nq]         which ping-pong copy is current
+    int nq, k;
 };
 
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+    uint32_t lo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v), m);
+    uint32_t hi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), m);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// Merge this warp's pending candidates (<= 64, unsorted) into the CTA's sorted top-k list:
+// register bitonic sort of the candidates (element i = r*32 + lane), then every element of both
+// sorted sequences finds its merged rank by binary search in the other one (keys are unique) and
+// is scattered into the other ping-pong copy. ~1 us instead of a full smem sort.
 __device__ __forceinline__ void flush_candidates(const ScanSmem& s, int cw, int q, int lane) {
-    int n = s.wcnt[cw * s.nq + q];
+    const int n = s.wcnt[cw * s.nq + q];
     if (n == 0) return;
     int* lock = &s.locks[q];
     if (lane == 0) {
@@ -86,13 +78,63 @@ __device__ __forceinline__ void flush_candidates(const ScanSmem& s, int cw, int 
     }
     __syncwarp();
     __threadfence_block();
-    volatile uint64_t* list = s.lists + static_cast<size_t>(q) * s.lcap;
-    const uint64_t* wb = s.wbuf + (static_cast<size_t>(cw) * s.nq + q) * SCAN_WB;
-    if (lane < SCAN_WB) list[s.k + lane] = (lane < n) ? wb[lane] : 0ull;
+    uint64_t* wb = s.wbuf + (static_cast<size_t>(cw) * s.nq + q) * SCAN_WB;
+    uint64_t e0 = (lane < n) ? wb[lane] : 0ull;
+    uint64_t e1 = (lane + 32 < n) ? wb[lane + 32] : 0ull;
+#pragma unroll
+    for (int k2 = 2; k2 <= 64; k2 <<= 1) {
+#pragma unroll
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            if (j == 32) {
+                const uint64_t mx = e0 > e1 ? e0 : e1, mn = e0 > e1 ? e1 : e0;   // k2 == 64: descending
+                e0 = mx;
+                e1 = mn;
+            } else {
+                const uint64_t p0 = shfl_xor_u64(e0, j), p1 = shfl_xor_u64(e1, j);
+                const bool lower = (lane & j) == 0;
+                const bool desc0 = (lane & k2) == 0;            // element index lane
+                const bool desc1 = ((lane + 32) & k2) == 0;     // element index lane + 32
+                e0 = ((lower == desc0) == (e0 > p0)) ? e0 : p0;
+                e1 = ((lower == desc1) == (e1 > p1)) ? e1 : p1;
+            }
+        }
+    }
+    wb[lane] = e0;
+    wb[lane + 32] = e1;
     __syncwarp();
-    warp_bitonic_desc(list, s.lcap, lane);
+    const int cur = s.cur[q];
+    const uint64_t* src = s.lists + (static_cast<size_t>(q) * 2 + cur) * s.k;
+    uint64_t* dst = s.lists + (static_cast<size_t>(q) * 2 + (cur ^ 1)) * s.k;
+    // candidates: rank = own index + #list entries greater
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const uint64_t b = r ? e1 : e0;
+        if (b != 0ull) {
+            int lo = 0, hi = s.k;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (src[mid] > b) lo = mid + 1; else hi = mid;
+            }
+            const int rank = r * 32 + lane + lo;
+            if (rank < s.k) dst[rank] = b;
+        }
+    }
+    // list entries: rank = own index + #candidates greater
+    for (int i = lane; i < s.k; i += 32) {
+        const uint64_t a = src[i];
+        if (a == 0ull) break;   // zero padding from here on (sorted descending)
+        int lo = 0, hi = SCAN_WB;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (wb[mid] > a) lo = mid + 1; else hi = mid;
+        }
+        const int rank = i + lo;
+        if (rank < s.k) dst[rank] = a;
+    }
+    __syncwarp();
     if (lane == 0) {
-        reinterpret_cast<volatile uint64_t*>(s.thr)[q] = list[s.k - 1];
+        reinterpret_cast<volatile uint64_t*>(s.thr)[q] = dst[s.k - 1];
+        s.cur[q] = cur ^ 1;
         s.wcnt[cw * s.nq + q] = 0;
     }
     __threadfence_block();
@@ -101,15 +143,22 @@ __device__ __forceinline__ void flush_candidates(const ScanSmem& s, int cw, int 
     __syncwarp();
 }
 
+// Append one accepted candidate to the warp-private pending buffer (no merge here: the caller
+// flushes between ring stages, after the stage has been handed back to the producer).
 __device__ __forceinline__ void push_candidate(const ScanSmem& s, int cw, int q, uint64_t key,
                                                int lane) {
-    int cnt = s.wcnt[cw * s.nq + q];
+    const int cnt = s.wcnt[cw * s.nq + q];
+    __syncwarp();
     if (lane == 0) {
         s.wbuf[(static_cast<size_t>(cw) * s.nq + q) * SCAN_WB + cnt] = key;
         s.wcnt[cw * s.nq + q] = cnt + 1;
     }
     __syncwarp();
-    if (cnt + 1 == SCAN_WB) flush_candidates(s, cw, q, lane);
+}
+
+__device__ __forceinline__ void flush_if_needed(const ScanSmem& s, int cw, int lane) {
+    for (int q = 0; q < s.nq; ++q)
+        if (s.wcnt[cw * s.nq + q] >= SCAN_WB_FLUSH) flush_candidates(s, cw, q, lane);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -192,7 +241,7 @@ struct ScanArgs {
     const float* Q;       // [nq][D] device
     uint64_t* partial;    // [nq][lists_total][k] keys
     int64_t N;
-    int D, nq, k, lcap;
+    int D, nq, k;
     int rps;              // rows per ring stage
     int stages;
     int chunks_per_cta;
@@ -210,15 +259,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ip_scan_topk_kernel(ScanArgs 
     float* ring = reinterpret_cast<float*>(p);
     p += static_cast<size_t>(a.stages) * stage_bytes;
     ScanSmem s;
-    s.nq = a.nq; s.k = a.k; s.lcap = a.lcap;
-    s.lists = reinterpret_cast<uint64_t*>(p); p += static_cast<size_t>(a.nq) * a.lcap * 8;
+    s.nq = a.nq; s.k = a.k;
+    s.lists = reinterpret_cast<uint64_t*>(p); p += static_cast<size_t>(a.nq) * 2 * a.k * 8;
     s.wbuf = reinterpret_cast<uint64_t*>(p);  p += static_cast<size_t>(SCAN_CW) * a.nq * SCAN_WB * 8;
     s.thr = reinterpret_cast<uint64_t*>(p);   p += static_cast<size_t>((a.nq + 1) & ~1) * 8;
     uint64_t* full = reinterpret_cast<uint64_t*>(p);  p += SCAN_MAX_STAGES * 8;
     uint64_t* empty = reinterpret_cast<uint64_t*>(p); p += SCAN_MAX_STAGES * 8;
     s.q = reinterpret_cast<float*>(p);        p += static_cast<size_t>(a.nq) * a.D * 4;
     s.wcnt = reinterpret_cast<int*>(p);       p += static_cast<size_t>(SCAN_CW) * a.nq * 4;
-    s.locks = reinterpret_cast<int*>(p);
+    s.locks = reinterpret_cast<int*>(p);      p += static_cast<size_t>(a.nq) * 4;
+    s.cur = reinterpret_cast<int*>(p);
 
     // chunk range of this CTA
     const int64_t total_chunks = (a.N + a.rps - 1) / a.rps;
@@ -227,12 +277,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ip_scan_topk_kernel(ScanArgs 
     if (c_end > total_chunks) c_end = total_chunks;
     const int nchunks = (c_end > c_begin) ? static_cast<int>(c_end - c_begin) : 0;
 
-    for (int i = threadIdx.x; i < a.nq * a.lcap; i += blockDim.x) s.lists[i] = 0ull;
+    for (int i = threadIdx.x; i < a.nq * 2 * a.k; i += blockDim.x) s.lists[i] = 0ull;
     for (int i = threadIdx.x; i < a.nq * a.D; i += blockDim.x) s.q[i] = a.Q[i];
     for (int i = threadIdx.x; i < SCAN_CW * a.nq; i += blockDim.x) s.wcnt[i] = 0;
     if (threadIdx.x < a.nq) {
         s.thr[threadIdx.x] = 0ull;
         s.locks[threadIdx.x] = 0;
+        s.cur[threadIdx.x] = 0;
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < a.stages; ++i) {
@@ -260,9 +311,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ip_scan_topk_kernel(ScanArgs 
         return;
     }
 
+    // Stage st is owned by consumer warp st % CW for the whole kernel: the owner observes every
+    // phase of full[st] in order, so the parity wait can never alias a phase it skipped.
     const int cw = warp - 1;
-    for (int c = cw; c < nchunks; c += SCAN_CW) {
+    for (int c = 0; c < nchunks; ++c) {
         const int st = c % a.stages, it = c / a.stages;
+        if (st % SCAN_CW != cw) continue;
         mbar_wait(&full[st], it & 1);
         const int64_t row0 = (c_begin + c) * a.rps;
         int64_t rows = a.N - row0;
@@ -272,7 +326,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ip_scan_topk_kernel(ScanArgs 
         consume_rows<NV>(s, stage, static_cast<int>(rows), a.D,
                          a.ord_base + static_cast<uint32_t>(row0), cw, lane);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
+        if (lane == 0) mbar_arrive(&empty[st]);   // hand the stage back before any list merge
+        flush_if_needed(s, cw, lane);
     }
     for (int q = 0; q < a.nq; ++q) flush_candidates(s, cw, q, lane);
     asm volatile("bar.sync 1, %0;" ::"r"(SCAN_CW * 32) : "memory");
@@ -280,7 +335,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ip_scan_topk_kernel(ScanArgs 
     for (int i = ct; i < a.nq * a.k; i += SCAN_CW * 32) {
         const int q = i / a.k, j = i - q * a.k;
         a.partial[(static_cast<size_t>(q) * a.lists_total + a.list_off + blockIdx.x) * a.k + j] =
-            s.lists[static_cast<size_t>(q) * a.lcap + j];
+            s.lists[(static_cast<size_t>(q) * 2 + s.cur[q]) * a.k + j];
     }
 }
 
@@ -290,19 +345,21 @@ __global__ void __launch_bounds__(SCAN_CW * 32, 1) ip_scan_topk_direct_kernel(Sc
     const int cw = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* p = smem;
     ScanSmem s;
-    s.nq = a.nq; s.k = a.k; s.lcap = a.lcap;
-    s.lists = reinterpret_cast<uint64_t*>(p); p += static_cast<size_t>(a.nq) * a.lcap * 8;
+    s.nq = a.nq; s.k = a.k;
+    s.lists = reinterpret_cast<uint64_t*>(p); p += static_cast<size_t>(a.nq) * 2 * a.k * 8;
     s.wbuf = reinterpret_cast<uint64_t*>(p);  p += static_cast<size_t>(SCAN_CW) * a.nq * SCAN_WB * 8;
     s.thr = reinterpret_cast<uint64_t*>(p);   p += static_cast<size_t>((a.nq + 1) & ~1) * 8;
     s.q = reinterpret_cast<float*>(p);        p += static_cast<size_t>(a.nq) * a.D * 4;
     s.wcnt = reinterpret_cast<int*>(p);       p += static_cast<size_t>(SCAN_CW) * a.nq * 4;
-    s.locks = reinterpret_cast<int*>(p);
-    for (int i = threadIdx.x; i < a.nq * a.lcap; i += blockDim.x) s.lists[i] = 0ull;
+    s.locks = reinterpret_cast<int*>(p);      p += static_cast<size_t>(a.nq) * 4;
+    s.cur = reinterpret_cast<int*>(p);
+    for (int i = threadIdx.x; i < a.nq * 2 * a.k; i += blockDim.x) s.lists[i] = 0ull;
     for (int i = threadIdx.x; i < a.nq * a.D; i += blockDim.x) s.q[i] = a.Q[i];
     for (int i = threadIdx.x; i < SCAN_CW * a.nq; i += blockDim.x) s.wcnt[i] = 0;
     if (threadIdx.x < a.nq) {
         s.thr[threadIdx.x] = 0ull;
         s.locks[threadIdx.x] = 0;
+        s.cur[threadIdx.x] = 0;
     }
     __syncthreads();
     const int64_t rows_per_cta = static_cast<int64_t>(a.chunks_per_cta) * a.rps;
@@ -320,13 +377,14 @@ __global__ void __launch_bounds__(SCAN_CW * 32, 1) ip_scan_topk_direct_kernel(Sc
             uint64_t key = make_key(acc, a.ord_base + static_cast<uint32_t>(r));
             if (key > thr[q]) push_candidate(s, cw, q, key, lane);
         }
+        flush_if_needed(s, cw, lane);
     }
     for (int q = 0; q < a.nq; ++q) flush_candidates(s, cw, q, lane);
     __syncthreads();
     for (int i = threadIdx.x; i < a.nq * a.k; i += blockDim.x) {
         const int q = i / a.k, j = i - q * a.k;
         a.partial[(static_cast<size_t>(q) * a.lists_total + a.list_off + blockIdx.x) * a.k + j] =
-            s.lists[static_cast<size_t>(q) * a.lcap + j];
+            s.lists[(static_cast<size_t>(q) * 2 + s.cur[q]) * a.k + j];
     }
 }
 
@@ -346,6 +404,8 @@ constexpr int MERGE_THREADS = 1024;
 
 __global__ void __launch_bounds__(MERGE_THREADS, 1) topk_merge_keys_kernel(MergeArgs a) {
     __shared__ uint32_t hist[256];
+    __shared__ uint32_t suf_local[256];
+    __shared__ uint32_t wtot[8];
     __shared__ uint64_t sel[TOPK_KMAX];
     __shared__ uint64_t s_prefix, s_mask;
     __shared__ int s_remaining, s_count;
@@ -365,23 +425,38 @@ __global__ void __launch_bounds__(MERGE_THREADS, 1) topk_merge_keys_kernel(Merge
         if (tid < 256) hist[tid] = 0;
         __syncthreads();
         const uint64_t prefix = s_prefix, mask = s_mask;
+        const uint32_t rem = static_cast<uint32_t>(s_remaining);
         const int shift = pass * 8;
         for (int i = tid; i < T; i += MERGE_THREADS) {
             uint64_t key = keys[i];
             if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1u);
         }
         __syncthreads();
-        if (tid == 0) {
-            int rem = s_remaining;
-            int b = 255;
-            for (; b > 0; --b) {
-                int c = static_cast<int>(hist[b]);
-                if (c >= rem) break;
-                rem -= c;
+        // suffix sums over the 256 digit buckets: warp shuffles inside each of the 8 warps, then
+        // the totals of the higher warps; the selected bucket is the one whose suffix sum first
+        // reaches the number of keys still wanted.
+        if (tid < 256) {
+            const uint32_t h = hist[tid];
+            uint32_t v = h;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t o = __shfl_down_sync(0xffffffffu, v, off);
+                if ((tid & 31) + off < 32) v += o;
             }
-            s_remaining = rem;
-            s_prefix = prefix | (static_cast<uint64_t>(b) << shift);
-            s_mask = mask | (0xFFull << shift);
+            if ((tid & 31) == 0) wtot[tid >> 5] = v;
+            suf_local[tid] = v;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            uint32_t higher = 0;
+            for (int w = (tid >> 5) + 1; w < 8; ++w) higher += wtot[w];
+            const uint32_t incl = suf_local[tid] + higher;      // sum over buckets >= tid
+            const uint32_t excl = incl - hist[tid];             // sum over buckets >  tid
+            if ((incl >= rem && excl < rem) || (tid == 0 && incl < rem)) {
+                s_remaining = static_cast<int>(rem - (incl >= rem ? excl : 0));
+                s_prefix = prefix | (static_cast<uint64_t>(tid) << shift);
+                s_mask = mask | (0xFFull << shift);
+            }
         }
         __syncthreads();
     }
@@ -494,25 +569,24 @@ static int next_pow2(int v) {
 struct ScanPlan {
     bool bulk;     // false: direct kernel
     int nv;        // template selector (0 generic)
-    int rps, stages, lcap, nqb;
+    int rps, stages, nqb;
     size_t smem;
 };
 
-static size_t scan_fixed_smem(int nqb, int D, int lcap) {
-    return static_cast<size_t>(nqb) * lcap * 8 + static_cast<size_t>(SCAN_CW) * nqb * SCAN_WB * 8 +
+static size_t scan_fixed_smem(int nqb, int D, int k) {
+    return static_cast<size_t>(nqb) * 2 * k * 8 + static_cast<size_t>(nqb) * 4 + static_cast<size_t>(SCAN_CW) * nqb * SCAN_WB * 8 +
            static_cast<size_t>(nqb) * 8 + 2 * SCAN_MAX_STAGES * 8 + static_cast<size_t>(nqb) * D * 4 +
            static_cast<size_t>(SCAN_CW) * nqb * 4 + static_cast<size_t>(nqb) * 4 + 256;
 }
 
 static int make_plan(int D, int nq, int k, bool aligned, ScanPlan* plan) {
     plan->rps = 8; plan->stages = 0; plan->smem = 0;
-    plan->lcap = next_pow2(k + SCAN_WB);
     plan->bulk = aligned && (D % 4 == 0) && (static_cast<size_t>(D) * 4 <= 65536);
     plan->nv = (plan->bulk && D % 128 == 0 && D / 128 >= 1 && D / 128 <= 8) ? D / 128 : 0;
     int nqb = nq < 8 ? nq : 8;
-    while (nqb > 1 && scan_fixed_smem(nqb, D, plan->lcap) > SCAN_SMEM_BUDGET / 2) nqb >>= 1;
+    while (nqb > 1 && scan_fixed_smem(nqb, D, k) > SCAN_SMEM_BUDGET / 2) nqb >>= 1;
     plan->nqb = nqb;
-    size_t fixed = scan_fixed_smem(nqb, D, plan->lcap);
+    size_t fixed = scan_fixed_smem(nqb, D, k);
     if (fixed > static_cast<size_t>(SCAN_SMEM_BUDGET))
         return fail(DRAG_ERR_UNSUPPORTED, "index search: k/d too large for shared memory");
     if (plan->bulk) {
@@ -524,6 +598,7 @@ static int make_plan(int D, int nq, int k, bool aligned, ScanPlan* plan) {
         size_t stage_bytes = static_cast<size_t>(rps) * D * 4;
         int stages = static_cast<int>((SCAN_SMEM_BUDGET - fixed) / stage_bytes);
         if (stages > SCAN_MAX_STAGES) stages = SCAN_MAX_STAGES;
+        if (stages > SCAN_CW) stages = (stages / SCAN_CW) * SCAN_CW;  // balanced stage ownership
         if (stages < 2) {
             plan->bulk = false;
         } else {
@@ -626,7 +701,7 @@ int index_search_device(Index* ix, const float* q, int nq, int k, float* D, int6
                     a.X = sg.X;
                     a.Q = q + static_cast<size_t>(q0) * ix->d;
                     a.partial = ix->partial + static_cast<size_t>(q0) * lists_total * k;
-                    a.N = sg.N; a.D = ix->d; a.nq = nqb; a.k = k; a.lcap = plan.lcap;
+                    a.N = sg.N; a.D = ix->d; a.nq = nqb; a.k = k;
                     a.rps = plan.rps; a.stages = plan.stages; a.chunks_per_cta = cpcs[i];
                     a.lists_total = lists_total; a.list_off = list_off; a.ord_base = ord;
                     // smem depends on the batch width only through `fixed`; keep the plan's size

@@ -73,6 +73,24 @@ int drag_topk_merge_device(const float* scores, const int64_t* ids, int nq, int 
 int drag_stem_stats(const float* img_dev, int B, int H, int W, const float* w_fold_dev, const float* b_fold_dev,
                     float eps, float* out_dev, void* stream);
 
+/* ---- bf16 GEMM core (tcgen05 / TMEM / TMA) ------------------------------------------------------
+ * out[M][N] = epilogue(A[M][K] * W[N][K]^T + bias): the nn.Linear calls inside clip.encode_image
+ * (retrieval/clip100_resnet_style_all_shots.py:171) and inside the diffusers Flux transformer that
+ * pipe(...) runs (batch_generate_flux_kshot.py:467-474, outpainting_updown_sampling_redux.py:1246-1257).
+ * A, W, bias, out, resid, gate are bf16 device pointers; fp32 accumulation.
+ * epi_mode: 0 bias, 1 gelu_tanh, 2 quick_gelu, 3 silu, 4 out = resid + gate[row/rows_per_batch][n] * (..)
+ * (gate NULL = plain residual add), 6 fp32 output (out is float*). K, lda, ldw multiples of 8; N of 32. */
+int drag_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epi_mode,
+                   const void* bias, void* out, int ldo, const void* resid, int ldr, const void* gate,
+                   int gate_ld, int rows_per_batch, void* stream);
+/* QKV projection fused with per-head RMSNorm(q), RMSNorm(k) and rotary embedding, scattered into the
+ * attention layout: q/k/v_out bf16 [B][heads][s_total][128] at token tok_offset + (row % rows_per_batch).
+ * W is [3*heads*128][K] (q rows, then k, then v); rope_cos/sin fp32 [s_total][64]. */
+int drag_gemm_qkv_rope(const void* A, int lda, const void* W, int ldw, int M, int K, int heads, const void* bias,
+                       void* q_out, void* k_out, void* v_out, const void* q_norm_w, const void* k_norm_w,
+                       const float* rope_cos, const float* rope_sin, int s_total, int tok_offset,
+                       int rows_per_batch, float rms_eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,11 +12,13 @@ import torch
 import torch.nn.functional as F
 
 
-def stem_forward(img: torch.Tensor, state: dict) -> torch.Tensor:
-    """[B,3,H,W] fp32 -> [B,64,H/4,W/4] (conv1, eval bn1, relu, maxpool)."""
-    x = F.conv2d(img.float(), state["conv1.weight"].float(), None, stride=2, padding=3)
-    x = F.batch_norm(x, state["bn1.running_mean"].float(), state["bn1.running_var"].float(),
-                     state["bn1.weight"].float(), state["bn1.bias"].float(), training=False, eps=1e-5)
+def stem_forward(img: torch.Tensor, state: dict, dtype=torch.float32) -> torch.Tensor:
+    """[B,3,H,W] -> [B,64,H/4,W/4] (conv1, eval bn1, relu, maxpool). dtype=float64 gives the
+    high-precision comparator used for ill-conditioned (near-constant) inputs."""
+    st = {k: v.to(dtype) for k, v in state.items()}
+    x = F.conv2d(img.to(dtype), st["conv1.weight"], None, stride=2, padding=3)
+    x = F.batch_norm(x, st["bn1.running_mean"], st["bn1.running_var"], st["bn1.weight"], st["bn1.bias"],
+                     training=False, eps=1e-5)
     x = F.relu(x)
     return F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
 
@@ -29,8 +31,8 @@ def calc_mean_std(feat: torch.Tensor, eps: float = 1e-5):
     return mean, std
 
 
-def style_features(img: torch.Tensor, state: dict) -> torch.Tensor:
+def style_features(img: torch.Tensor, state: dict, dtype=torch.float32) -> torch.Tensor:
     """[B,3,256,256] in [0,1] -> [B,128] = cat(mean64, std64)."""
     with torch.no_grad():
-        mean, std = calc_mean_std(stem_forward(img, state))
-        return torch.cat([mean.flatten(1), std.flatten(1)], dim=1)
+        mean, std = calc_mean_std(stem_forward(img, state, dtype))
+        return torch.cat([mean.flatten(1), std.flatten(1)], dim=1).float()

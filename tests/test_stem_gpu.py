@@ -50,7 +50,10 @@ def test_matches_oracle(enc, b, kind):
     else:
         x = (torch.rand(b, 3, 256, 256, generator=g) > 0.97).float()
     got = enc.style_features(x.cuda()).cpu()
-    want = S.style_features(x, enc.state)
+    # near-constant maps make sqrt(var + eps) ill-conditioned in fp32 (the reference's own torch
+    # fp32 var has the same problem), so those cases are judged against the float64 oracle
+    dtype = torch.float32 if kind == "rand" else torch.float64
+    want = S.style_features(x, enc.state, dtype)
     torch.testing.assert_close(got, want, rtol=RTOL, atol=2e-6)
 
 
