@@ -128,6 +128,15 @@ def scan_algorithmic_bytes(n, d, nq, k):
     return n * d * 4 + nq * d * 4 + nq * k * 12
 
 
+def scan_traffic_from_profile():
+    """dram read+write bytes per launch of the scan kernel from the committed ncu --set full capture."""
+    p = REPO / "profiles" / "r01_scan_traffic.json"
+    try:
+        return json.loads(p.read_text())["traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def make_corpus_device(n, d, seed, device):
     import torch
     g = torch.Generator(device=device).manual_seed(seed)
@@ -223,7 +232,7 @@ def run_scan(args):
             "roofline": {"bound": "hbm", "achieved": round(alg / (kern_avg * 1e-3) / 1e9, 1),
                          "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": round(alg / (kern_avg * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
-                         "traffic": None, "kernel": "ip_scan_topk_kernel<4>", "kernel_ms": round(kern_avg, 4),
+                         "traffic": scan_traffic_from_profile(), "kernel": "ip_scan_topk_kernel<4>", "kernel_ms": round(kern_avg, 4),
                          "peak_source": peaks["source"]},
         }
         if world == 1:

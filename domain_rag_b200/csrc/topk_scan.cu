@@ -68,15 +68,25 @@ __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
 // register bitonic sort of the candidates (element i = r*32 + lane), then every element of both
 // sorted sequences finds its merged rank by binary search in the other one (keys are unique) and
 // is scattered into the other ping-pong copy. ~1 us instead of a full smem sort.
-__device__ __forceinline__ void flush_candidates(const ScanSmem& s, int cw, int q, int lane) {
+// Lock protocol: test-and-test-and-set with back-off. Waiters poll with a plain shared load and
+// sleep between polls, so they do not saturate the shared-memory atomic unit the lock holder's own
+// loads go through (a tight atomicCAS spin by 11 warps slowed every merge ~10x).
+__device__ __forceinline__ bool try_lock(int* lock, int lane) {
+    int got = 0;
+    if (lane == 0) got = (*reinterpret_cast<volatile int*>(lock) == 0 && atomicCAS(lock, 0, 1) == 0) ? 1 : 0;
+    return __shfl_sync(0xffffffffu, got, 0) != 0;
+}
+
+// blocking = false: give up if another warp holds the list (caller retries after its next stage).
+__device__ __forceinline__ bool flush_candidates(const ScanSmem& s, int cw, int q, int lane,
+                                                 bool blocking = true) {
     const int n = s.wcnt[cw * s.nq + q];
-    if (n == 0) return;
+    if (n == 0) return true;
     int* lock = &s.locks[q];
-    if (lane == 0) {
-        while (atomicCAS(lock, 0, 1) != 0) {
-        }
+    while (!try_lock(lock, lane)) {
+        if (!blocking) return false;
+        __nanosleep(200);
     }
-    __syncwarp();
     __threadfence_block();
     uint64_t* wb = s.wbuf + (static_cast<size_t>(cw) * s.nq + q) * SCAN_WB;
     uint64_t e0 = (lane < n) ? wb[lane] : 0ull;
@@ -141,6 +151,7 @@ __device__ __forceinline__ void flush_candidates(const ScanSmem& s, int cw, int 
     __syncwarp();
     if (lane == 0) atomicExch(lock, 0);
     __syncwarp();
+    return true;
 }
 
 // Append one accepted candidate to the warp-private pending buffer (no merge here: the caller
@@ -156,9 +167,13 @@ __device__ __forceinline__ void push_candidate(const ScanSmem& s, int cw, int q,
     __syncwarp();
 }
 
-__device__ __forceinline__ void flush_if_needed(const ScanSmem& s, int cw, int lane) {
-    for (int q = 0; q < s.nq; ++q)
-        if (s.wcnt[cw * s.nq + q] >= SCAN_WB_FLUSH) flush_candidates(s, cw, q, lane);
+// Called between ring stages. `next_rows` bounds how many candidates the next stage can add per
+// query: the merge is only forced (blocking) when the pending buffer could overflow.
+__device__ __forceinline__ void flush_if_needed(const ScanSmem& s, int cw, int lane, int next_rows) {
+    for (int q = 0; q < s.nq; ++q) {
+        const int cnt = s.wcnt[cw * s.nq + q];
+        if (cnt >= SCAN_WB_FLUSH) flush_candidates(s, cw, q, lane, cnt + next_rows > SCAN_WB);
+    }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -314,20 +329,22 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ip_scan_topk_kernel(ScanArgs 
     // Stage st is owned by consumer warp st % CW for the whole kernel: the owner observes every
     // phase of full[st] in order, so the parity wait can never alias a phase it skipped.
     const int cw = warp - 1;
-    for (int c = 0; c < nchunks; ++c) {
-        const int st = c % a.stages, it = c / a.stages;
-        if (st % SCAN_CW != cw) continue;
-        mbar_wait(&full[st], it & 1);
-        const int64_t row0 = (c_begin + c) * a.rps;
-        int64_t rows = a.N - row0;
-        if (rows > a.rps) rows = a.rps;
-        const float* stage = reinterpret_cast<const float*>(reinterpret_cast<uint8_t*>(ring) +
-                                                            static_cast<size_t>(st) * stage_bytes);
-        consume_rows<NV>(s, stage, static_cast<int>(rows), a.D,
-                         a.ord_base + static_cast<uint32_t>(row0), cw, lane);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);   // hand the stage back before any list merge
-        flush_if_needed(s, cw, lane);
+    for (int base = 0, it = 0; base < nchunks; base += a.stages, ++it) {
+        for (int st = cw; st < a.stages; st += SCAN_CW) {
+            const int c = base + st;
+            if (c >= nchunks) break;
+            mbar_wait(&full[st], it & 1);
+            const int64_t row0 = (c_begin + c) * a.rps;
+            int64_t rows = a.N - row0;
+            if (rows > a.rps) rows = a.rps;
+            const float* stage = reinterpret_cast<const float*>(reinterpret_cast<uint8_t*>(ring) +
+                                                                static_cast<size_t>(st) * stage_bytes);
+            consume_rows<NV>(s, stage, static_cast<int>(rows), a.D,
+                             a.ord_base + static_cast<uint32_t>(row0), cw, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);   // hand the stage back before any list merge
+            flush_if_needed(s, cw, lane, a.rps);
+        }
     }
     for (int q = 0; q < a.nq; ++q) flush_candidates(s, cw, q, lane);
     asm volatile("bar.sync 1, %0;" ::"r"(SCAN_CW * 32) : "memory");
@@ -377,7 +394,7 @@ __global__ void __launch_bounds__(SCAN_CW * 32, 1) ip_scan_topk_direct_kernel(Sc
             uint64_t key = make_key(acc, a.ord_base + static_cast<uint32_t>(r));
             if (key > thr[q]) push_candidate(s, cw, q, key, lane);
         }
-        flush_if_needed(s, cw, lane);
+        flush_if_needed(s, cw, lane, 1);
     }
     for (int q = 0; q < a.nq; ++q) flush_candidates(s, cw, q, lane);
     __syncthreads();
