@@ -42,6 +42,25 @@ SIGNATURES = {
     "drag_gemm_qkv_rope": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "drag_attention_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "drag_layernorm_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "drag_timestep_embed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "drag_euler_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
+                                  C.c_void_p]),
+    "drag_redux_blend": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "drag_l2_normalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "drag_flux_create": (C.c_int, [C.c_void_p, c_void_pp]),
+    "drag_flux_destroy": (C.c_int, [C.c_void_p]),
+    "drag_flux_set_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "drag_flux_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                    C.c_int, C.c_int, C.c_void_p]),
+    "drag_prof_enable": (C.c_int, [C.c_int]),
+    "drag_prof_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "drag_debug_set": (C.c_int, [C.c_int, C.c_int]),
     "drag_stem_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_float, C.c_void_p, C.c_void_p]),
 }

@@ -17,12 +17,11 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "flux_ops.cuh"
+#include "prof.cuh"
 #include "ptx.cuh"
 
 namespace drag {
-
-int make_tmap_bf16_3d(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
-                      uint64_t stride2_elems, uint32_t box0, uint32_t box1);
 
 constexpr int AT_THREADS = 192;
 constexpr int AT_TILE = 128;
@@ -38,9 +37,12 @@ constexpr int AT_SMEM = AT_BAR_OFF + 256 + 1024;
 constexpr float AT_RESCALE_THRESHOLD = 8.0f;           // log2 domain
 
 struct AttnArgs {
-    __nv_bfloat16* out;    // [B][S][H*128]
+    __nv_bfloat16* out0;   // tokens [0, split): row b*split + s, leading dim ld0
+    __nv_bfloat16* out1;   // tokens [split, S): row b*(S-split) + s-split, leading dim ld1
+    int ld0, ld1, split;
     int S, H;
     float scale_log2;      // log2(e) / sqrt(128)
+    uint32_t v_lbo, v_sbo; // MN-major V descriptor strides (bytes)
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
@@ -146,7 +148,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll
                 for (int nh = 0; nh < 2; ++nh) {
                     // V half nh: [128 kv rows][64 hd], 128-byte rows; 16 kv rows per k-step = 2048 B
-                    const uint64_t vdsc = umma_desc_mn_sw128(v_addr + nh * AT_HALF_BYTES + ks * 2048, 0, 1024);
+                    const uint64_t vdsc = umma_desc_mn_sw128(v_addr + nh * AT_HALF_BYTES + ks * 2048, a.v_lbo, a.v_sbo);
                     tc_mma_f16(tmem_base + 256 + nh * 64, pd, vdsc, idesc_pv, (j | ks) != 0);
                 }
             }
@@ -239,7 +241,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const float inv = 1.f / l;
         const int srow = q0 + r;
         const int b = bh / a.H, h = bh - b * a.H;
-        __nv_bfloat16* orow = a.out + (static_cast<size_t>(b) * a.S + srow) * (a.H * AT_HD) + h * AT_HD;
+        __nv_bfloat16* orow = (srow < a.split)
+            ? a.out0 + (static_cast<size_t>(b) * a.split + srow) * a.ld0 + h * AT_HD
+            : a.out1 + (static_cast<size_t>(b) * (a.S - a.split) + (srow - a.split)) * a.ld1 + h * AT_HD;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             uint32_t v[32];
@@ -270,11 +274,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     }
 }
 
-// q, k, v bf16 [B][H][S][128] contiguous; out bf16 [B][S][H*128].
-int attention_bf16(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out,
-                   int B, int H, int S, cudaStream_t st) {
-    DRAG_REQUIRE(q && k && v && out, "attention: null pointer");
-    DRAG_REQUIRE(B >= 1 && H >= 1 && S >= 1, "attention: empty problem");
+// Debug knob (drag_debug_set): MN-major V descriptor strides.
+uint32_t g_attn_v_lbo = 0, g_attn_v_sbo = 1024;
+
+int attention_bf16(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int B, int H, int S,
+                   int split, __nv_bfloat16* out0, int ld0, __nv_bfloat16* out1, int ld1, cudaStream_t st) {
+    DRAG_REQUIRE(q && k && v, "attention: null pointer");
+    DRAG_REQUIRE(B >= 1 && H >= 1 && S >= 1 && split >= 0 && split <= S, "attention: bad sizes");
+    DRAG_REQUIRE((split == 0 || out0) && (split == S || out1), "attention: null output");
+    DRAG_REQUIRE(ld0 % 8 == 0 && ld1 % 8 == 0, "attention: output leading dims must be multiples of 8");
     CUtensorMap tq, tk, tv;
     const uint64_t bh = static_cast<uint64_t>(B) * H;
     int rc = make_tmap_bf16_3d(&tq, q, AT_HD, S, bh, AT_HD, static_cast<uint64_t>(S) * AT_HD, 64, AT_TILE);
@@ -289,12 +297,15 @@ int attention_bf16(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bf
         attr_set = true;
     }
     AttnArgs a;
-    a.out = out;
+    a.out0 = out0; a.out1 = out1; a.ld0 = ld0; a.ld1 = ld1; a.split = split;
     a.S = S;
     a.H = H;
     a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(AT_HD));
+    a.v_lbo = g_attn_v_lbo; a.v_sbo = g_attn_v_sbo;
     dim3 grid((S + AT_TILE - 1) / AT_TILE, static_cast<unsigned>(bh));
+    const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * H * static_cast<double>(S) * S * AT_HD, st);
     attention_tcgen05_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, a);
+    prof_end(slot, st);
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }

@@ -6,6 +6,8 @@
 
 #include "../../include/domainrag_b200.h"
 #include "common.cuh"
+#include "flux_engine.cuh"
+#include "flux_ops.cuh"
 #include "gemm.cuh"
 #include "index.cuh"
 
@@ -23,6 +25,10 @@ int device_sm_count() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
     return n;
 }
+
+extern uint32_t g_attn_v_lbo, g_attn_v_sbo;
+int prof_enable(int on);
+int prof_collect(double* ms, double* work, int* count, int n_classes);
 
 }  // namespace drag
 
@@ -265,6 +271,77 @@ int drag_gemm_qkv_rope(const void* A, int lda, const void* W, int ldw, int M, in
     e.rms_eps = rms_eps;
     return gemm_bf16(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(W), ldw, M,
                      3 * heads * 128, K, e, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------ row kernels
+#define BF(p) static_cast<const __nv_bfloat16*>(p)
+#define BFM(p) static_cast<__nv_bfloat16*>(p)
+#define ST(p) reinterpret_cast<cudaStream_t>(p)
+
+int drag_attention_bf16(const void* q, const void* k, const void* v, int B, int H, int S, int split, void* out0,
+                        int ld0, void* out1, int ld1, void* stream) {
+    return attention_bf16(BF(q), BF(k), BF(v), B, H, S, split, BFM(out0), ld0, BFM(out1), ld1, ST(stream));
+}
+int drag_layernorm_bf16(const void* x, int ldx, void* out, int ldo, int M, int d, const void* mul, int mul_ld,
+                        const void* add, int add_ld, int adaln, int rows_per_batch, float eps, void* stream) {
+    return layernorm_bf16(BF(x), ldx, BFM(out), ldo, M, d, BF(mul), mul_ld, BF(add), add_ld, adaln, rows_per_batch, eps,
+                          ST(stream));
+}
+int drag_timestep_embed(const float* t_dev, void* out, int B, void* stream) {
+    return timestep_embed(t_dev, BFM(out), B, ST(stream));
+}
+int drag_euler_step(void* x, int ldx, const void* v, int ldv, int rows, int cols, float dsigma, void* stream) {
+    return euler_step(BFM(x), ldx, BF(v), ldv, rows, cols, dsigma, ST(stream));
+}
+int drag_redux_blend(const void* txt, const void* img, const void* pooled, const float* s_embed_dev,
+                     const float* s_pool_dev, void* out_embeds, void* out_pooled, int B, int n_txt, int n_img, int dim,
+                     int pooled_dim, void* stream) {
+    return redux_blend(BF(txt), BF(img), BF(pooled), s_embed_dev, s_pool_dev, BFM(out_embeds), BFM(out_pooled), B,
+                       n_txt, n_img, dim, pooled_dim, ST(stream));
+}
+int drag_l2_normalize(const float* x, float* out, int rows, int d, void* stream) {
+    return l2_normalize(x, out, rows, d, ST(stream));
+}
+
+// ------------------------------------------------------------------------------------ flux engine
+int drag_flux_create(const drag_flux_config* cfg, drag_flux_t** out) {
+    DRAG_REQUIRE(cfg && out, "drag_flux_create: null pointer");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(DRAG_ERR_NO_DEVICE, "drag_flux_create: no CUDA device (this library has no CPU path)");
+    FluxCfg c;
+    c.in_channels = cfg->in_channels; c.d = cfg->d; c.heads = cfg->heads; c.n_double = cfg->n_double;
+    c.n_single = cfg->n_single; c.txt_dim = cfg->txt_dim; c.pooled_dim = cfg->pooled_dim;
+    c.out_channels = cfg->out_channels; c.guidance = cfg->guidance; c.max_batch = cfg->max_batch;
+    c.max_img_tokens = cfg->max_img_tokens; c.txt_tokens = cfg->txt_tokens;
+    FluxEngine* e = nullptr;
+    int rc = flux_create(c, &e);
+    if (rc) return rc;
+    *out = reinterpret_cast<drag_flux_t*>(e);
+    return DRAG_OK;
+}
+int drag_flux_destroy(drag_flux_t* h) { return flux_destroy(reinterpret_cast<FluxEngine*>(h)); }
+int drag_flux_set_weights(drag_flux_t* h, const void* const* ptrs, int n) {
+    return flux_set_weights(reinterpret_cast<FluxEngine*>(h), ptrs, n);
+}
+int drag_flux_forward(drag_flux_t* h, const void* x, int ldx, const void* ctx, const void* pooled, const float* t_dev,
+                      const float* g_dev, const float* rope_cos, const float* rope_sin, int B, int S_img, void* v_out,
+                      int ldv, int n_double_run, int n_single_run, void* stream) {
+    return flux_forward(reinterpret_cast<FluxEngine*>(h), BF(x), ldx, BF(ctx), BF(pooled), t_dev, g_dev, rope_cos,
+                        rope_sin, B, S_img, BFM(v_out), ldv, n_double_run, n_single_run, ST(stream));
+}
+
+int drag_prof_enable(int on) { return prof_enable(on); }
+int drag_prof_collect(double* ms, double* work, int* count, int n_classes) {
+    DRAG_REQUIRE(ms && work && count && n_classes >= 1, "drag_prof_collect: bad arguments");
+    return prof_collect(ms, work, count, n_classes);
+}
+
+int drag_debug_set(int key, int value) {
+    if (key == 1) g_attn_v_lbo = static_cast<uint32_t>(value);
+    else if (key == 2) g_attn_v_sbo = static_cast<uint32_t>(value);
+    else return fail(DRAG_ERR_INVALID, "drag_debug_set: unknown key");
+    return DRAG_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,216 @@
+// HBM-bound elementwise / row kernels around the GEMM and attention cores of the ViT and Flux paths:
+// LayerNorm (+AdaLN modulate or affine), sinusoidal timestep embedding, SiLU of the summed
+// conditioning vector, flow-match Euler update, Redux prompt blend, L2 normalisation.
+// All bf16 storage, fp32 arithmetic; 16-byte vector accesses; one warp per row for the row kernels.
+#include "common.cuh"
+#include "flux_ops.cuh"
+
+namespace drag {
+
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* v) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float* v) {
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = *reinterpret_cast<uint4*>(h);
+}
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// out[row] = LN(x[row]) * mul + add.
+//   mul_add_one = 1: mul = 1 + mulp[b*mul_ld + c]   (AdaLN: scale)     add = addp[b*add_ld + c] (shift)
+//   mul_add_one = 0: mul = mulp[c] (gamma)                              add = addp[c] (beta); either may be null
+// b = row / rows_per_batch. Two exact passes for mean / variance (second pass hits L1/L2).
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                                        __nv_bfloat16* __restrict__ out, int ldo, int M, int d,
+                                                        const __nv_bfloat16* __restrict__ mulp, int mul_ld,
+                                                        const __nv_bfloat16* __restrict__ addp, int add_ld,
+                                                        int mul_add_one, int rows_per_batch, float eps) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const __nv_bfloat16* xr = x + static_cast<size_t>(row) * ldx;
+    float s = 0.f;
+    for (int c = lane * 8; c < d; c += 256) {
+        float v[8];
+        ld8(xr + c, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[i];
+    }
+    const float mean = wsum(s) / d;
+    float ss = 0.f;
+    for (int c = lane * 8; c < d; c += 256) {
+        float v[8];
+        ld8(xr + c, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float t = v[i] - mean;
+            ss = fmaf(t, t, ss);
+        }
+    }
+    const float rstd = rsqrtf(wsum(ss) / d + eps);
+    const int b = row / rows_per_batch;
+    const __nv_bfloat16* mr = mulp ? mulp + static_cast<size_t>(mul_add_one ? b : 0) * mul_ld : nullptr;
+    const __nv_bfloat16* ar = addp ? addp + static_cast<size_t>(mul_add_one ? b : 0) * add_ld : nullptr;
+    __nv_bfloat16* orow = out + static_cast<size_t>(row) * ldo;
+    for (int c = lane * 8; c < d; c += 256) {
+        float v[8], mu[8], ad[8];
+        ld8(xr + c, v);
+        if (mr) ld8(mr + c, mu);
+        if (ar) ld8(ar + c, ad);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float y = (v[i] - mean) * rstd;
+            if (mr) y *= (mul_add_one ? 1.f + mu[i] : mu[i]);
+            if (ar) y += ad[i];
+            v[i] = y;
+        }
+        st8(orow + c, v);
+    }
+}
+
+int layernorm_bf16(const __nv_bfloat16* x, int ldx, __nv_bfloat16* out, int ldo, int M, int d,
+                   const __nv_bfloat16* mul, int mul_ld, const __nv_bfloat16* add, int add_ld, int mul_add_one,
+                   int rows_per_batch, float eps, cudaStream_t st) {
+    DRAG_REQUIRE(x && out && M >= 1 && d >= 8 && d % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "layernorm: bad arguments");
+    if (rows_per_batch <= 0) rows_per_batch = 1 << 30;
+    layernorm_kernel<<<ceil_div(M, 8), 256, 0, st>>>(x, ldx, out, ldo, M, d, mul, mul_ld, add, add_ld, mul_add_one,
+                                                     rows_per_batch, eps);
+    DRAG_CUDA(cudaGetLastError());
+    return DRAG_OK;
+}
+
+// emb[b][0:128] = cos(1000 t_b w_i), emb[b][128:256] = sin(...), w_i = exp(-ln(1e4) i / 128).
+__global__ void timestep_embed_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 128) return;
+    const int b = i >> 7, j = i & 127;
+    const float freq = expf(-9.210340371976184f * static_cast<float>(j) / 128.f);
+    const float arg = 1000.f * t[b] * freq;
+    float sn, cs;
+    sincosf(arg, &sn, &cs);
+    out[b * 256 + j] = __float2bfloat16(cs);
+    out[b * 256 + 128 + j] = __float2bfloat16(sn);
+}
+int timestep_embed(const float* t_dev, __nv_bfloat16* out, int B, cudaStream_t st) {
+    DRAG_REQUIRE(t_dev && out && B >= 1, "timestep_embed: bad arguments");
+    timestep_embed_kernel<<<ceil_div(B * 128, 128), 128, 0, st>>>(t_dev, out, B);
+    DRAG_CUDA(cudaGetLastError());
+    return DRAG_OK;
+}
+
+// out = silu(a + b + c)  (b, c optional) - the conditioning vector fed to every modulation Linear.
+__global__ void sum_silu_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, const __nv_bfloat16* c,
+                                __nv_bfloat16* out, int n, int apply_silu) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // each stage rounds to bf16 like the reference's bf16 tensor adds
+    float v = __bfloat162float(a[i]);
+    if (b) v = __bfloat162float(__float2bfloat16(v + __bfloat162float(b[i])));
+    if (c) v = __bfloat162float(__float2bfloat16(v + __bfloat162float(c[i])));
+    if (apply_silu) v = v / (1.f + __expf(-v));
+    out[i] = __float2bfloat16(v);
+}
+int sum_silu(const __nv_bfloat16* a, const __nv_bfloat16* b, const __nv_bfloat16* c, __nv_bfloat16* out, int n,
+             int apply_silu, cudaStream_t st) {
+    DRAG_REQUIRE(a && out && n >= 1, "sum_silu: bad arguments");
+    sum_silu_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a, b, c, out, n, apply_silu);
+    DRAG_CUDA(cudaGetLastError());
+    return DRAG_OK;
+}
+
+// x[r][c] = bf16(float(x[r][c]) + dsigma * float(v[r][c]))   flow-match Euler step on a strided view
+__global__ void euler_step_kernel(__nv_bfloat16* x, int ldx, const __nv_bfloat16* v, int ldv, int rows, int cols,
+                                  float dsigma) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int cpr = cols / 8;
+    if (i >= static_cast<int64_t>(rows) * cpr) return;
+    const int r = static_cast<int>(i / cpr), c = static_cast<int>(i - static_cast<int64_t>(r) * cpr) * 8;
+    float xv[8], vv[8];
+    ld8(x + static_cast<size_t>(r) * ldx + c, xv);
+    ld8(v + static_cast<size_t>(r) * ldv + c, vv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xv[j] = __fadd_rn(xv[j], __fmul_rn(dsigma, vv[j]));   // unfused, like torch
+    st8(x + static_cast<size_t>(r) * ldx + c, xv);
+}
+int euler_step(__nv_bfloat16* x, int ldx, const __nv_bfloat16* v, int ldv, int rows, int cols, float dsigma,
+               cudaStream_t st) {
+    DRAG_REQUIRE(x && v && rows >= 1 && cols % 8 == 0 && ldx % 8 == 0 && ldv % 8 == 0, "euler_step: bad arguments");
+    const int64_t n = static_cast<int64_t>(rows) * (cols / 8);
+    euler_step_kernel<<<ceil_div(n, 256), 256, 0, st>>>(x, ldx, v, ldv, rows, cols, dsigma);
+    DRAG_CUDA(cudaGetLastError());
+    return DRAG_OK;
+}
+
+// Redux prompt blend: out_embeds[t][c] = sum_b s_embed[b] * (t < n_txt ? txt[b][t][c] : img[b][t-n_txt][c]);
+// out_pooled[c] = sum_b s_pool[b] * pooled[b][c]. Products and the running sum round to bf16 like
+// the reference's bf16 tensor ops.
+__global__ void redux_blend_kernel(const __nv_bfloat16* txt, const __nv_bfloat16* img, const __nv_bfloat16* pooled,
+                                   const float* s_embed, const float* s_pool, __nv_bfloat16* out_embeds,
+                                   __nv_bfloat16* out_pooled, int B, int n_txt, int n_img, int dim, int pooled_dim) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t n_embed = static_cast<int64_t>(n_txt + n_img) * dim;
+    if (i < n_embed) {
+        const int t = static_cast<int>(i / dim), c = static_cast<int>(i - static_cast<int64_t>(t) * dim);
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b) {
+            const __nv_bfloat16 e = (t < n_txt) ? txt[(static_cast<size_t>(b) * n_txt + t) * dim + c]
+                                                : img[(static_cast<size_t>(b) * n_img + (t - n_txt)) * dim + c];
+            const float prod = __bfloat162float(__float2bfloat16(__bfloat162float(e) * __bfloat162float(__float2bfloat16(s_embed[b]))));
+            acc = (b == 0) ? prod : __bfloat162float(__float2bfloat16(acc + prod));
+        }
+        out_embeds[i] = __float2bfloat16(acc);
+    } else if (i < n_embed + pooled_dim) {
+        const int c = static_cast<int>(i - n_embed);
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b) {
+            const float prod = __bfloat162float(__float2bfloat16(
+                __bfloat162float(pooled[static_cast<size_t>(b) * pooled_dim + c]) * __bfloat162float(__float2bfloat16(s_pool[b]))));
+            acc = (b == 0) ? prod : __bfloat162float(__float2bfloat16(acc + prod));
+        }
+        out_pooled[c] = __float2bfloat16(acc);
+    }
+}
+int redux_blend(const __nv_bfloat16* txt, const __nv_bfloat16* img, const __nv_bfloat16* pooled, const float* s_embed,
+                const float* s_pool, __nv_bfloat16* out_embeds, __nv_bfloat16* out_pooled, int B, int n_txt, int n_img,
+                int dim, int pooled_dim, cudaStream_t st) {
+    DRAG_REQUIRE(txt && img && pooled && s_embed && s_pool && out_embeds && out_pooled && B >= 1, "redux_blend: bad arguments");
+    const int64_t n = static_cast<int64_t>(n_txt + n_img) * dim + pooled_dim;
+    redux_blend_kernel<<<ceil_div(n, 256), 256, 0, st>>>(txt, img, pooled, s_embed, s_pool, out_embeds, out_pooled, B,
+                                                         n_txt, n_img, dim, pooled_dim);
+    DRAG_CUDA(cudaGetLastError());
+    return DRAG_OK;
+}
+
+// out[r] = x[r] / ||x[r]||_2  (fp32 in/out) - the caller-side normalisation of retrieval...:172.
+__global__ void l2_normalize_kernel(const float* x, float* out, int rows, int d) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float ss = 0.f;
+    for (int c = lane; c < d; c += 32) {
+        const float v = x[static_cast<size_t>(row) * d + c];
+        ss = fmaf(v, v, ss);
+    }
+    const float inv = 1.f / sqrtf(wsum(ss));
+    for (int c = lane; c < d; c += 32) out[static_cast<size_t>(row) * d + c] = x[static_cast<size_t>(row) * d + c] * inv;
+}
+int l2_normalize(const float* x, float* out, int rows, int d, cudaStream_t st) {
+    DRAG_REQUIRE(x && out && rows >= 1 && d >= 1, "l2_normalize: bad arguments");
+    l2_normalize_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(x, out, rows, d);
+    DRAG_CUDA(cudaGetLastError());
+    return DRAG_OK;
+}
+
+}  // namespace drag

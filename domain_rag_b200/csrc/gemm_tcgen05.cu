@@ -15,7 +15,9 @@
 
 #include <mutex>
 
+#include "flux_ops.cuh"
 #include "gemm.cuh"
+#include "prof.cuh"
 #include "ptx.cuh"
 
 namespace drag {
@@ -351,6 +353,22 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t
     return DRAG_OK;
 }
 
+// 3-D bf16 tensor [d2][d1][d0] (d0 contiguous); box = box0 x box1 x 1, SWIZZLE_128B (box0 * 2 bytes == 128).
+int make_tmap_bf16_3d(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+                      uint64_t stride2_elems, uint32_t box0, uint32_t box1) {
+    std::call_once(g_encode_once, load_encode);
+    if (!g_encode) return fail(DRAG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_elems * 2, stride2_elems * 2};
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DRAG_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: " + std::to_string(r));
+    return DRAG_OK;
+}
+
 template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& sh, const GemmEpi& epi,
                        cudaStream_t st) {
@@ -399,11 +417,14 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tmB, W, N, K, ldw, bn);
     if (rc) return rc;
+    const int slot = prof_begin(PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
     switch (bn) {
-        case 256: return launch_gemm<256>(tmA, tmB, sh, epi, st);
-        case 128: return launch_gemm<128>(tmA, tmB, sh, epi, st);
-        default:  return launch_gemm<64>(tmA, tmB, sh, epi, st);
+        case 256: rc = launch_gemm<256>(tmA, tmB, sh, epi, st); break;
+        case 128: rc = launch_gemm<128>(tmA, tmB, sh, epi, st); break;
+        default:  rc = launch_gemm<64>(tmA, tmB, sh, epi, st); break;
     }
+    prof_end(slot, st);
+    return rc;
 }
 
 }  // namespace drag

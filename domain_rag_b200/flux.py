@@ -1,0 +1,285 @@
+"""Flux MMDiT on the sm_100a engine + the pipeline objects the reference scripts call.
+
+Reference call sites:
+  batch_generate_flux_kshot.py:467-474   pipe(guidance_scale=2.5, num_inference_steps=50, height=1024,
+        width=1024, generator=torch.Generator("cpu").manual_seed(0), **pipe_prior_output).images
+  outpainting_updown_sampling_redux.py:1246-1257   pipe_fill(image=..., mask_image=..., height=H, width=W,
+        guidance_scale=g, num_inference_steps=50, prompt_embeds=..., pooled_prompt_embeds=...,
+        generator=..., strength=s).images[0]
+Both run diffusers' FluxTransformer2DModel once per step; here every step is one drag_flux_forward
+(C++ orchestration over the tcgen05 GEMM / attention kernels) plus one drag_euler_step.
+No PyTorch arithmetic on the step path; torch only owns the device buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+@dataclass
+class FluxConfig:
+    in_channels: int = 64          # 64 FLUX.1-dev (FluxPipeline), 384 FLUX.1-Fill-dev (FluxFillPipeline)
+    d: int = 3072
+    heads: int = 24
+    n_double: int = 19
+    n_single: int = 38
+    txt_dim: int = 4096
+    pooled_dim: int = 768
+    out_channels: int = 64
+    guidance: bool = True
+    axes_dim: Tuple[int, int, int] = (16, 56, 56)
+    theta: float = 10000.0
+    mlp_ratio: int = 4
+
+    @property
+    def n_mod(self) -> int:
+        return self.n_double * 12 * self.d + self.n_single * 3 * self.d + 2 * self.d
+
+
+def param_shapes(cfg: FluxConfig) -> Dict[str, tuple]:
+    """Fused parameter layout consumed by the engine (see oracle/flux.py for the meaning of each)."""
+    d, hd, r = cfg.d, 128, cfg.mlp_ratio
+    s = {"x_in.w": (d, cfg.in_channels), "x_in.b": (d,), "ctx_in.w": (d, cfg.txt_dim), "ctx_in.b": (d,),
+         "t_in.w1": (d, 256), "t_in.b1": (d,), "t_in.w2": (d, d), "t_in.b2": (d,)}
+    if cfg.guidance:
+        s.update({"g_in.w1": (d, 256), "g_in.b1": (d,), "g_in.w2": (d, d), "g_in.b2": (d,)})
+    s.update({"p_in.w1": (d, cfg.pooled_dim), "p_in.b1": (d,), "p_in.w2": (d, d), "p_in.b2": (d,),
+              "mod.w": (cfg.n_mod, d), "mod.b": (cfg.n_mod,),
+              "final.w": (cfg.out_channels, d), "final.b": (cfg.out_channels,)})
+    for i in range(cfg.n_double):
+        for st in ("img", "txt"):
+            p = f"double.{i}.{st}."
+            s.update({p + "qkv.w": (3 * d, d), p + "qkv.b": (3 * d,), p + "qnorm": (hd,), p + "knorm": (hd,),
+                      p + "out.w": (d, d), p + "out.b": (d,), p + "mlp1.w": (r * d, d), p + "mlp1.b": (r * d,),
+                      p + "mlp2.w": (d, r * d), p + "mlp2.b": (d,)})
+    for i in range(cfg.n_single):
+        p = f"single.{i}."
+        s.update({p + "qkv.w": (3 * d, d), p + "qkv.b": (3 * d,), p + "qnorm": (hd,), p + "knorm": (hd,),
+                  p + "mlp.w": (r * d, d), p + "mlp.b": (r * d,), p + "out.w": (d, (1 + r) * d), p + "out.b": (d,)})
+    return s
+
+
+def param_order(cfg: FluxConfig) -> List[Optional[str]]:
+    """Canonical pointer order of drag_flux_set_weights: 20 globals (guidance slots None when the
+    model has no guidance embedder), 20 per double block (img then txt), 8 per single block."""
+    g = ["g_in.w1", "g_in.b1", "g_in.w2", "g_in.b2"] if cfg.guidance else [None] * 4
+    order: List[Optional[str]] = ["x_in.w", "x_in.b", "ctx_in.w", "ctx_in.b", "t_in.w1", "t_in.b1", "t_in.w2",
+                                  "t_in.b2", *g, "p_in.w1", "p_in.b1", "p_in.w2", "p_in.b2", "mod.w", "mod.b",
+                                  "final.w", "final.b"]
+    for i in range(cfg.n_double):
+        for st in ("img", "txt"):
+            p = f"double.{i}.{st}."
+            order += [p + k for k in ("qkv.w", "qkv.b", "qnorm", "knorm", "out.w", "out.b", "mlp1.w", "mlp1.b",
+                                      "mlp2.w", "mlp2.b")]
+    for i in range(cfg.n_single):
+        p = f"single.{i}."
+        order += [p + k for k in ("qkv.w", "qkv.b", "qnorm", "knorm", "mlp.w", "mlp.b", "out.w", "out.b")]
+    return order
+
+
+def init_params_device(cfg: FluxConfig, seed: int = 3000, device="cuda") -> Dict[str, torch.Tensor]:
+    """Random-init bf16 weights generated ON the device (11.9 B parameters at full size; no checkpoints
+    offline). Variance preserving: Linear std = fan_in^-1/2, biases 0.02, modulation Linear half
+    that (shift/scale/gate are exercised but stay O(1)), RMSNorm weights ~ 1. Large tensors are drawn
+    in row chunks to bound the fp32 staging memory."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = {}
+    for name, shape in param_shapes(cfg).items():
+        if name.endswith("norm"):
+            t = (1.0 + 0.1 * torch.randn(shape, generator=g, device=device)).bfloat16()
+        elif len(shape) == 2:
+            std = shape[1] ** -0.5 * (0.5 if name == "mod.w" else 1.0)
+            t = torch.empty(shape, dtype=torch.bfloat16, device=device)
+            rows = max(1, (1 << 26) // shape[1])
+            for r0 in range(0, shape[0], rows):
+                r1 = min(shape[0], r0 + rows)
+                t[r0:r1] = (torch.randn((r1 - r0, shape[1]), generator=g, device=device) * std).bfloat16()
+        else:
+            std = 0.1 if name == "mod.b" else 0.02
+            t = (torch.randn(shape, generator=g, device=device) * std).bfloat16()
+        out[name] = t
+    return out
+
+
+def rope_tables(ids: torch.Tensor, axes_dim=(16, 56, 56), theta: float = 10000.0):
+    """ids [S,3] (host) -> (cos, sin) fp32 [S,64]; angles in float64 like diffusers' FluxPosEmbed."""
+    cos, sin = [], []
+    for i, a in enumerate(axes_dim):
+        omega = 1.0 / (theta ** (torch.arange(0, a, 2, dtype=torch.float64) / a))
+        ang = ids[:, i].double()[:, None] * omega[None]
+        cos.append(torch.cos(ang))
+        sin.append(torch.sin(ang))
+    return torch.cat(cos, -1).float().contiguous(), torch.cat(sin, -1).float().contiguous()
+
+
+def image_ids(h2: int, w2: int) -> torch.Tensor:
+    ids = torch.zeros(h2, w2, 3)
+    ids[..., 1] = torch.arange(h2)[:, None]
+    ids[..., 2] = torch.arange(w2)[None, :]
+    return ids.reshape(h2 * w2, 3)
+
+
+def flow_match_sigmas(num_steps: int, seq_len: int) -> List[float]:
+    """sigma_i = linspace(1, 1/T, T) shifted by mu(seq_len) (FlowMatchEulerDiscreteScheduler with
+    dynamic shifting as the Flux pipelines configure it), with the terminal 0 appended."""
+    m = (1.15 - 0.5) / (4096 - 256)
+    mu = seq_len * m + (0.5 - m * 256)
+    sig = torch.linspace(1.0, 1.0 / num_steps, num_steps, dtype=torch.float64)
+    sig = math.exp(mu) / (math.exp(mu) + (1.0 / sig - 1.0))
+    return [float(s) for s in sig.float()] + [0.0]
+
+
+def pack_latents(z: torch.Tensor) -> torch.Tensor:
+    """[B,16,h,w] -> [B,(h/2)(w/2),64] (data movement only)."""
+    B, Cc, h, w = z.shape
+    return z.view(B, Cc, h // 2, 2, w // 2, 2).permute(0, 2, 4, 1, 3, 5).reshape(B, (h // 2) * (w // 2), Cc * 4)
+
+
+def unpack_latents(x: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    B, _, ch = x.shape
+    Cc = ch // 4
+    return x.view(B, h // 2, w // 2, Cc, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(B, Cc, h, w)
+
+
+class FluxTransformer:
+    """FluxTransformer2DModel stand-in: owns bf16 device weights and one C++ engine."""
+
+    def __init__(self, cfg: FluxConfig, params: Dict[str, torch.Tensor], max_batch: int, max_img_tokens: int,
+                 txt_tokens: int, device="cuda"):
+        lib = _lib.load()
+        self.cfg, self.device = cfg, torch.device(device)
+        self.params = {k: v.to(self.device, torch.bfloat16).contiguous() for k, v in params.items()}
+        missing = [n for n in param_shapes(cfg) if n not in self.params]
+        if missing:
+            raise KeyError(f"missing Flux parameters: {missing[:4]}...")
+        self.max_batch, self.max_img_tokens, self.txt_tokens = max_batch, max_img_tokens, txt_tokens
+        c = (C.c_int * 12)(cfg.in_channels, cfg.d, cfg.heads, cfg.n_double, cfg.n_single, cfg.txt_dim, cfg.pooled_dim,
+                           cfg.out_channels, int(cfg.guidance), max_batch, max_img_tokens, txt_tokens)
+        self._h = C.c_void_p()
+        _lib.check(lib.drag_flux_create(C.byref(c), C.byref(self._h)), "drag_flux_create")
+        order = param_order(cfg)
+        ptrs = (C.c_void_p * len(order))(*[self.params[n].data_ptr() if n else None for n in order])
+        _lib.check(lib.drag_flux_set_weights(self._h, ptrs, len(order)), "drag_flux_set_weights")
+
+    def forward(self, x, ctx, pooled, t, g, rope_cos, rope_sin, out=None, n_double_run=-1, n_single_run=-1):
+        """x bf16 [B,S_img,ldx>=C_in] (may be a channel-strided view), ctx bf16 [B,S_txt,txt_dim], pooled bf16
+        [B,pooled_dim], t/g fp32 [B] device tensors -> v bf16 [B,S_img,out_channels]."""
+        B, S_img = x.shape[0], x.shape[1]
+        assert x.stride(2) == 1 and x.stride(0) == S_img * x.stride(1)
+        assert ctx.is_contiguous() and pooled.is_contiguous() and ctx.shape[1] == self.txt_tokens
+        if out is None:
+            out = torch.empty((B, S_img, self.cfg.out_channels), dtype=torch.bfloat16, device=x.device)
+        _lib.check(_lib.load().drag_flux_forward(
+            self._h, _lib.ptr(x), x.stride(1), _lib.ptr(ctx), _lib.ptr(pooled), _lib.ptr(t),
+            _lib.ptr(g) if g is not None else None, _lib.ptr(rope_cos), _lib.ptr(rope_sin), B, S_img,
+            _lib.ptr(out), out.stride(1), n_double_run, n_single_run, _lib.current_stream_ptr(x.device)),
+            "drag_flux_forward")
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                _lib.load().drag_flux_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+
+def euler_step_(x: torch.Tensor, v: torch.Tensor, dsigma: float) -> None:
+    """In place x += dsigma * v on [B,S,C] bf16 views (channel-strided allowed)."""
+    B, S, Cc = v.shape
+    _lib.check(_lib.load().drag_euler_step(_lib.ptr(x), x.stride(1), _lib.ptr(v), v.stride(1), B * S, Cc,
+                                           float(dsigma), _lib.current_stream_ptr(x.device)), "drag_euler_step")
+
+
+def redux_blend(txt_tokens, img_tokens, pooled, s_embed, s_pool):
+    """FluxPriorReduxPipeline output from precomputed encoder tokens: bf16 [B,512,4096], [B,729,4096],
+    [B,768], fp32 scales [B] -> (prompt_embeds [1,1241,4096], pooled_prompt_embeds [1,768])."""
+    B, n_txt, dim = txt_tokens.shape
+    n_img = img_tokens.shape[1]
+    dev = txt_tokens.device
+    out_e = torch.empty((1, n_txt + n_img, dim), dtype=torch.bfloat16, device=dev)
+    out_p = torch.empty((1, pooled.shape[1]), dtype=torch.bfloat16, device=dev)
+    se = torch.as_tensor(s_embed, dtype=torch.float32, device=dev).contiguous()
+    sp = torch.as_tensor(s_pool, dtype=torch.float32, device=dev).contiguous()
+    _lib.check(_lib.load().drag_redux_blend(_lib.ptr(txt_tokens.contiguous()), _lib.ptr(img_tokens.contiguous()),
+                                            _lib.ptr(pooled.contiguous()), _lib.ptr(se), _lib.ptr(sp), _lib.ptr(out_e),
+                                            _lib.ptr(out_p), B, n_txt, n_img, dim, pooled.shape[1],
+                                            _lib.current_stream_ptr(dev)), "drag_redux_blend")
+    return out_e, out_p
+
+
+@dataclass
+class PipelineOutput:
+    latents: torch.Tensor                      # [B,16,H/8,W/8] bf16 (unpacked)
+    images: Optional[list] = None              # PIL images once the VAE decoder is built
+    steps_run: int = 0
+
+
+class FluxPipeline:
+    """Mirror of the diffusers pipeline call the reference makes (kwargs, CPU generator semantics,
+    schedule, Euler update). Text/image encoders and the VAE are outside this round's scope: the
+    caller passes prompt_embeds / pooled_prompt_embeds (e.g. from redux_blend) and receives latents."""
+
+    def __init__(self, transformer: FluxTransformer):
+        self.transformer = transformer
+        self._rope_cache = {}
+
+    def _rope(self, h2, w2, s_txt, device):
+        key = (h2, w2, s_txt)
+        if key not in self._rope_cache:
+            ids = torch.cat([torch.zeros(s_txt, 3), image_ids(h2, w2)], 0)
+            cos, sin = rope_tables(ids, self.transformer.cfg.axes_dim, self.transformer.cfg.theta)
+            self._rope_cache[key] = (cos.to(device), sin.to(device))
+        return self._rope_cache[key]
+
+    def prepare_latents(self, batch, height, width, generator, device):
+        """randn([B,16,H/8,W/8]) drawn with the CPU generator in bf16, then moved to the GPU (the reference
+        passes torch.Generator("cpu").manual_seed(0), batch_generate_flux_kshot.py:472); H, W floored to /16."""
+        h, w = 2 * (int(height) // 16), 2 * (int(width) // 16)
+        z = torch.randn((batch, 16, h, w), generator=generator, dtype=torch.bfloat16)
+        return pack_latents(z).contiguous().pin_memory().to(device, non_blocking=True), h, w
+
+    def __call__(self, prompt_embeds, pooled_prompt_embeds, guidance_scale=3.5, num_inference_steps=28, height=1024,
+                 width=1024, generator=None, latents=None, extra_cond=None, strength=1.0, image_latents=None,
+                 output_type="latent"):
+        tr = self.transformer
+        dev = tr.device
+        B = prompt_embeds.shape[0]
+        if latents is None:
+            latents, h, w = self.prepare_latents(B, height, width, generator, dev)
+        else:
+            h, w = 2 * (int(height) // 16), 2 * (int(width) // 16)
+        S_img = latents.shape[1]
+        sig = flow_match_sigmas(num_inference_steps, S_img)
+        cos, sin = self._rope(h // 2, w // 2, prompt_embeds.shape[1], dev)
+        # img2img / fill: run only the last int(T*strength) steps from a noised image (reference strength tables)
+        start = 0
+        if strength < 1.0:
+            start = num_inference_steps - int(min(num_inference_steps * strength, num_inference_steps))
+            if image_latents is not None:
+                latents = (sig[start] * latents.float() + (1.0 - sig[start]) * image_latents.float()).bfloat16()
+        c_lat = latents.shape[2]
+        if extra_cond is not None:       # Fill: x lives in the first 64 channels of a persistent [B,S,384] buffer
+            buf = torch.cat([latents, extra_cond.to(latents.dtype)], dim=-1).contiguous()
+        else:
+            buf = latents.contiguous()
+        x_view = buf[:, :, :c_lat]
+        ctx = prompt_embeds.to(dev, torch.bfloat16).contiguous()
+        pooled = pooled_prompt_embeds.to(dev, torch.bfloat16).contiguous()
+        g = torch.full((B,), float(guidance_scale), dtype=torch.float32, device=dev) if tr.cfg.guidance else None
+        t_all = torch.tensor(sig[:-1], dtype=torch.float32, device=dev)[:, None].expand(-1, B).contiguous()
+        v = torch.empty((B, S_img, tr.cfg.out_channels), dtype=torch.bfloat16, device=dev)
+        for i in range(start, num_inference_steps):
+            tr.forward(buf, ctx, pooled, t_all[i], g, cos, sin, out=v)
+            euler_step_(x_view, v, sig[i + 1] - sig[i])
+        lat = unpack_latents(x_view.contiguous(), h, w)
+        if output_type != "latent":
+            raise NotImplementedError("VAE decode is the next scope row (SURVEY 8f N1); use output_type='latent'")
+        return PipelineOutput(latents=lat, images=None, steps_run=num_inference_steps - start)

@@ -45,3 +45,50 @@ def qkv_rope(a, w, bias, q_out, k_out, v_out, q_norm_w, k_norm_w, rope_cos, rope
         _lib.ptr(k_out), _lib.ptr(v_out), _lib.ptr(q_norm_w), _lib.ptr(k_norm_w), _lib.ptr(rope_cos),
         _lib.ptr(rope_sin), S, tok_offset, rows_per_batch, eps, _lib.current_stream_ptr(a.device)),
         "drag_gemm_qkv_rope")
+
+
+def attention(q, k, v, split=0, out0=None, out1=None):
+    """q,k,v bf16 [B,H,S,128] -> (out0 [B*split, H*128] or None, out1 [B*(S-split), H*128])."""
+    B, H, S, hd = q.shape
+    assert hd == 128 and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+    if split > 0 and out0 is None:
+        out0 = torch.empty((B * split, H * 128), dtype=torch.bfloat16, device=q.device)
+    if split < S and out1 is None:
+        out1 = torch.empty((B * (S - split), H * 128), dtype=torch.bfloat16, device=q.device)
+    _lib.check(_lib.load().drag_attention_bf16(
+        _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), B, H, S, split, _lib.ptr(out0), out0.stride(0) if out0 is not None else 8,
+        _lib.ptr(out1), out1.stride(0) if out1 is not None else 8, _lib.current_stream_ptr(q.device)),
+        "drag_attention_bf16")
+    return out0, out1
+
+
+def layernorm(x, mul=None, add=None, adaln=False, rows_per_batch=0, eps=1e-6, out=None):
+    """LayerNorm without affine followed by * (1 + mul[b]) + add[b] (adaln) or * mul + add (affine)."""
+    M, d = x.shape
+    if out is None:
+        out = torch.empty((M, d), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().drag_layernorm_bf16(
+        _lib.ptr(x), x.stride(0), _lib.ptr(out), out.stride(0), M, d, _lib.ptr(mul),
+        (mul.stride(0) if (mul is not None and mul.dim() == 2) else 0), _lib.ptr(add),
+        (add.stride(0) if (add is not None and add.dim() == 2) else 0), int(adaln), rows_per_batch, eps,
+        _lib.current_stream_ptr(x.device)), "drag_layernorm_bf16")
+    return out
+
+
+def timestep_embed(t):
+    out = torch.empty((t.shape[0], 256), dtype=torch.bfloat16, device=t.device)
+    _lib.check(_lib.load().drag_timestep_embed(_lib.ptr(t), _lib.ptr(out), t.shape[0],
+                                               _lib.current_stream_ptr(t.device)), "drag_timestep_embed")
+    return out
+
+
+def l2_normalize(x):
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().drag_l2_normalize(_lib.ptr(x), _lib.ptr(out), x.shape[0], x.shape[1],
+                                             _lib.current_stream_ptr(x.device)), "drag_l2_normalize")
+    return out
+
+
+def debug_set(key: int, value: int) -> None:
+    _lib.check(_lib.load().drag_debug_set(key, value), "drag_debug_set")

@@ -91,6 +91,58 @@ int drag_gemm_qkv_rope(const void* A, int lda, const void* W, int ldw, int M, in
                        const float* rope_cos, const float* rope_sin, int s_total, int tok_offset,
                        int rows_per_batch, float rms_eps, void* stream);
 
+/* ---- attention / row kernels of the Flux and ViT paths ------------------------------------------
+ * Non-causal attention, head dim 128 (F.scaled_dot_product_attention in the diffusers Flux blocks):
+ * q,k,v bf16 [B][H][S][128]; token s < split is written to out0 row (b*split+s), token s >= split to out1
+ * row (b*(S-split)+s-split); head h occupies columns [h*128,(h+1)*128) of a row with leading dim ld0/ld1. */
+int drag_attention_bf16(const void* q, const void* k, const void* v, int B, int H, int S, int split, void* out0,
+                        int ld0, void* out1, int ld1, void* stream);
+/* out = LayerNorm(x) (no affine, eps) then * (1 + mul[b]) + add[b] when adaln = 1 (AdaLN modulate, b =
+ * row / rows_per_batch, per-batch vectors with stride mul_ld / add_ld), or * mul + add per channel when
+ * adaln = 0 (plain affine LayerNorm; either pointer may be NULL). bf16, d % 8 == 0. */
+int drag_layernorm_bf16(const void* x, int ldx, void* out, int ldo, int M, int d, const void* mul, int mul_ld,
+                        const void* add, int add_ld, int adaln, int rows_per_batch, float eps, void* stream);
+/* Sinusoidal embedding of 1000*t: out bf16 [B][256] = [cos | sin]; t fp32 [B] on the device. */
+int drag_timestep_embed(const float* t_dev, void* out, int B, void* stream);
+/* Flow-match Euler update on a strided bf16 view: x += dsigma * v (fp32 arithmetic). */
+int drag_euler_step(void* x, int ldx, const void* v, int ldv, int rows, int cols, float dsigma, void* stream);
+/* FluxPriorReduxPipeline output blend (batch_generate_flux_kshot.py:459-465, outpainting...:1237-1243):
+ * out_embeds[1][n_txt+n_img][dim] = sum_b s_embed[b] * cat(txt[b], img[b]); out_pooled = sum_b s_pool[b]*pooled[b]. */
+int drag_redux_blend(const void* txt, const void* img, const void* pooled, const float* s_embed_dev,
+                     const float* s_pool_dev, void* out_embeds, void* out_pooled, int B, int n_txt, int n_img, int dim,
+                     int pooled_dim, void* stream);
+/* out[r] = x[r] / ||x[r]||_2, fp32 (image_embedding / image_embedding.norm(dim=-1), retrieval...:172). */
+int drag_l2_normalize(const float* x, float* out, int rows, int d, void* stream);
+
+/* ---- Flux MMDiT engine --------------------------------------------------------------------------
+ * One FluxTransformer2DModel.forward per call (the denoising step inside pipe(...) /
+ * pipe_fill(...): batch_generate_flux_kshot.py:467-474, outpainting_updown_sampling_redux.py:1246-1257).
+ * Weights are caller-owned bf16 device pointers in the canonical order documented in
+ * domain_rag_b200/flux.py (param_order); the engine owns its activation workspace. */
+typedef struct drag_flux drag_flux_t;
+typedef struct {
+    int in_channels, d, heads, n_double, n_single, txt_dim, pooled_dim, out_channels, guidance;
+    int max_batch, max_img_tokens, txt_tokens;
+} drag_flux_config;
+int drag_flux_create(const drag_flux_config* cfg, drag_flux_t** out);
+int drag_flux_destroy(drag_flux_t* h);
+int drag_flux_set_weights(drag_flux_t* h, const void* const* ptrs, int n);
+/* x bf16 [B*S_img][ldx] (first in_channels columns), ctx bf16 [B*txt_tokens][txt_dim], pooled bf16
+ * [B][pooled_dim], t_dev / g_dev fp32 [B] (sigma and guidance scale), rope tables fp32 [txt_tokens+S_img][64];
+ * v_out bf16 [B*S_img][ldv]. n_double_run / n_single_run < 0 run every block. */
+int drag_flux_forward(drag_flux_t* h, const void* x, int ldx, const void* ctx, const void* pooled, const float* t_dev,
+                      const float* g_dev, const float* rope_cos, const float* rope_sin, int B, int S_img, void* v_out,
+                      int ldv, int n_double_run, int n_single_run, void* stream);
+
+/* Per-launch CUDA-event timing of the heavy kernels on their launching stream (bench.py roofline):
+ * class 0 = tcgen05 GEMM (work = 2*M*N*K flops), class 1 = attention (work = 4*B*H*S*S*128 flops).
+ * drag_prof_collect synchronises, returns summed milliseconds / work / launch counts per class, and resets. */
+int drag_prof_enable(int on);
+int drag_prof_collect(double* ms, double* work, int* count, int n_classes);
+
+/* Debug knobs for bring-up (key 1/2: MN-major V descriptor leading/stride byte offsets of the attention). */
+int drag_debug_set(int key, int value);
+
 #ifdef __cplusplus
 }
 #endif

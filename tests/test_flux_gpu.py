@@ -1,0 +1,140 @@
+"""GPU parity: attention / row kernels vs PyTorch fp32 references of the same op, and the Flux MMDiT
+engine (forward + sampling loop) vs the CPU fp32 oracle at reduced size (full width is infeasible on
+the CPU: 88.85 TFLOP per forward)."""
+import math
+
+import pytest
+import torch
+
+from oracle import flux as OF
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(lib):
+    from domain_rag_b200 import ops
+    return ops
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).bfloat16()
+
+
+def rel_l2(got, want):
+    return ((got.float() - want.float()).norm() / want.float().norm().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("B,H,S,split", [(1, 2, 128, 0), (1, 2, 256, 0), (2, 3, 300, 77), (1, 4, 1000, 0),
+                                         (1, 24, 2265, 1241), (1, 2, 5337, 1241), (2, 2, 89, 89)])
+def test_attention_matches_sdpa(ops, B, H, S, split):
+    q, k, v = rnd((B, H, S, 128), 1), rnd((B, H, S, 128), 2), rnd((B, H, S, 128), 3)
+    o0, o1 = ops.attention(q, k, v, split)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    ref = ref.permute(0, 2, 1, 3).reshape(B, S, H * 128)
+    if split > 0:
+        assert rel_l2(o0.view(B, split, -1), ref[:, :split]) < 1e-2
+    if split < S:
+        got = o1.view(B, S - split, -1)
+        assert rel_l2(got, ref[:, split:]) < 1e-2
+        assert (got.float() - ref[:, split:]).abs().max().item() < 2e-2
+
+
+def test_attention_large_logits(ops):
+    """Running-max growth across tiles exercises the lazy O rescale."""
+    B, H, S = 1, 2, 700
+    q, k, v = rnd((B, H, S, 128), 4, 3.0), rnd((B, H, S, 128), 5, 3.0), rnd((B, H, S, 128), 6)
+    k[:, :, 600:] *= 2.0          # late keys dominate -> max jumps in the last tiles
+    _, o = ops.attention(q, k, v, 0)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    assert rel_l2(o.view(B, S, -1), ref.permute(0, 2, 1, 3).reshape(B, S, -1)) < 2e-2
+
+
+@pytest.mark.parametrize("M,d,rpb", [(100, 768, 0), (333, 3072, 111), (50, 1024, 25), (7, 256, 7)])
+def test_layernorm_adaln_and_affine(ops, M, d, rpb):
+    x = rnd((M, d), 7, 2.0) + 0.5
+    nb = 1 if rpb == 0 else M // rpb
+    scale, shift = rnd((nb, d), 8, 0.3), rnd((nb, d), 9, 0.3)
+    got = ops.layernorm(x, scale, shift, adaln=True, rows_per_batch=rpb, eps=1e-6)
+    ln = torch.nn.functional.layer_norm(x.float(), (d,), eps=1e-6)
+    rep = M if rpb == 0 else rpb
+    want = ln * (1 + scale.float().repeat_interleave(rep, 0)) + shift.float().repeat_interleave(rep, 0)
+    assert rel_l2(got, want) < 5e-3
+    gamma, beta = rnd((d,), 10, 0.5) + 1.0, rnd((d,), 11, 0.1)
+    got = ops.layernorm(x, gamma, beta, adaln=False, eps=1e-5)
+    want = torch.nn.functional.layer_norm(x.float(), (d,), gamma.float(), beta.float(), eps=1e-5)
+    assert rel_l2(got, want) < 5e-3
+
+
+def test_timestep_embed_euler_redux_l2(ops, lib):
+    from domain_rag_b200 import flux as F
+    t = torch.tensor([1.0, 0.5, 0.0123], device="cuda")
+    got = ops.timestep_embed(t).float().cpu()
+    want = OF.timestep_embedding(t.cpu())
+    assert (got - want).abs().max().item() < 1e-2
+    x, v = rnd((2, 50, 384), 12), rnd((2, 50, 64), 13)
+    xv = x[:, :, :64]
+    want = OF.euler_step(xv.cpu().clone(), v.cpu(), 0.7, 0.65)
+    F.euler_step_(xv, v, 0.65 - 0.7)
+    assert torch.equal(xv.cpu(), want)            # fp32 fma then one bf16 rounding
+    txt, img, pooled = rnd((2, 16, 64), 14), rnd((2, 9, 64), 15), rnd((2, 32), 16)
+    e, p = F.redux_blend(txt, img, pooled, [0.8, 1.0], [1.0, 1.0])
+    we, wp = OF.redux_blend(txt.cpu(), img.cpu(), pooled.cpu(), torch.tensor([0.8, 1.0]).bfloat16(),
+                            torch.tensor([1.0, 1.0]).bfloat16())
+    assert torch.equal(e.cpu(), we) and torch.equal(p.cpu(), wp)
+    y = torch.randn(5, 512, device="cuda")
+    assert torch.allclose(ops.l2_normalize(y), y / y.norm(dim=-1, keepdim=True), atol=1e-6)
+
+
+def small_cfg(in_channels=64, guidance=True):
+    return dict(in_channels=in_channels, d=256, heads=2, n_double=2, n_single=2, txt_dim=64, pooled_dim=32,
+                out_channels=64, guidance=guidance)
+
+
+@pytest.mark.parametrize("in_channels,guidance,B,h2,w2,s_txt", [(64, True, 1, 8, 8, 40), (384, True, 2, 6, 10, 77),
+                                                                (64, False, 1, 12, 12, 130)])
+def test_flux_forward_matches_oracle(lib, in_channels, guidance, B, h2, w2, s_txt):
+    from domain_rag_b200 import flux as F
+    ocfg = OF.FluxConfig(**small_cfg(in_channels, guidance))
+    cfg = F.FluxConfig(**small_cfg(in_channels, guidance))
+    p32 = OF.init_params(ocfg, seed=3000)
+    p32 = {k: v.bfloat16().float() for k, v in p32.items()}        # both sides see the same bf16 weights
+    S_img = h2 * w2
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, S_img, in_channels, generator=g).bfloat16()
+    ctx = torch.randn(B, s_txt, 64, generator=g).bfloat16()
+    pooled = torch.randn(B, 32, generator=g).bfloat16()
+    t, gd = torch.tensor([0.8] * B), torch.tensor([2.5] * B)
+    img_ids, txt_ids = OF.image_ids(h2, w2), torch.zeros(s_txt, 3)
+    want = OF.flux_forward(p32, ocfg, x.float(), ctx.float(), pooled.float(), t, gd, img_ids, txt_ids)
+    tr = F.FluxTransformer(cfg, p32, max_batch=B, max_img_tokens=S_img, txt_tokens=s_txt)
+    cos, sin = F.rope_tables(torch.cat([txt_ids, img_ids], 0))
+    oc, osn = OF.rope_tables(torch.cat([txt_ids, img_ids], 0))
+    assert torch.equal(cos, oc) and torch.equal(sin, osn)
+    got = tr.forward(x.cuda(), ctx.cuda(), pooled.cuda(), t.cuda(), gd.cuda() if guidance else None, cos.cuda(),
+                     sin.cuda())
+    torch.cuda.synchronize()
+    r = rel_l2(got.cpu(), want)
+    assert r < 3e-2, f"rel-L2 {r}"        # bf16 activations through 4 blocks vs fp32 oracle
+
+
+def test_flux_sampling_matches_oracle(lib):
+    """Full pipeline call (CPU-generator latents, shifted sigmas, Euler) vs the oracle's sample()."""
+    from domain_rag_b200 import flux as F
+    ocfg, cfg = OF.FluxConfig(**small_cfg()), F.FluxConfig(**small_cfg())
+    p32 = {k: v.bfloat16().float() for k, v in OF.init_params(ocfg, seed=3001).items()}
+    s_txt, H, W, T = 24, 128, 160, 4
+    g = torch.Generator().manual_seed(2)
+    ctx, pooled = torch.randn(1, s_txt, 64, generator=g).bfloat16(), torch.randn(1, 32, generator=g).bfloat16()
+    tr = F.FluxTransformer(cfg, p32, max_batch=1, max_img_tokens=(H // 16) * (W // 16), txt_tokens=s_txt)
+    pipe = F.FluxPipeline(tr)
+    out = pipe(prompt_embeds=ctx, pooled_prompt_embeds=pooled, guidance_scale=2.5, num_inference_steps=T, height=H,
+               width=W, generator=torch.Generator("cpu").manual_seed(0))
+    z0 = torch.randn((1, 16, H // 8, W // 8), generator=torch.Generator("cpu").manual_seed(0), dtype=torch.bfloat16)
+    x = OF.sample(p32, ocfg, OF.pack_latents(z0).float(), ctx.float(), pooled.float(), 2.5, T, H // 16, W // 16)
+    want = OF.unpack_latents(x, H // 8, W // 8)
+    assert out.latents.shape == want.shape and out.steps_run == T
+    assert OF.flow_match_sigmas(T, x.shape[1]).tolist() == pytest.approx(F.flow_match_sigmas(T, x.shape[1]))
+    r = rel_l2(out.latents.cpu(), want)
+    assert r < 3e-2, f"rel-L2 {r}"
