@@ -24,100 +24,8 @@ REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
 
 
-# --------------------------------------------------------------------------------------------- util
-def measured_peaks() -> dict:
-    p = REPO / "MEASURED_PEAKS.json"
-    if p.exists():
-        d = json.loads(p.read_text())
-        d["source"] = "measured"
-        return d
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
-
-
-class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.proc = None
-        self.path = None
-
-    def start(self):
-        try:
-            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
-            self.path = f.name
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
-
-    def stop(self) -> dict:
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        try:
-            for line in open(self.path):
-                c = [x.strip() for x in line.split(",")]
-                if len(c) < 9:
-                    continue
-                try:
-                    sm.append(float(c[1]))
-                    mx.append(float(c[2]))
-                except ValueError:
-                    continue
-                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"],
-                                   c[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
-        return out
-
-
-def dist_setup(n_gpus: int):
-    import torch
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    else:
-        torch.cuda.set_device(0)
-    return rank, world, local
-
-
-def barrier(world):
-    import torch
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-    torch.cuda.synchronize()
-
-
-def max_over_ranks(x: float, world: int) -> float:
-    if world == 1:
-        return x
-    import torch
-    import torch.distributed as dist
-    t = torch.tensor([x], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+from domain_rag_b200.benchutil import (ClockSampler, barrier, dist_setup, max_over_ranks,  # noqa: E402
+                                       measured_peaks)
 
 
 # ------------------------------------------------------------------------------------ scan workload
@@ -327,12 +235,12 @@ def default_workload() -> str:
 
 
 def run_compose(args):
-    from domain_rag_b200.bench_compose import run
+    from bench_compose import run
     return run(args)
 
 
 def run_compose_reference(args):
-    from domain_rag_b200.bench_compose import run_reference
+    from bench_compose import run_reference
     return run_reference(args)
 
 

@@ -1,0 +1,219 @@
+"""Compose workload of bench.py: composed 1024^2 images/sec at 50 Flux-Redux steps (BASELINE.json metric).
+
+One "step" of the bench = one composed image on each GPU: Redux prompt blend (512 T5 + 729 Redux
+tokens, reference batch_generate_flux_kshot.py:459-465 / outpainting_updown_sampling_redux.py:1237-1243)
+followed by 50 denoising steps of the FLUX.1-Fill-dev-shaped MMDiT (19 double + 38 single blocks,
+d = 3072, 24 heads, C_in = 384, S = 1241 + 4096 tokens) with the flow-match Euler update, batch 1 per
+GPU like the reference. Random-init weights and synthetic tokens (no checkpoints / encoders offline);
+VAE decode and the SigLIP/T5 encoders are outside the timed region (not built yet).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+
+HEIGHT = WIDTH = 1024
+STEPS = 50
+S_TXT, N_T5, N_REDUX = 1241, 512, 729
+GUIDANCE = 30.0                      # outpainting_updown_sampling_redux.py:45-56 default_guidance_scale
+D, HEADS, N_DOUBLE, N_SINGLE = 3072, 24, 19, 38
+
+
+def flops_per_forward(s_img: int, s_txt: int = S_TXT, d: int = D, blocks: int = N_DOUBLE + N_SINGLE):
+    """per block 24 d^2 S (GEMMs) + 4 S^2 d (attention), S = s_txt + s_img."""
+    s = s_img + s_txt
+    gemm = blocks * 24.0 * d * d * s
+    attn = blocks * 4.0 * s * s * d
+    return gemm, attn
+
+
+def prof_collect():
+    from domain_rag_b200 import _lib
+    ms, work, cnt = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_int * 2)()
+    _lib.check(_lib.load().drag_prof_collect(ms, work, cnt, 2), "drag_prof_collect")
+    return [(ms[i], work[i], cnt[i]) for i in range(2)]
+
+
+def build_model(device, seed=3000, in_channels=384):
+    import torch
+
+    from domain_rag_b200.flux import FluxConfig, FluxPipeline, FluxTransformer, init_params_device
+    cfg = FluxConfig(in_channels=in_channels, d=D, heads=HEADS, n_double=N_DOUBLE, n_single=N_SINGLE)
+    params = init_params_device(cfg, seed=seed, device=device)
+    tr = FluxTransformer(cfg, params, max_batch=1, max_img_tokens=(HEIGHT // 16) * (WIDTH // 16), txt_tokens=S_TXT,
+                         device=device)
+    return cfg, tr, FluxPipeline(tr)
+
+
+def synth_inputs(seed: int):
+    """Host-side (pinned) synthetic stand-ins for what the encoders / VAE would hand to the pipeline."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    s_img = (HEIGHT // 16) * (WIDTH // 16)
+    t5 = torch.randn(1, N_T5, 4096, generator=g).bfloat16().pin_memory()
+    redux = torch.randn(1, N_REDUX, 4096, generator=g).bfloat16().pin_memory()
+    pooled = torch.randn(1, 768, generator=g).bfloat16().pin_memory()
+    cond = torch.randn(1, s_img, 320, generator=g).bfloat16().pin_memory()   # masked-image latents (64) + mask (256)
+    return t5, redux, pooled, cond
+
+
+def run(args):
+    import torch
+
+    from domain_rag_b200 import _lib
+    from domain_rag_b200 import benchutil as B
+    from domain_rag_b200.flux import redux_blend
+
+    rank, world, local = B.dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    cfg, tr, pipe = build_model(dev)
+    t5_h, redux_h, pooled_h, cond_h = synth_inputs(3000 + rank)
+    t5, redux, pooled, cond = (t.to(dev) for t in (t5_h, redux_h, pooled_h, cond_h))
+    s_img = (HEIGHT // 16) * (WIDTH // 16)
+    gen = torch.Generator("cpu")
+
+    def compose_device(seed):
+        """Inputs already resident in HBM: blend -> 50 steps -> final latents (stay on the device)."""
+        pe, pp = redux_blend(t5, redux, pooled, [1.0], [1.0])
+        lat, _, _ = latents_cache[seed % len(latents_cache)]
+        return pipe(prompt_embeds=pe, pooled_prompt_embeds=pp, guidance_scale=GUIDANCE, num_inference_steps=STEPS,
+                    height=HEIGHT, width=WIDTH, latents=lat.clone(), extra_cond=cond)
+
+    latents_cache = [pipe.prepare_latents(1, HEIGHT, WIDTH, gen.manual_seed(s), dev) for s in range(2)]
+    torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        compose_device(i)
+    B.barrier(world)
+    sampler = B.ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    B.barrier(world)
+    e0.record()
+    for i in range(args.steps):
+        out = compose_device(i)
+    e1.record()
+    B.barrier(world)
+    total_ms = B.max_over_ranks(e0.elapsed_time(e1), world)
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # dominant-kernel timing: CUDA-event bracket around every GEMM / attention launch of ONE more image
+    lib.drag_prof_enable(1)
+    compose_device(0)
+    torch.cuda.synchronize()
+    (g_ms, g_fl, g_n), (a_ms, a_fl, a_n) = prof_collect()
+    lib.drag_prof_enable(0)
+
+    # end to end through the pipeline call with HOST buffers: H2D of tokens / conditioning / latents drawn
+    # with the CPU generator, D2H of the final latents, every image
+    def compose_e2e(seed):
+        t5d, rd, pd, cd = (t.to(dev, non_blocking=True) for t in (t5_h, redux_h, pooled_h, cond_h))
+        pe, pp = redux_blend(t5d, rd, pd, [1.0], [1.0])
+        o = pipe(prompt_embeds=pe, pooled_prompt_embeds=pp, guidance_scale=GUIDANCE, num_inference_steps=STEPS,
+                 height=HEIGHT, width=WIDTH, generator=gen.manual_seed(seed), extra_cond=cd)
+        return o.latents.cpu()
+
+    n_e2e = max(1, min(args.steps, 3))
+    compose_e2e(0)
+    B.barrier(world)
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        lat_h = compose_e2e(i)
+    B.barrier(world)
+    e2e_s = B.max_over_ranks(time.perf_counter() - t0, world) / n_e2e
+
+    if rank != 0:
+        return None
+    ms_per_step = total_ms / args.steps
+    gemm_fl, attn_fl = flops_per_forward(s_img)
+    peaks = B.measured_peaks()
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    kernels_per_forward = 12 + N_DOUBLE * 13 + N_SINGLE * 5 + 2   # see flux_engine.cu
+    out = {
+        "metric": "composed images/sec (1024^2, 50-step Flux-Redux, device-timed)",
+        "value": round(world / (ms_per_step * 1e-3), 5), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "C4 per-GPU slice: Flux-Redux composition 1024^2, 50 steps, batch 1 per GPU "
+                               "(Fill-shaped MMDiT C_in=384, 19+38 blocks, S=1241+4096, guidance 30), random-init "
+                               "weights, synthetic T5/Redux tokens; VAE + encoders outside the timed region",
+                   "l2_policy": "23.8 GB of weights + 0.4 GB of activations stream per denoising step (>> 126 MB L2)",
+                   "flops_per_image": STEPS * (gemm_fl + attn_fl),
+                   "achieved_tflops": round(STEPS * (gemm_fl + attn_fl) / (ms_per_step * 1e-3) / 1e12, 1)},
+        "e2e": {"value": round(world / e2e_s, 5), "unit": "images/s",
+                "h2d_bytes_per_step": int(sum(t.numel() * 2 for t in (t5_h, redux_h, pooled_h, cond_h)) + s_img * 64 * 2),
+                "d2h_bytes_per_step": int(lat_h.numel() * 2)},
+        "gpu_launches": args.steps * (STEPS * (kernels_per_forward + 1) + 1),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": round(g_fl / (g_ms * 1e-3) / 1e12, 1), "peak": peak,
+                     "unit": "TFLOP/s", "frac": round(g_fl / (g_ms * 1e-3) / 1e12 / peak, 4), "traffic": None,
+                     "kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of one image)",
+                     "kernel_ms": round(g_ms / max(g_n, 1), 4), "launches": g_n,
+                     "share_of_step": round(g_ms / (g_ms + a_ms), 4), "peak_source": peaks["source"] + " (sustained)",
+                     "attention": {"achieved": round(a_fl / (a_ms * 1e-3) / 1e12, 1), "kernel_ms": round(a_ms / max(a_n, 1), 4),
+                                   "launches": a_n, "share_of_step": round(a_ms / (g_ms + a_ms), 4)}},
+        "cpu_baseline": cpu_baseline(),
+    }
+    return out
+
+
+def _time_oracle_block(n_double: int, n_single: int, s_img: int, seed: int):
+    """Seconds for one oracle forward with the given block counts at full width / sequence (fp32 CPU)."""
+    import torch
+
+    from oracle import flux as OF
+    cfg = OF.FluxConfig(in_channels=384, d=D, heads=HEADS, n_double=n_double, n_single=n_single)
+    p = OF.init_params(cfg, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(1, s_img, 384, generator=g)
+    ctx = torch.randn(1, S_TXT, 4096, generator=g)
+    pooled = torch.randn(1, 768, generator=g)
+    t, gd = torch.tensor([0.7]), torch.tensor([GUIDANCE])
+    ids, tids = OF.image_ids(int(s_img ** 0.5), int(s_img ** 0.5)), torch.zeros(S_TXT, 3)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        OF.flux_forward(p, cfg, x, ctx, pooled, t, gd, ids, tids)
+        return time.perf_counter() - t0
+
+
+def cpu_baseline():
+    """Oracle on the host cores, bounded sample: ONE double block and ONE single block at full width and
+    full sequence (d=3072, S=5337), extrapolated to 19 + 38 blocks x 50 steps (embedders < 0.1 %)."""
+    import torch
+    torch.set_num_threads(os.cpu_count())
+    s_img = (HEIGHT // 16) * (WIDTH // 16)
+    base = _time_oracle_block(0, 0, s_img, 1)
+    t_d = max(_time_oracle_block(1, 0, s_img, 2) - base, 1e-6)
+    t_s = max(_time_oracle_block(0, 1, s_img, 3) - base, 1e-6)
+    per_image = STEPS * (N_DOUBLE * t_d + N_SINGLE * t_s + base)
+    return {"value": round(1.0 / per_image, 8), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"oracle.flux_forward fp32: 1 double block ({t_d:.2f} s) + 1 single block ({t_s:.2f} s) at "
+                      f"d=3072, S=5337, extrapolated x19/x38 x50 steps (a full image is ~{per_image / 3600:.1f} h)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    cb = None
+    vals = []
+    for _ in range(max(1, min(args.steps, 2))):
+        cb = cpu_baseline()
+        vals.append(cb["value"])
+    val = sum(vals) / len(vals)
+    cb["value"] = val
+    return {"impl": "reference", "metric": "composed images/sec (1024^2, 50-step Flux-Redux, device-timed)",
+            "value": val, "unit": "images/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(1e3 / val, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C4 per-GPU slice: Flux-Redux composition 1024^2, 50 steps, batch 1 "
+                                   "(CPU oracle, extrapolated from one double + one single block per step sample)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

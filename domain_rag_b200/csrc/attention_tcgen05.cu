@@ -25,33 +25,44 @@ namespace drag {
 
 constexpr int AT_THREADS = 192;
 constexpr int AT_TILE = 128;
-constexpr int AT_HD = 128;
 constexpr int AT_HALF_BYTES = AT_TILE * 64 * 2;        // 16 KB: 128 rows x 64 bf16
-constexpr int AT_TILE_BYTES = 2 * AT_HALF_BYTES;       // 32 KB
-constexpr int AT_Q_OFF = 0;
-constexpr int AT_K_OFF = AT_TILE_BYTES;
-constexpr int AT_V_OFF = AT_K_OFF + 2 * AT_TILE_BYTES;
-constexpr int AT_P_OFF = AT_V_OFF + 2 * AT_TILE_BYTES;
-constexpr int AT_BAR_OFF = AT_P_OFF + AT_TILE_BYTES;
-constexpr int AT_SMEM = AT_BAR_OFF + 256 + 1024;
 constexpr float AT_RESCALE_THRESHOLD = 8.0f;           // log2 domain
+
+// Head dim HD = 128 (Flux) or 64 (CLIP ViT): tiles are HD/64 swizzled halves of 128 rows x 64 bf16.
+template <int HD>
+struct AttnCfg {
+    static constexpr int NH = HD / 64;
+    static constexpr int TILE_BYTES = NH * AT_HALF_BYTES;          // Q / K / V tile
+    static constexpr int P_BYTES = 2 * AT_HALF_BYTES;              // P is always 128 x 128
+    static constexpr int Q_OFF = 0;
+    static constexpr int K_OFF = TILE_BYTES;
+    static constexpr int V_OFF = K_OFF + 2 * TILE_BYTES;
+    static constexpr int P_OFF = V_OFF + 2 * TILE_BYTES;
+    static constexpr int BAR_OFF = P_OFF + P_BYTES;
+    static constexpr int SMEM = BAR_OFF + 256 + 1024;
+};
 
 struct AttnArgs {
     __nv_bfloat16* out0;   // tokens [0, split): row b*split + s, leading dim ld0
     __nv_bfloat16* out1;   // tokens [split, S): row b*(S-split) + s-split, leading dim ld1
     int ld0, ld1, split;
     int S, H;
-    float scale_log2;      // log2(e) / sqrt(128)
+    float scale_log2;      // log2(e) / sqrt(head_dim)
     uint32_t v_lbo, v_sbo; // MN-major V descriptor strides (bytes)
 };
 
+template <int HD>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, AttnArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_BAR_OFF);
+    using Cfg = AttnCfg<HD>;
+    constexpr int AT_HD = HD;
+    constexpr int AT_TILE_BYTES = Cfg::TILE_BYTES;
+    constexpr int AT_Q_OFF = Cfg::Q_OFF, AT_K_OFF = Cfg::K_OFF, AT_V_OFF = Cfg::V_OFF, AT_P_OFF = Cfg::P_OFF;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
     uint64_t* q_full = bars + 0;
     uint64_t* k_full = bars + 1;    // [2]
     uint64_t* k_empty = bars + 3;   // [2]
@@ -97,20 +108,23 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     if (warp == 0 && lane == 0) {
         // ------------------------------------------------------------------ TMA producer
         mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
-        tma_load_3d(smem + AT_Q_OFF, &tmQ, 0, q0, bh, q_full);
-        tma_load_3d(smem + AT_Q_OFF + AT_HALF_BYTES, &tmQ, 64, q0, bh, q_full);
+#pragma unroll
+        for (int hf = 0; hf < Cfg::NH; ++hf)
+            tma_load_3d(smem + AT_Q_OFF + hf * AT_HALF_BYTES, &tmQ, hf * 64, q0, bh, q_full);
         for (int j = 0; j < n_tiles; ++j) {
             const int st = j & 1, par = (j >> 1) & 1;
             uint8_t* kd = smem + AT_K_OFF + st * AT_TILE_BYTES;
             uint8_t* vd = smem + AT_V_OFF + st * AT_TILE_BYTES;
             mbar_wait(&k_empty[st], par ^ 1);
             mbar_arrive_expect_tx(&k_full[st], AT_TILE_BYTES);
-            tma_load_3d(kd, &tmK, 0, j * AT_TILE, bh, &k_full[st]);
-            tma_load_3d(kd + AT_HALF_BYTES, &tmK, 64, j * AT_TILE, bh, &k_full[st]);
+#pragma unroll
+            for (int hf = 0; hf < Cfg::NH; ++hf)
+                tma_load_3d(kd + hf * AT_HALF_BYTES, &tmK, hf * 64, j * AT_TILE, bh, &k_full[st]);
             mbar_wait(&v_empty[st], par ^ 1);
             mbar_arrive_expect_tx(&v_full[st], AT_TILE_BYTES);
-            tma_load_3d(vd, &tmV, 0, j * AT_TILE, bh, &v_full[st]);
-            tma_load_3d(vd + AT_HALF_BYTES, &tmV, 64, j * AT_TILE, bh, &v_full[st]);
+#pragma unroll
+            for (int hf = 0; hf < Cfg::NH; ++hf)
+                tma_load_3d(vd + hf * AT_HALF_BYTES, &tmV, hf * 64, j * AT_TILE, bh, &v_full[st]);
         }
     } else if (warp == 1 && lane == 0) {
         // ------------------------------------------------------------------ MMA issuer
@@ -146,7 +160,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             for (int ks = 0; ks < AT_TILE / 16; ++ks) {
                 const uint64_t pd = umma_desc_k_sw128(p_addr + (ks >> 2) * AT_HALF_BYTES + (ks & 3) * 32);
 #pragma unroll
-                for (int nh = 0; nh < 2; ++nh) {
+                for (int nh = 0; nh < Cfg::NH; ++nh) {
                     // V half nh: [128 kv rows][64 hd], 128-byte rows; 16 kv rows per k-step = 2048 B
                     const uint64_t vdsc = umma_desc_mn_sw128(v_addr + nh * AT_HALF_BYTES + ks * 2048, a.v_lbo, a.v_sbo);
                     tc_mma_f16(tmem_base + 256 + nh * 64, pd, vdsc, idesc_pv, (j | ks) != 0);
@@ -189,7 +203,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     tc_fence_after();
                     waited = true;
 #pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < HD / 32; ++c) {
                         uint32_t v[32];
                         tmem_ld_32x32(t_lane + 256 + c * 32, v);
                         tmem_ld_wait();
@@ -245,7 +259,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             ? a.out0 + (static_cast<size_t>(b) * a.split + srow) * a.ld0 + h * AT_HD
             : a.out1 + (static_cast<size_t>(b) * (a.S - a.split) + (srow - a.split)) * a.ld1 + h * AT_HD;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < HD / 32; ++c) {
             uint32_t v[32];
             tmem_ld_32x32(t_lane + 256 + c * 32, v);
             tmem_ld_wait();
@@ -277,37 +291,49 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 // Debug knob (drag_debug_set): MN-major V descriptor strides.
 uint32_t g_attn_v_lbo = 0, g_attn_v_sbo = 1024;
 
-int attention_bf16(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int B, int H, int S,
-                   int split, __nv_bfloat16* out0, int ld0, __nv_bfloat16* out1, int ld1, cudaStream_t st) {
-    DRAG_REQUIRE(q && k && v, "attention: null pointer");
-    DRAG_REQUIRE(B >= 1 && H >= 1 && S >= 1 && split >= 0 && split <= S, "attention: bad sizes");
-    DRAG_REQUIRE((split == 0 || out0) && (split == S || out1), "attention: null output");
-    DRAG_REQUIRE(ld0 % 8 == 0 && ld1 % 8 == 0, "attention: output leading dims must be multiples of 8");
+template <int HD>
+static int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int B, int H, int S,
+                            AttnArgs a, cudaStream_t st) {
+    using Cfg = AttnCfg<HD>;
     CUtensorMap tq, tk, tv;
     const uint64_t bh = static_cast<uint64_t>(B) * H;
-    int rc = make_tmap_bf16_3d(&tq, q, AT_HD, S, bh, AT_HD, static_cast<uint64_t>(S) * AT_HD, 64, AT_TILE);
+    int rc = make_tmap_bf16_3d(&tq, q, HD, S, bh, HD, static_cast<uint64_t>(S) * HD, 64, AT_TILE);
     if (rc) return rc;
-    rc = make_tmap_bf16_3d(&tk, k, AT_HD, S, bh, AT_HD, static_cast<uint64_t>(S) * AT_HD, 64, AT_TILE);
+    rc = make_tmap_bf16_3d(&tk, k, HD, S, bh, HD, static_cast<uint64_t>(S) * HD, 64, AT_TILE);
     if (rc) return rc;
-    rc = make_tmap_bf16_3d(&tv, v, AT_HD, S, bh, AT_HD, static_cast<uint64_t>(S) * AT_HD, 64, AT_TILE);
+    rc = make_tmap_bf16_3d(&tv, v, HD, S, bh, HD, static_cast<uint64_t>(S) * HD, 64, AT_TILE);
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        DRAG_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+        DRAG_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM));
         attr_set = true;
     }
+    a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+    dim3 grid((S + AT_TILE - 1) / AT_TILE, static_cast<unsigned>(bh));
+    const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * H * static_cast<double>(S) * S * HD, st);
+    attention_tcgen05_kernel<HD><<<grid, AT_THREADS, Cfg::SMEM, st>>>(tq, tk, tv, a);
+    prof_end(slot, st);
+    DRAG_CUDA(cudaGetLastError());
+    return DRAG_OK;
+}
+
+int attention_bf16(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int B, int H, int S,
+                   int head_dim, int split, __nv_bfloat16* out0, int ld0, __nv_bfloat16* out1, int ld1,
+                   cudaStream_t st) {
+    DRAG_REQUIRE(q && k && v, "attention: null pointer");
+    DRAG_REQUIRE(head_dim == 64 || head_dim == 128, "attention: head_dim must be 64 or 128");
+    DRAG_REQUIRE(B >= 1 && H >= 1 && S >= 1 && split >= 0 && split <= S, "attention: bad sizes");
+    DRAG_REQUIRE((split == 0 || out0) && (split == S || out1), "attention: null output");
+    DRAG_REQUIRE(ld0 % 8 == 0 && ld1 % 8 == 0, "attention: output leading dims must be multiples of 8");
     AttnArgs a;
     a.out0 = out0; a.out1 = out1; a.ld0 = ld0; a.ld1 = ld1; a.split = split;
     a.S = S;
     a.H = H;
-    a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(AT_HD));
+    a.scale_log2 = 0.f;
     a.v_lbo = g_attn_v_lbo; a.v_sbo = g_attn_v_sbo;
-    dim3 grid((S + AT_TILE - 1) / AT_TILE, static_cast<unsigned>(bh));
-    const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * H * static_cast<double>(S) * S * AT_HD, st);
-    attention_tcgen05_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, a);
-    prof_end(slot, st);
-    DRAG_CUDA(cudaGetLastError());
-    return DRAG_OK;
+    if (head_dim == 128) return launch_attention<128>(q, k, v, B, H, S, a, st);
+    return launch_attention<64>(q, k, v, B, H, S, a, st);
 }
 
 }  // namespace drag

@@ -278,9 +278,9 @@ int drag_gemm_qkv_rope(const void* A, int lda, const void* W, int ldw, int M, in
 #define BFM(p) static_cast<__nv_bfloat16*>(p)
 #define ST(p) reinterpret_cast<cudaStream_t>(p)
 
-int drag_attention_bf16(const void* q, const void* k, const void* v, int B, int H, int S, int split, void* out0,
-                        int ld0, void* out1, int ld1, void* stream) {
-    return attention_bf16(BF(q), BF(k), BF(v), B, H, S, split, BFM(out0), ld0, BFM(out1), ld1, ST(stream));
+int drag_attention_bf16(const void* q, const void* k, const void* v, int B, int H, int S, int head_dim, int split,
+                        void* out0, int ld0, void* out1, int ld1, void* stream) {
+    return attention_bf16(BF(q), BF(k), BF(v), B, H, S, head_dim, split, BFM(out0), ld0, BFM(out1), ld1, ST(stream));
 }
 int drag_layernorm_bf16(const void* x, int ldx, void* out, int ldo, int M, int d, const void* mul, int mul_ld,
                         const void* add, int add_ld, int adaln, int rows_per_batch, float eps, void* stream) {
@@ -301,6 +301,28 @@ int drag_redux_blend(const void* txt, const void* img, const void* pooled, const
 }
 int drag_l2_normalize(const float* x, float* out, int rows, int d, void* stream) {
     return l2_normalize(x, out, rows, d, ST(stream));
+}
+
+int drag_gemm_qkv_split(const void* A, int lda, const void* W, int ldw, int M, int K, int heads, int head_dim,
+                        const void* bias, void* q_out, void* k_out, void* v_out, int s_total, int tok_offset,
+                        int rows_per_batch, void* stream) {
+    GemmEpi e;
+    e.mode = EPI_QKV_SPLIT;
+    e.bias = BF(bias);
+    e.q_out = BFM(q_out); e.k_out = BFM(k_out); e.v_out = BFM(v_out);
+    e.heads = heads;
+    e.head_dim = head_dim;
+    e.s_total = s_total;
+    e.tok_offset = tok_offset;
+    e.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : (1 << 30);
+    return gemm_bf16(BF(A), lda, BF(W), ldw, M, 3 * heads * head_dim, K, e, ST(stream));
+}
+int drag_vit_patchify(const float* img, void* out, int B, int R, int patch, int kpad, void* stream) {
+    return vit_patchify(img, BFM(out), B, R, patch, kpad, ST(stream));
+}
+int drag_vit_assemble(const void* patch_emb, const void* cls, const void* pos, void* x, int B, int n_patch, int w,
+                      void* stream) {
+    return vit_assemble(BF(patch_emb), BF(cls), BF(pos), BFM(x), B, n_patch, w, ST(stream));
 }
 
 // ------------------------------------------------------------------------------------ flux engine

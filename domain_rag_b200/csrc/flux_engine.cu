@@ -205,7 +205,7 @@ int flux_forward(FluxEngine* e, const __nv_bfloat16* x, int ldx, const __nv_bflo
         FX(layernorm_bf16(e->txt, d, h_txt, d, Mt, d, mt + d, n_mod, mt, n_mod, 1, St, 1e-6f, st));
         FX(qkv_linear(e, h_txt, wt.qkv_w, wt.qkv_b, wt.qnorm, wt.knorm, Mt, St, 0, S, rope_cos, rope_sin, st));
         FX(qkv_linear(e, h_img, wi.qkv_w, wi.qkv_b, wi.qnorm, wi.knorm, Mi, Si, St, S, rope_cos, rope_sin, st));
-        FX(attention_bf16(e->q, e->k, e->v, B, H, S, St, e->attn_txt, d, e->attn_img, d, st));
+        FX(attention_bf16(e->q, e->k, e->v, B, H, S, 128, St, e->attn_txt, d, e->attn_img, d, st));
         // image stream
         FX(gated_linear(e->attn_img, d, wi.out_w, d, Mi, d, wi.out_b, e->img, d, mi + 2 * d, n_mod, Si, st));
         FX(layernorm_bf16(e->img, d, h_img, d, Mi, d, mi + 4 * d, n_mod, mi + 3 * d, n_mod, 1, Si, 1e-6f, st));
@@ -233,7 +233,7 @@ int flux_forward(FluxEngine* e, const __nv_bfloat16* x, int ldx, const __nv_bflo
         FX(layernorm_bf16(e->z, d, e->h, d, M, d, ms + d, n_mod, ms, n_mod, 1, S, 1e-6f, st));
         FX(qkv_linear(e, e->h, w.qkv_w, w.qkv_b, w.qnorm, w.knorm, M, S, 0, S, rope_cos, rope_sin, st));
         FX(linear(e->h, d, w.mlp_w, d, M, 4 * d, w.mlp_b, EPI_GELU_TANH, e->wide + d, 5 * d, st));
-        FX(attention_bf16(e->q, e->k, e->v, B, H, S, 0, nullptr, 8, e->wide, 5 * d, st));
+        FX(attention_bf16(e->q, e->k, e->v, B, H, S, 128, 0, nullptr, 8, e->wide, 5 * d, st));
         FX(gated_linear(e->wide, 5 * d, w.out_w, 5 * d, M, d, w.out_b, e->z, d, ms + 2 * d, n_mod, S, st));
     }
 

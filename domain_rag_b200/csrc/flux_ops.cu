@@ -213,4 +213,59 @@ int l2_normalize(const float* x, float* out, int rows, int d, cudaStream_t st) {
     return DRAG_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------- ViT glue
+// Patch extraction for the stride == kernel conv of the ViT stem (conv1 of OpenAI CLIP's
+// VisionTransformer): img fp32 [B][3][R][R] -> patches bf16 [B*g*g][kpad], column (c, py, px),
+// zero padded from 3*p*p to kpad so the GEMM's K is TMA friendly.
+__global__ void vit_patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int R,
+                                    int p, int g, int kpad) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = static_cast<int64_t>(B) * g * g * kpad;
+    if (i >= total) return;
+    const int col = static_cast<int>(i % kpad);
+    const int64_t row = i / kpad;
+    const int gx = static_cast<int>(row % g), gy = static_cast<int>((row / g) % g), b = static_cast<int>(row / (g * g));
+    float v = 0.f;
+    if (col < 3 * p * p) {
+        const int c = col / (p * p), r2 = col - c * p * p, py = r2 / p, px = r2 - py * p;
+        v = img[((static_cast<size_t>(b) * 3 + c) * R + gy * p + py) * R + gx * p + px];
+    }
+    out[i] = __float2bfloat16(v);
+}
+int vit_patchify(const float* img, __nv_bfloat16* out, int B, int R, int p, int kpad, cudaStream_t st) {
+    DRAG_REQUIRE(img && out && B >= 1 && R % p == 0 && kpad >= 3 * p * p && kpad % 8 == 0, "vit_patchify: bad arguments");
+    const int g = R / p;
+    const int64_t total = static_cast<int64_t>(B) * g * g * kpad;
+    vit_patchify_kernel<<<ceil_div(total, 256), 256, 0, st>>>(img, out, B, R, p, g, kpad);
+    DRAG_CUDA(cudaGetLastError());
+    return DRAG_OK;
+}
+
+// x[b][0] = cls + pos[0]; x[b][1+i] = patch_emb[b][i] + pos[1+i]   (bf16, width w, L = n_patch + 1)
+__global__ void vit_assemble_kernel(const __nv_bfloat16* __restrict__ pe, const __nv_bfloat16* __restrict__ cls,
+                                    const __nv_bfloat16* __restrict__ pos, __nv_bfloat16* __restrict__ x, int B,
+                                    int n_patch, int w) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int L = n_patch + 1, w8 = w / 8;
+    if (i >= static_cast<int64_t>(B) * L * w8) return;
+    const int c = static_cast<int>(i % w8) * 8;
+    const int t = static_cast<int>((i / w8) % L), b = static_cast<int>(i / (static_cast<int64_t>(w8) * L));
+    float a[8], pz[8];
+    if (t == 0) ld8(cls + c, a);
+    else ld8(pe + (static_cast<size_t>(b) * n_patch + t - 1) * w + c, a);
+    ld8(pos + static_cast<size_t>(t) * w + c, pz);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += pz[j];
+    st8(x + (static_cast<size_t>(b) * L + t) * w + c, a);
+}
+int vit_assemble(const __nv_bfloat16* patch_emb, const __nv_bfloat16* cls, const __nv_bfloat16* pos, __nv_bfloat16* x,
+                 int B, int n_patch, int w, cudaStream_t st) {
+    DRAG_REQUIRE(patch_emb && cls && pos && x && B >= 1 && w % 8 == 0, "vit_assemble: bad arguments");
+    const int64_t total = static_cast<int64_t>(B) * (n_patch + 1) * (w / 8);
+    vit_assemble_kernel<<<ceil_div(total, 256), 256, 0, st>>>(patch_emb, cls, pos, x, B, n_patch, w);
+    DRAG_CUDA(cudaGetLastError());
+    return DRAG_OK;
+}
+
 }  // namespace drag

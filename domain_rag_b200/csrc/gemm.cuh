@@ -14,6 +14,7 @@ enum GemmEpiMode : int {
     EPI_GATE_RESID = 4,  // out = resid + gate[b][n] * (acc + bias) (gate == null: plain residual)
     EPI_QKV_ROPE = 5,    // per-head RMSNorm(q,k) + RoPE, scatter to [B][H][S][128]
     EPI_BIAS_F32 = 6,    // out_f32 = acc + bias
+    EPI_QKV_SPLIT = 7,   // acc + bias scattered to q/k/v [B][H][S][head_dim] (no norm / rope; CLIP ViT)
 };
 
 struct GemmEpi {
@@ -37,6 +38,7 @@ struct GemmEpi {
     const float* rope_cos = nullptr;      // [S_total][64]
     const float* rope_sin = nullptr;      // [S_total][64]
     int heads = 0, s_total = 0, tok_offset = 0;
+    int head_dim = 128;                   // EPI_QKV_SPLIT: 64 or 128
     float rms_eps = 1e-6f;
 };
 

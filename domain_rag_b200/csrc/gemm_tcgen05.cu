@@ -111,7 +111,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, float (&v)[32],
             }
         }
     }
-    if (e.mode == EPI_BIAS_F32) {
+    if (e.mode == EPI_QKV_SPLIT) {
+        // 32-column chunk lies inside one head (head_dim is a multiple of 32)
+        const int hw = e.heads * e.head_dim;
+        const int which = col0 / hw;
+        const int rem = col0 - which * hw;
+        const int head = rem / e.head_dim, c = rem - head * e.head_dim;
+        const int b = row / e.rows_per_batch;
+        const int pos = e.tok_offset + (row - b * e.rows_per_batch);
+        __nv_bfloat16* base = which == 0 ? e.q_out : (which == 1 ? e.k_out : e.v_out);
+        __nv_bfloat16* dst = base + ((static_cast<size_t>(b) * e.heads + head) * e.s_total + pos) * e.head_dim + c;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) store_bf16x8(dst + j, &v[j]);
+    } else if (e.mode == EPI_BIAS_F32) {
         float* dst = e.out_f32 + static_cast<size_t>(row) * e.ldo + col0;
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
@@ -402,6 +414,11 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
         DRAG_REQUIRE(epi.q_out && epi.k_out && epi.v_out && epi.rope_cos && epi.rope_sin && epi.q_norm_w &&
                          epi.k_norm_w, "gemm qkv epilogue: null pointer");
         bn = (N % 256 == 0) ? 256 : 128;
+    } else if (epi.mode == EPI_QKV_SPLIT) {
+        DRAG_REQUIRE((epi.head_dim == 64 || epi.head_dim == 128) && N == 3 * epi.heads * epi.head_dim,
+                     "gemm qkv-split epilogue: N must be 3*heads*head_dim");
+        DRAG_REQUIRE(epi.q_out && epi.k_out && epi.v_out, "gemm qkv-split epilogue: null pointer");
+        if (N % 256 != 0 || N <= 256) bn = (N % 128 == 0 && N > 128) ? 128 : 64;
     } else {
         DRAG_REQUIRE(epi.out || epi.out_f32, "gemm: null output");
         if (N % 256 != 0 || N <= 256) bn = (N % 128 == 0 && N > 128) ? 128 : 64;

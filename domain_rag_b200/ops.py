@@ -48,15 +48,15 @@ def qkv_rope(a, w, bias, q_out, k_out, v_out, q_norm_w, k_norm_w, rope_cos, rope
 
 
 def attention(q, k, v, split=0, out0=None, out1=None):
-    """q,k,v bf16 [B,H,S,128] -> (out0 [B*split, H*128] or None, out1 [B*(S-split), H*128])."""
+    """q,k,v bf16 [B,H,S,hd] (hd 64 or 128) -> (out0 [B*split, H*hd] or None, out1 [B*(S-split), H*hd])."""
     B, H, S, hd = q.shape
-    assert hd == 128 and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+    assert hd in (64, 128) and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
     if split > 0 and out0 is None:
-        out0 = torch.empty((B * split, H * 128), dtype=torch.bfloat16, device=q.device)
+        out0 = torch.empty((B * split, H * hd), dtype=torch.bfloat16, device=q.device)
     if split < S and out1 is None:
-        out1 = torch.empty((B * (S - split), H * 128), dtype=torch.bfloat16, device=q.device)
+        out1 = torch.empty((B * (S - split), H * hd), dtype=torch.bfloat16, device=q.device)
     _lib.check(_lib.load().drag_attention_bf16(
-        _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), B, H, S, split, _lib.ptr(out0), out0.stride(0) if out0 is not None else 8,
+        _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), B, H, S, hd, split, _lib.ptr(out0), out0.stride(0) if out0 is not None else 8,
         _lib.ptr(out1), out1.stride(0) if out1 is not None else 8, _lib.current_stream_ptr(q.device)),
         "drag_attention_bf16")
     return out0, out1

@@ -92,11 +92,11 @@ int drag_gemm_qkv_rope(const void* A, int lda, const void* W, int ldw, int M, in
                        int rows_per_batch, float rms_eps, void* stream);
 
 /* ---- attention / row kernels of the Flux and ViT paths ------------------------------------------
- * Non-causal attention, head dim 128 (F.scaled_dot_product_attention in the diffusers Flux blocks):
- * q,k,v bf16 [B][H][S][128]; token s < split is written to out0 row (b*split+s), token s >= split to out1
- * row (b*(S-split)+s-split); head h occupies columns [h*128,(h+1)*128) of a row with leading dim ld0/ld1. */
-int drag_attention_bf16(const void* q, const void* k, const void* v, int B, int H, int S, int split, void* out0,
-                        int ld0, void* out1, int ld1, void* stream);
+ * Non-causal attention, head_dim 128 (F.scaled_dot_product_attention in the diffusers Flux blocks) or 64
+ * (nn.MultiheadAttention in OpenAI CLIP's ViT): q,k,v bf16 [B][H][S][head_dim]; token s < split is written to out0 row (b*split+s), token s >= split to out1
+ * row (b*(S-split)+s-split); head h occupies columns [h*head_dim,(h+1)*head_dim) of a row with leading dim ld0/ld1. */
+int drag_attention_bf16(const void* q, const void* k, const void* v, int B, int H, int S, int head_dim, int split,
+                        void* out0, int ld0, void* out1, int ld1, void* stream);
 /* out = LayerNorm(x) (no affine, eps) then * (1 + mul[b]) + add[b] when adaln = 1 (AdaLN modulate, b =
  * row / rows_per_batch, per-batch vectors with stride mul_ld / add_ld), or * mul + add per channel when
  * adaln = 0 (plain affine LayerNorm; either pointer may be NULL). bf16, d % 8 == 0. */
@@ -113,6 +113,18 @@ int drag_redux_blend(const void* txt, const void* img, const void* pooled, const
                      int pooled_dim, void* stream);
 /* out[r] = x[r] / ||x[r]||_2, fp32 (image_embedding / image_embedding.norm(dim=-1), retrieval...:172). */
 int drag_l2_normalize(const float* x, float* out, int rows, int d, void* stream);
+
+/* ---- CLIP ViT image encoder pieces (model.encode_image, retrieval/clip100_resnet_style_all_shots.py:171) ---
+ * QKV projection scattered head-major for the attention kernel: q/k/v_out bf16 [B][heads][s_total][head_dim]. */
+int drag_gemm_qkv_split(const void* A, int lda, const void* W, int ldw, int M, int K, int heads, int head_dim,
+                        const void* bias, void* q_out, void* k_out, void* v_out, int s_total, int tok_offset,
+                        int rows_per_batch, void* stream);
+/* conv1 (kernel == stride == patch, no bias) as patch extraction + GEMM: img fp32 [B][3][R][R] ->
+ * bf16 [B*(R/patch)^2][kpad], columns (c, py, px) zero padded to kpad (multiple of 8). */
+int drag_vit_patchify(const float* img, void* out, int B, int R, int patch, int kpad, void* stream);
+/* x[b][0] = class_embedding + pos[0]; x[b][1+i] = patch_emb[b][i] + pos[1+i]  (bf16 [B][n_patch+1][w]). */
+int drag_vit_assemble(const void* patch_emb, const void* cls, const void* pos, void* x, int B, int n_patch, int w,
+                      void* stream);
 
 /* ---- Flux MMDiT engine --------------------------------------------------------------------------
  * One FluxTransformer2DModel.forward per call (the denoising step inside pipe(...) /
