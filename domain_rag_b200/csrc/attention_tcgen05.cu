@@ -1,19 +1,24 @@
-// Non-causal joint (text + image) attention for the Flux MMDiT blocks, head dim 128, on tcgen05.
-//   out[b][s][h*128 + :] = softmax(q k^T / sqrt(128)) v      q,k,v bf16 [B][H][S][128]
-// (F.scaled_dot_product_attention inside diffusers' Flux attention processor, reached from
-//  pipe(...) at batch_generate_flux_kshot.py:467-474 / outpainting_updown_sampling_redux.py:1246-1257.)
+// Non-causal attention for the Flux MMDiT blocks (head dim 128, joint text+image sequence) and the
+// CLIP ViT blocks (head dim 64) on tcgen05:   out = softmax(q k^T / sqrt(hd)) v,  q,k,v bf16 [B][H][S][hd]
+// (F.scaled_dot_product_attention inside diffusers' Flux attention processor, reached from pipe(...) at
+//  batch_generate_flux_kshot.py:467-474 / outpainting_updown_sampling_redux.py:1246-1257; and
+//  nn.MultiheadAttention inside clip.encode_image, retrieval/clip100_resnet_style_all_shots.py:171.)
 //
-// One CTA per (128-query tile, batch*head); flash-attention style loop over 128-key tiles:
-//   warp 0   TMA: Q once, K/V tiles into 2-stage rings (3-D tensor maps, SWIZZLE_128B, rows past
-//            the sequence end are zero-filled by TMA);
-//   warp 1   MMA issuer: S[j%2] = Q K_j^T (UMMA 128x128x16, both operands K-major) into one of two
-//            TMEM score buffers, so QK^T of tile j+1 overlaps the softmax of tile j; then
-//            O += P_j V_j (UMMA 128x64x16 twice per k-step, V consumed MN-major straight from the
-//            row-major tile - no transpose);
-//   warps 2-5 softmax: thread = query row. tcgen05.ld the score row, online max/sum in the exp2
-//            domain, lazy rescale of the TMEM-resident O (only when the running max grows by > 8),
-//            P written to shared memory as bf16 in the swizzled K-major layout the MMA reads.
-// TMEM: S0 [0,128) S1 [128,256) O [256,384).
+// One CTA per (256-query block, batch*head) = two 128-row query tiles A and B that ping-pong on the
+// tensor core, flash-attention style loop over 128-key tiles shared by both:
+//   warp 0        TMA: Q_A, Q_B once; K/V tiles into 2-stage rings (3-D tensor maps, SWIZZLE_128B, rows
+//                 past the sequence end zero-filled by TMA);
+//   warp 1        MMA issuer (one thread): S_X = Q_X K_j^T (UMMA 128x128x16, SS) into TMEM, and
+//                 O_X += P_X V_j with P read straight from TMEM (TS form) and V consumed MN-major from
+//                 its row-major tile (UMMA 128x64x16 per 64-wide half of the head dim);
+//   warps 4-7 / 8-11  softmax warpgroup of tile A / B: thread = query row. Pass 1 reads the score row
+//                 from TMEM for the running max, lazy rescale of the TMEM-resident O (only when the max
+//                 grew by > 8 in the exp2 domain), pass 2 re-reads the scores, exponentiates and writes
+//                 P as packed bf16 IN PLACE over the first 64 columns of its own S buffer.
+// While one warpgroup does softmax the tensor core works for the other tile. The tensor pipe executes
+// MMAs in issue order, so S_X(j+1) = Q_X K_{j+1}^T may be issued right after O_X += P_X(j) V_j even
+// though it overwrites P_X(j).
+// TMEM columns: S_A/P_A [0,128)  S_B/P_B [128,256)  O_A [256,256+hd)  O_B [384,384+hd).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -23,22 +28,20 @@
 
 namespace drag {
 
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 384;                        // 12 warps (warps 2,3 idle: keeps the softmax
+                                                       // warpgroups aligned to TMEM lane quarters)
 constexpr int AT_TILE = 128;
 constexpr int AT_HALF_BYTES = AT_TILE * 64 * 2;        // 16 KB: 128 rows x 64 bf16
 constexpr float AT_RESCALE_THRESHOLD = 8.0f;           // log2 domain
 
-// Head dim HD = 128 (Flux) or 64 (CLIP ViT): tiles are HD/64 swizzled halves of 128 rows x 64 bf16.
 template <int HD>
 struct AttnCfg {
     static constexpr int NH = HD / 64;
-    static constexpr int TILE_BYTES = NH * AT_HALF_BYTES;          // Q / K / V tile
-    static constexpr int P_BYTES = 2 * AT_HALF_BYTES;              // P is always 128 x 128
-    static constexpr int Q_OFF = 0;
-    static constexpr int K_OFF = TILE_BYTES;
-    static constexpr int V_OFF = K_OFF + 2 * TILE_BYTES;
-    static constexpr int P_OFF = V_OFF + 2 * TILE_BYTES;
-    static constexpr int BAR_OFF = P_OFF + P_BYTES;
+    static constexpr int TILE_BYTES = NH * AT_HALF_BYTES;          // one Q / K / V tile
+    static constexpr int Q_OFF = 0;                                // Q_A, Q_B
+    static constexpr int K_OFF = 2 * TILE_BYTES;                   // 2 stages
+    static constexpr int V_OFF = K_OFF + 2 * TILE_BYTES;           // 2 stages
+    static constexpr int BAR_OFF = V_OFF + 2 * TILE_BYTES;
     static constexpr int SMEM = BAR_OFF + 256 + 1024;
 };
 
@@ -48,36 +51,49 @@ struct AttnArgs {
     int ld0, ld1, split;
     int S, H;
     float scale_log2;      // log2(e) / sqrt(head_dim)
-    uint32_t v_lbo, v_sbo; // MN-major V descriptor strides (bytes)
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// registers -> TMEM, 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
 
 template <int HD>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, AttnArgs a) {
+    using Cfg = AttnCfg<HD>;
+    constexpr int TILE_BYTES = Cfg::TILE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-    using Cfg = AttnCfg<HD>;
-    constexpr int AT_HD = HD;
-    constexpr int AT_TILE_BYTES = Cfg::TILE_BYTES;
-    constexpr int AT_Q_OFF = Cfg::Q_OFF, AT_K_OFF = Cfg::K_OFF, AT_V_OFF = Cfg::V_OFF, AT_P_OFF = Cfg::P_OFF;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
     uint64_t* q_full = bars + 0;
     uint64_t* k_full = bars + 1;    // [2]
     uint64_t* k_empty = bars + 3;   // [2]
     uint64_t* v_full = bars + 5;    // [2]
     uint64_t* v_empty = bars + 7;   // [2]
-    uint64_t* s_full = bars + 9;    // [2]
-    uint64_t* s_empty = bars + 11;  // [2]
-    uint64_t* p_full = bars + 13;
-    uint64_t* pv_done = bars + 14;
+    uint64_t* s_full = bars + 9;    // [2] per query tile
+    uint64_t* p_full = bars + 11;   // [2]
+    uint64_t* pv_done = bars + 13;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * AT_TILE;
+    const int q0 = blockIdx.x * 2 * AT_TILE;
     const int bh = blockIdx.y;
     const int n_tiles = (a.S + AT_TILE - 1) / AT_TILE;
+    const bool has_b = (q0 + AT_TILE) < a.S;           // second query tile holds at least one row
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmQ);
@@ -90,10 +106,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             mbar_init(&v_full[i], 1);
             mbar_init(&v_empty[i], 1);
             mbar_init(&s_full[i], 1);
-            mbar_init(&s_empty[i], 4);
+            mbar_init(&p_full[i], 4);
+            mbar_init(&pv_done[i], 1);
         }
-        mbar_init(p_full, 4);
-        mbar_init(pv_done, 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -107,21 +122,24 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
     if (warp == 0 && lane == 0) {
         // ------------------------------------------------------------------ TMA producer
-        mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
+        mbar_arrive_expect_tx(q_full, (has_b ? 2 : 1) * TILE_BYTES);
 #pragma unroll
-        for (int hf = 0; hf < Cfg::NH; ++hf)
-            tma_load_3d(smem + AT_Q_OFF + hf * AT_HALF_BYTES, &tmQ, hf * 64, q0, bh, q_full);
+        for (int hf = 0; hf < Cfg::NH; ++hf) {
+            tma_load_3d(smem + Cfg::Q_OFF + hf * AT_HALF_BYTES, &tmQ, hf * 64, q0, bh, q_full);
+            if (has_b)
+                tma_load_3d(smem + Cfg::Q_OFF + TILE_BYTES + hf * AT_HALF_BYTES, &tmQ, hf * 64, q0 + AT_TILE, bh, q_full);
+        }
         for (int j = 0; j < n_tiles; ++j) {
             const int st = j & 1, par = (j >> 1) & 1;
-            uint8_t* kd = smem + AT_K_OFF + st * AT_TILE_BYTES;
-            uint8_t* vd = smem + AT_V_OFF + st * AT_TILE_BYTES;
+            uint8_t* kd = smem + Cfg::K_OFF + st * TILE_BYTES;
+            uint8_t* vd = smem + Cfg::V_OFF + st * TILE_BYTES;
             mbar_wait(&k_empty[st], par ^ 1);
-            mbar_arrive_expect_tx(&k_full[st], AT_TILE_BYTES);
+            mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
 #pragma unroll
             for (int hf = 0; hf < Cfg::NH; ++hf)
                 tma_load_3d(kd + hf * AT_HALF_BYTES, &tmK, hf * 64, j * AT_TILE, bh, &k_full[st]);
             mbar_wait(&v_empty[st], par ^ 1);
-            mbar_arrive_expect_tx(&v_full[st], AT_TILE_BYTES);
+            mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
 #pragma unroll
             for (int hf = 0; hf < Cfg::NH; ++hf)
                 tma_load_3d(vd + hf * AT_HALF_BYTES, &tmV, hf * 64, j * AT_TILE, bh, &v_full[st]);
@@ -129,139 +147,166 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     } else if (warp == 1 && lane == 0) {
         // ------------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);   // B (V) is MN-major
-        const uint32_t q_addr = smem_u32(smem + AT_Q_OFF);
-        const uint32_t p_addr = smem_u32(smem + AT_P_OFF);
-        auto issue_qk = [&](int t) {
-            const int st = t & 1, par = (t >> 1) & 1;
-            mbar_wait(&k_full[st], par);
-            mbar_wait(&s_empty[st], par ^ 1);
-            tc_fence_after();
-            const uint32_t k_addr = smem_u32(smem + AT_K_OFF + st * AT_TILE_BYTES);
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);   // A = P from TMEM (K-major), B = V MN-major
+        const uint32_t q_addr = smem_u32(smem + Cfg::Q_OFF);
+        auto issue_qk = [&](int x, int st) {     // S_x = Q_x K^T  (K tile already waited for)
+            const uint32_t k_addr = smem_u32(smem + Cfg::K_OFF + st * TILE_BYTES);
 #pragma unroll
-            for (int ks = 0; ks < AT_HD / 16; ++ks) {
+            for (int ks = 0; ks < HD / 16; ++ks) {
                 const uint32_t off = (ks >> 2) * AT_HALF_BYTES + (ks & 3) * 32;
-                tc_mma_f16(tmem_base + st * 128, umma_desc_k_sw128(q_addr + off), umma_desc_k_sw128(k_addr + off),
-                           idesc_qk, ks != 0);
+                tc_mma_f16(tmem_base + x * 128, umma_desc_k_sw128(q_addr + x * TILE_BYTES + off),
+                           umma_desc_k_sw128(k_addr + off), idesc_qk, ks != 0);
             }
-            tc_commit(&s_full[st]);
-            tc_commit(&k_empty[st]);
+            tc_commit(&s_full[x]);
         };
-        mbar_wait(q_full, 0);
-        issue_qk(0);
-        for (int j = 0; j < n_tiles; ++j) {
-            if (j + 1 < n_tiles) issue_qk(j + 1);
-            const int st = j & 1, par = (j >> 1) & 1;
-            mbar_wait(p_full, j & 1);
-            mbar_wait(&v_full[st], par);
-            tc_fence_after();
-            const uint32_t v_addr = smem_u32(smem + AT_V_OFF + st * AT_TILE_BYTES);
+        auto issue_pv = [&](int x, int st, int j) {   // O_x += P_x V   (P_x: packed bf16 in S_x columns [0,64))
+            const uint32_t v_addr = smem_u32(smem + Cfg::V_OFF + st * TILE_BYTES);
 #pragma unroll
             for (int ks = 0; ks < AT_TILE / 16; ++ks) {
-                const uint64_t pd = umma_desc_k_sw128(p_addr + (ks >> 2) * AT_HALF_BYTES + (ks & 3) * 32);
 #pragma unroll
                 for (int nh = 0; nh < Cfg::NH; ++nh) {
-                    // V half nh: [128 kv rows][64 hd], 128-byte rows; 16 kv rows per k-step = 2048 B
-                    const uint64_t vdsc = umma_desc_mn_sw128(v_addr + nh * AT_HALF_BYTES + ks * 2048, a.v_lbo, a.v_sbo);
-                    tc_mma_f16(tmem_base + 256 + nh * 64, pd, vdsc, idesc_pv, (j | ks) != 0);
+                    // V half nh: [128 kv rows][64 hd], 128-byte rows; 16 kv rows per k-step = 2048 B; SBO = 1024
+                    const uint64_t vdsc = umma_desc_mn_sw128(v_addr + nh * AT_HALF_BYTES + ks * 2048, 0, 1024);
+                    tc_mma_f16_ts(tmem_base + 256 + x * 128 + nh * 64, tmem_base + x * 128 + ks * 8, vdsc, idesc_pv,
+                                  (j | ks) != 0);
                 }
             }
+            tc_commit(&pv_done[x]);
+        };
+        mbar_wait(q_full, 0);
+        mbar_wait(&k_full[0], 0);
+        tc_fence_after();
+        issue_qk(0, 0);
+        if (has_b) issue_qk(1, 0);
+        tc_commit(&k_empty[0]);
+        for (int j = 0; j < n_tiles; ++j) {
+            const int st = j & 1, par = (j >> 1) & 1;
+            const int nst = (j + 1) & 1, npar = ((j + 1) >> 1) & 1;
+            const bool more = (j + 1) < n_tiles;
+            mbar_wait(&p_full[0], j & 1);
+            mbar_wait(&v_full[st], par);
+            tc_fence_after();
+            issue_pv(0, st, j);
+            if (more) {
+                mbar_wait(&k_full[nst], npar);
+                tc_fence_after();
+                issue_qk(0, nst);
+            }
+            if (has_b) {
+                mbar_wait(&p_full[1], j & 1);
+                tc_fence_after();
+                issue_pv(1, st, j);
+                if (more) issue_qk(1, nst);
+            }
             tc_commit(&v_empty[st]);
-            tc_commit(pv_done);
+            if (more) tc_commit(&k_empty[nst]);
         }
-    } else if (warp >= 2) {
+    } else if (warp >= 4 && (warp < 8 || has_b)) {
         // ------------------------------------------------------------------ softmax + epilogue
+        const int x = (warp >= 8) ? 1 : 0;                 // query tile of this warpgroup
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;                 // query row inside the tile
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-        uint8_t* p_row = smem + AT_P_OFF + r * 128;
+        const uint32_t t_s = t_lane + x * 128;             // S / P
+        const uint32_t t_o = t_lane + 256 + x * 128;       // O
         float m = -INFINITY, l = 0.f;
         for (int j = 0; j < n_tiles; ++j) {
-            const int st = j & 1, par = (j >> 1) & 1;
-            mbar_wait(&s_full[st], par);
+            mbar_wait(&s_full[x], j & 1);
             tc_fence_after();
-            const uint32_t t_s = t_lane + st * 128;
             const int kv_valid = a.S - j * AT_TILE;        // columns >= kv_valid are past the sequence end
+            const bool full_tile = kv_valid >= AT_TILE;
             float mx = -INFINITY;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_s + c * 32, v);
                 tmem_ld_wait();
+                if (full_tile) {
+                    float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+                    float m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float sv = (c * 32 + i < kv_valid) ? __uint_as_float(v[i]) : -INFINITY;
-                    mx = fmaxf(mx, sv);
+                    for (int i = 4; i < 32; i += 4) {
+                        m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                        m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+                    }
+                    mx = fmaxf(mx, fmaxf(m0, m1));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
                 }
             }
             const float m_new = fmaxf(m, mx * a.scale_log2);
-            bool waited = false;
             if (__any_sync(0xffffffffu, m_new > m + AT_RESCALE_THRESHOLD)) {
-                const float alpha = exp2f(m - m_new);      // 0 on the first tile (m = -inf)
+                const float alpha = ex2_approx(m - m_new);   // 0 on the first tile (m = -inf)
                 if (j > 0) {
-                    mbar_wait(pv_done, (j - 1) & 1);       // O += P_{j-1} V_{j-1} has landed
+                    mbar_wait(&pv_done[x], (j - 1) & 1);     // O_x += P_x(j-1) V_{j-1} has landed
                     tc_fence_after();
-                    waited = true;
 #pragma unroll 1
                     for (int c = 0; c < HD / 32; ++c) {
                         uint32_t v[32];
-                        tmem_ld_32x32(t_lane + 256 + c * 32, v);
+                        tmem_ld_32x32(t_o + c * 32, v);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                        tmem_st_32x32(t_lane + 256 + c * 32, v);
+                        tmem_st_32x32(t_o + c * 32, v);
                     }
-                    tmem_st_wait();
                 }
                 l *= alpha;
                 m = m_new;
             }
-            if (j > 0 && !waited) mbar_wait(pv_done, (j - 1) & 1);   // P buffer is free again
-            float rowsum = 0.f;
+            const float neg_m = -m;
+            float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_s + c * 32, v);
                 tmem_ld_wait();
                 uint32_t packed[16];
+                if (full_tile) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float p0 = (c * 32 + i < kv_valid) ? exp2f(__uint_as_float(v[i]) * a.scale_log2 - m) : 0.f;
-                    float p1 = (c * 32 + i + 1 < kv_valid) ? exp2f(__uint_as_float(v[i + 1]) * a.scale_log2 - m) : 0.f;
-                    rowsum += p0 + p1;
-                    __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
-                    packed[i >> 1] = *reinterpret_cast<uint32_t*>(&pk);
-                }
-                // kv columns [c*32, c*32+32) -> half c/2, 16-byte chunks (c%2)*4 + g, XOR-swizzled by row
-                uint8_t* dst = p_row + (c >> 1) * AT_HALF_BYTES;
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), a.scale_log2, neg_m));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), a.scale_log2, neg_m));
+                        sum0 += p0;
+                        sum1 += p1;
+                        __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
+                        packed[i >> 1] = *reinterpret_cast<uint32_t*>(&pk);
+                    }
+                } else {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
-                    *reinterpret_cast<uint4*>(dst + chunk * 16) =
-                        make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = (c * 32 + i < kv_valid)
+                                             ? ex2_approx(fmaf(__uint_as_float(v[i]), a.scale_log2, neg_m)) : 0.f;
+                        const float p1 = (c * 32 + i + 1 < kv_valid)
+                                             ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), a.scale_log2, neg_m)) : 0.f;
+                        sum0 += p0;
+                        sum1 += p1;
+                        __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
+                        packed[i >> 1] = *reinterpret_cast<uint32_t*>(&pk);
+                    }
                 }
+                // P columns [16c, 16c+16) overwrite score columns that were already consumed (<= 32c+31)
+                tmem_st_32x16(t_s + c * 16, packed);
             }
-            l += rowsum;
+            l += sum0 + sum1;
+            tmem_st_wait();
             tc_fence_before();
-            fence_proxy_async();           // generic-proxy smem writes -> visible to the MMA (async proxy)
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&s_empty[st]);
-                mbar_arrive(p_full);
-            }
+            if (lane == 0) mbar_arrive(&p_full[x]);
         }
-        mbar_wait(pv_done, (n_tiles - 1) & 1);
+        mbar_wait(&pv_done[x], (n_tiles - 1) & 1);
         tc_fence_after();
         const float inv = 1.f / l;
-        const int srow = q0 + r;
+        const int srow = q0 + x * AT_TILE + r;
         const int b = bh / a.H, h = bh - b * a.H;
         __nv_bfloat16* orow = (srow < a.split)
-            ? a.out0 + (static_cast<size_t>(b) * a.split + srow) * a.ld0 + h * AT_HD
-            : a.out1 + (static_cast<size_t>(b) * (a.S - a.split) + (srow - a.split)) * a.ld1 + h * AT_HD;
+            ? a.out0 + (static_cast<size_t>(b) * a.split + srow) * a.ld0 + h * HD
+            : a.out1 + (static_cast<size_t>(b) * (a.S - a.split) + (srow - a.split)) * a.ld1 + h * HD;
 #pragma unroll 1
         for (int c = 0; c < HD / 32; ++c) {
             uint32_t v[32];
-            tmem_ld_32x32(t_lane + 256 + c * 32, v);
+            tmem_ld_32x32(t_o + c * 32, v);
             tmem_ld_wait();
             if (srow < a.S) {
 #pragma unroll
@@ -288,9 +333,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     }
 }
 
-// Debug knob (drag_debug_set): MN-major V descriptor strides.
-uint32_t g_attn_v_lbo = 0, g_attn_v_sbo = 1024;
-
 template <int HD>
 static int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int B, int H, int S,
                             AttnArgs a, cudaStream_t st) {
@@ -310,13 +352,16 @@ static int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, cons
         attr_set = true;
     }
     a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
-    dim3 grid((S + AT_TILE - 1) / AT_TILE, static_cast<unsigned>(bh));
+    dim3 grid((S + 2 * AT_TILE - 1) / (2 * AT_TILE), static_cast<unsigned>(bh));
     const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * H * static_cast<double>(S) * S * HD, st);
     attention_tcgen05_kernel<HD><<<grid, AT_THREADS, Cfg::SMEM, st>>>(tq, tk, tv, a);
     prof_end(slot, st);
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
+
+// Debug knobs kept for ABI stability (drag_debug_set keys 1/2); unused by the current kernel.
+uint32_t g_attn_v_lbo = 0, g_attn_v_sbo = 1024;
 
 int attention_bf16(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int B, int H, int S,
                    int head_dim, int split, __nv_bfloat16* out0, int ld0, __nv_bfloat16* out1, int ld1,
@@ -331,7 +376,6 @@ int attention_bf16(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bf
     a.S = S;
     a.H = H;
     a.scale_log2 = 0.f;
-    a.v_lbo = g_attn_v_lbo; a.v_sbo = g_attn_v_sbo;
     if (head_dim == 128) return launch_attention<128>(q, k, v, B, H, S, a, st);
     return launch_attention<64>(q, k, v, B, H, S, a, st);
 }
