@@ -59,6 +59,32 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// 2^x for x <= ~8 on the FMA/ALU pipes: x = n + f with n = round(x), f in [-0.5, 0.5];
+// 2^f by a cubic with max relative error 1.0e-4 (bf16 P has 2^-9), 2^n by adding n to the exponent field.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -125.f);
+    const float t = x + 12582912.f;                    // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+    const float f = x - (t - 12582912.f);
+    float p = fmaf(0.05500871315598488f, f, 0.24221068620681763f);
+    p = fmaf(p, f, 0.6932829022407532f);
+    p = fmaf(p, f, 1.0f);
+    return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// Register re-balancing between warpgroups (all four warps of a warpgroup execute it).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // registers -> TMEM, 32 lanes x 16 columns
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
     asm volatile(
@@ -119,6 +145,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+
+    // register re-balancing: the data-movement warpgroup gives registers to the two softmax warpgroups
+    if (warp < 4) {
+    setmaxnreg_dec<96>();
 
     if (warp == 0 && lane == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -201,7 +231,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             tc_commit(&v_empty[st]);
             if (more) tc_commit(&k_empty[nst]);
         }
-    } else if (warp >= 4 && (warp < 8 || has_b)) {
+    }
+    } else {
+    setmaxnreg_inc<208>();
+    if (warp < 8 || has_b) {
         // ------------------------------------------------------------------ softmax + epilogue
         const int x = (warp >= 8) ? 1 : 0;                 // query tile of this warpgroup
         const int quarter = warp & 3;
@@ -214,29 +247,24 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             mbar_wait(&s_full[x], j & 1);
             tc_fence_after();
             const int kv_valid = a.S - j * AT_TILE;        // columns >= kv_valid are past the sequence end
-            const bool full_tile = kv_valid >= AT_TILE;
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(t_s + c * 32, v);
-                tmem_ld_wait();
-                if (full_tile) {
-                    float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
-                    float m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+            // the whole 128-wide score row of this thread in registers: ONE TMEM pass per key tile
+            uint32_t v[AT_TILE];
 #pragma unroll
-                    for (int i = 4; i < 32; i += 4) {
-                        m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-                        m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
-                    }
-                    mx = fmaxf(mx, fmaxf(m0, m1));
-                } else {
+            for (int c = 0; c < AT_TILE; c += 32) tmem_ld_32x32_ptr(t_s + c, &v[c]);
+            tmem_ld_wait();
+            if (kv_valid < AT_TILE) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-                }
+                for (int i = 0; i < AT_TILE; ++i)
+                    if (i >= kv_valid) v[i] = 0xff800000u;   // -inf: exp2 -> 0, never the maximum
             }
-            const float m_new = fmaxf(m, mx * a.scale_log2);
+            float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+            float m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+#pragma unroll
+            for (int i = 4; i < AT_TILE; i += 4) {
+                m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            }
+            const float m_new = fmaxf(m, fmaxf(m0, m1) * a.scale_log2);
             if (__any_sync(0xffffffffu, m_new > m + AT_RESCALE_THRESHOLD)) {
                 const float alpha = ex2_approx(m - m_new);   // 0 on the first tile (m = -inf)
                 if (j > 0) {
@@ -244,12 +272,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     tc_fence_after();
 #pragma unroll 1
                     for (int c = 0; c < HD / 32; ++c) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_o + c * 32, v);
+                        uint32_t o[32];
+                        tmem_ld_32x32(t_o + c * 32, o);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                        tmem_st_32x32(t_o + c * 32, v);
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st_32x32(t_o + c * 32, o);
                     }
                 }
                 l *= alpha;
@@ -257,37 +285,24 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             }
             const float neg_m = -m;
             float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(t_s + c * 32, v);
-                tmem_ld_wait();
+            // P as packed bf16 written IN PLACE over the first 64 columns of S. One exponential in four runs
+            // as a Cody-Waite + cubic polynomial on the FMA pipe, the rest on the MUFU pipe (exp2 is the
+            // co-bottleneck of the tensor core at head dim 128).
+#pragma unroll
+            for (int c = 0; c < AT_TILE; c += 32) {
                 uint32_t packed[16];
-                if (full_tile) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), a.scale_log2, neg_m));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), a.scale_log2, neg_m));
-                        sum0 += p0;
-                        sum1 += p1;
-                        __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
-                        packed[i >> 1] = *reinterpret_cast<uint32_t*>(&pk);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float p0 = (c * 32 + i < kv_valid)
-                                             ? ex2_approx(fmaf(__uint_as_float(v[i]), a.scale_log2, neg_m)) : 0.f;
-                        const float p1 = (c * 32 + i + 1 < kv_valid)
-                                             ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), a.scale_log2, neg_m)) : 0.f;
-                        sum0 += p0;
-                        sum1 += p1;
-                        __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
-                        packed[i >> 1] = *reinterpret_cast<uint32_t*>(&pk);
-                    }
+                for (int i = 0; i < 32; i += 2) {
+                    const float x0 = fmaf(__uint_as_float(v[c + i]), a.scale_log2, neg_m);
+                    const float x1 = fmaf(__uint_as_float(v[c + i + 1]), a.scale_log2, neg_m);
+                    const float p0 = ex2_approx(x0);
+                    const float p1 = ((i & 2) == 2) ? ex2_poly(x1) : ex2_approx(x1);
+                    sum0 += p0;
+                    sum1 += p1;
+                    __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
+                    packed[i >> 1] = *reinterpret_cast<uint32_t*>(&pk);
                 }
-                // P columns [16c, 16c+16) overwrite score columns that were already consumed (<= 32c+31)
-                tmem_st_32x16(t_s + c * 16, packed);
+                tmem_st_32x16(t_s + (c >> 1), packed);
             }
             l += sum0 + sum1;
             tmem_st_wait();
@@ -324,6 +339,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 }
             }
         }
+    }
     }
     tc_fence_before();
     __syncthreads();

@@ -6,7 +6,8 @@
 //   warp 1 (1 lane)  MMA issuer: tcgen05.mma cta_group::1 kind::f16, UMMA 128 x BN x 16, fp32
 //                    accumulators in TMEM (2 accumulator stages x BN columns), tcgen05.commit
 //                    releases ring slots and publishes finished accumulators;
-//   warps 2..5       epilogue: tcgen05.ld (32 lanes x 32 columns per instruction), fused
+//   warps 2..9       epilogue (two warps per TMEM lane quarter, each owning half of the tile's columns):
+//                    tcgen05.ld (32 lanes x 32 columns per instruction, double buffered), fused
 //                    bias / activation / gate*x+residual / per-head RMSNorm+RoPE, bf16 stores.
 // The epilogue of tile i overlaps the MMAs of tile i+1 through the double-buffered accumulator.
 // Tile order is M-fastest so that concurrently running CTAs share the same W tile in L2.
@@ -24,7 +25,8 @@ namespace drag {
 
 constexpr int G_BM = 128;
 constexpr int G_BK = 64;
-constexpr int G_THREADS = 192;
+constexpr int G_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int G_EPI_WARPS = 8;
 constexpr int G_EPI_WARP0 = 2;
 
 template <int BN>
@@ -135,6 +137,95 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, float (&v)[32],
     }
 }
 
+// Epilogue of one accumulator tile: TMEM -> registers -> fused op -> global. Thread = one output row; the
+// 8 epilogue warps are two groups of 4 (one warp per TMEM lane quarter each): group `half` owns columns
+// [half*BN/2, (half+1)*BN/2) of the tile, so every SM sub-partition has two warps to hide TMEM / global latency.
+// t_addr: TMEM address of this warp's lane quarter at column 0 of the accumulator.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, const GemmShape& sh, uint32_t t_addr, int row,
+                                              int n_blk, int half) {
+    if (epi.mode == EPI_QKV_ROPE) {
+        // BN covers BN/128 whole heads (one per warp group at BN = 256); columns [0,H*128) q, [H*128,2H*128) k, rest v.
+        // The whole 128-wide head row lives in registers: one TMEM pass for sum of squares, RMSNorm, RoPE and store.
+        constexpr int hd = 128;
+        if (BN < 256 && half != 0) return;
+        const int h0 = (BN >= 256) ? half * hd : 0;
+        const int b = row / epi.rows_per_batch;
+        const int pos = epi.tok_offset + (row - b * epi.rows_per_batch);
+        const int col_h = n_blk * BN + h0;
+        const int which = col_h / (epi.heads * hd);          // 0 q, 1 k, 2 v
+        const int head = (col_h - which * epi.heads * hd) / hd;
+        __nv_bfloat16* dst_base = (which == 0 ? epi.q_out : (which == 1 ? epi.k_out : epi.v_out));
+        uint32_t r[hd];
+#pragma unroll
+        for (int c = 0; c < hd; c += 32) tmem_ld_32x32_ptr(t_addr + h0 + c, &r[c]);
+        tmem_ld_wait();
+        float* x = reinterpret_cast<float*>(r);      // in place: x[j] = bf16(acc + bias)
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < hd; j += 8) {
+            float bb[8];
+            if (epi.bias) load_bf16x8(epi.bias + col_h + j, bb);
+#pragma unroll
+            for (int tt = 0; tt < 8; ++tt) {
+                const float xv = bf16_round(__uint_as_float(r[j + tt]) + (epi.bias ? bb[tt] : 0.f));
+                r[j + tt] = __float_as_uint(xv);
+                ss = fmaf(xv, xv, ss);
+            }
+        }
+        if (row >= sh.M) return;
+        __nv_bfloat16* dst = dst_base + ((static_cast<size_t>(b) * epi.heads + head) * epi.s_total + pos) * hd;
+        if (which < 2) {
+            const float inv_rms = rsqrtf(ss * (1.f / hd) + epi.rms_eps);
+            const __nv_bfloat16* nw = (which == 0) ? epi.q_norm_w : epi.k_norm_w;
+            const float* cs = epi.rope_cos + static_cast<size_t>(pos) * (hd / 2);
+            const float* sn = epi.rope_sin + static_cast<size_t>(pos) * (hd / 2);
+#pragma unroll
+            for (int j = 0; j < hd; j += 8) {
+                float w[8];
+                load_bf16x8(nw + j, w);
+                const float4 c4 = *reinterpret_cast<const float4*>(cs + j / 2);
+                const float4 s4 = *reinterpret_cast<const float4*>(sn + j / 2);
+                const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+                const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+                float o[8];
+#pragma unroll
+                for (int tt = 0; tt < 4; ++tt) {
+                    const float x0 = bf16_round(bf16_round(x[j + 2 * tt] * inv_rms) * w[2 * tt]);
+                    const float x1 = bf16_round(bf16_round(x[j + 2 * tt + 1] * inv_rms) * w[2 * tt + 1]);
+                    o[2 * tt] = x0 * cc[tt] - x1 * sv[tt];
+                    o[2 * tt + 1] = x1 * cc[tt] + x0 * sv[tt];
+                }
+                store_bf16x8(dst + j, o);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < hd; j += 8) store_bf16x8(dst + j, &x[j]);
+        }
+    } else {
+        // generic: BN/2 columns per warp group in 32-column chunks, the TMEM load of chunk i+1 in flight while
+        // chunk i is processed (tcgen05.wait::ld covers every earlier load of this thread)
+        constexpr int NC = BN / 64;
+        const int c0 = half * (BN / 2);
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(t_addr + c0, ra);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            tmem_ld_wait();
+            uint32_t (&cur)[32] = (i & 1) ? rb : ra;
+            uint32_t (&nxt)[32] = (i & 1) ? ra : rb;
+            if (i + 1 < NC) tmem_ld_32x32(t_addr + c0 + (i + 1) * 32, nxt);
+            const int col0 = n_blk * BN + c0 + i * 32;
+            if (row < sh.M && col0 < sh.N) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]);
+                epilogue_chunk(epi, v, row, col0, sh.N);
+            }
+        }
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -162,7 +253,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);   // one arrival per epilogue warp
+            mbar_init(&tmem_empty[i], G_EPI_WARPS);   // one arrival per epilogue warp
         }
         fence_mbar_init();
     }
@@ -227,102 +318,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-            if (epi.mode == EPI_QKV_ROPE) {
-                // BN covers BN/128 whole heads; columns [0,H*128) q, [H*128, 2H*128) k, rest v
-                const int hd = 128;
-                const int b = row / epi.rows_per_batch;
-                const int pos = epi.tok_offset + (row - b * epi.rows_per_batch);
-#pragma unroll 1
-                for (int h0 = 0; h0 < BN; h0 += hd) {
-                    const int col_h = n_blk * BN + h0;
-                    const int which = col_h / (epi.heads * hd);          // 0 q, 1 k, 2 v
-                    const int head = (col_h - which * epi.heads * hd) / hd;
-                    __nv_bfloat16* dst_base = (which == 0 ? epi.q_out : (which == 1 ? epi.k_out : epi.v_out));
-                    float inv_rms = 1.f;
-                    if (which < 2) {   // pass 1: sum of squares of the bf16-rounded projection
-                        float ss = 0.f;
-#pragma unroll 1
-                        for (int c = 0; c < hd; c += 32) {
-                            uint32_t r[32];
-                            tmem_ld_32x32(t_addr + h0 + c, r);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                float bb[8];
-                                if (epi.bias) load_bf16x8(epi.bias + col_h + c + j, bb);
-#pragma unroll
-                                for (int tt = 0; tt < 8; ++tt) {
-                                    float x = __uint_as_float(r[j + tt]) + (epi.bias ? bb[tt] : 0.f);
-                                    x = bf16_round(x);
-                                    ss = fmaf(x, x, ss);
-                                }
-                            }
-                        }
-                        inv_rms = rsqrtf(ss * (1.f / hd) + epi.rms_eps);
-                    }
-                    const __nv_bfloat16* nw = (which == 0) ? epi.q_norm_w : epi.k_norm_w;
-#pragma unroll 1
-                    for (int c = 0; c < hd; c += 32) {
-                        uint32_t r[32];
-                        tmem_ld_32x32(t_addr + h0 + c, r);
-                        tmem_ld_wait();
-                        float v[32];
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            float bb[8];
-                            if (epi.bias) load_bf16x8(epi.bias + col_h + c + j, bb);
-#pragma unroll
-                            for (int tt = 0; tt < 8; ++tt)
-                                v[j + tt] = bf16_round(__uint_as_float(r[j + tt]) + (epi.bias ? bb[tt] : 0.f));
-                        }
-                        if (which < 2 && row < sh.M) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                float w[8];
-                                load_bf16x8(nw + c + j, w);
-#pragma unroll
-                                for (int tt = 0; tt < 8; ++tt)
-                                    v[j + tt] = bf16_round(bf16_round(v[j + tt] * inv_rms) * w[tt]);
-                            }
-                            const float* cs = epi.rope_cos + static_cast<size_t>(pos) * (hd / 2) + c / 2;
-                            const float* sn = epi.rope_sin + static_cast<size_t>(pos) * (hd / 2) + c / 2;
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4) {
-                                const float4 c4 = *reinterpret_cast<const float4*>(cs + j);
-                                const float4 s4 = *reinterpret_cast<const float4*>(sn + j);
-                                const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-                                const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-                                for (int tt = 0; tt < 4; ++tt) {
-                                    const float x0 = v[2 * (j + tt)], x1 = v[2 * (j + tt) + 1];
-                                    v[2 * (j + tt)] = x0 * cc[tt] - x1 * sv[tt];
-                                    v[2 * (j + tt) + 1] = x1 * cc[tt] + x0 * sv[tt];
-                                }
-                            }
-                        }
-                        if (row < sh.M) {
-                            __nv_bfloat16* dst = dst_base +
-                                ((static_cast<size_t>(b) * epi.heads + head) * epi.s_total + pos) * hd + c;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) store_bf16x8(dst + j, &v[j]);
-                        }
-                    }
-                }
-            } else {
-#pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(t_addr + c, r);
-                    tmem_ld_wait();
-                    const int col0 = n_blk * BN + c;
-                    if (row < sh.M && col0 < sh.N) {
-                        float v[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                        epilogue_chunk(epi, v, row, col0, sh.N);
-                    }
-                }
-            }
+            epilogue_tile<BN>(epi, sh, t_addr, row, n_blk, (warp - G_EPI_WARP0) >> 2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -334,6 +330,135 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+
+// ------------------------------------------------------------------------------ CTA-pair variant
+// Two CTAs of one cluster (the two SMs of a TPC) compute one 256 x BN tile with tcgen05.mma.cta_group::2:
+// each CTA stages ITS 128 rows of A and ITS BN/2 rows of W (32 KB per stage at BN = 256 instead of 48 KB),
+// the leader CTA's single issuing thread drives both tensor cores, and each CTA's TMEM receives the 128 x BN
+// accumulator of its own rows. Per-SM L2->smem traffic drops by a third (the 1-CTA kernel sits on the L2
+// bandwidth cap), shared-memory operand reads by a quarter. Barriers: full[] lives in the leader and counts the
+// TMA bytes of both CTAs; empty[] / tmem_full[] exist in both CTAs and are signalled by multicast commits;
+// tmem_empty[] lives in the leader and collects the 8 + 8 epilogue warps of the pair.
+template <int BN>
+struct Gemm2Cfg {
+    static constexpr int A_BYTES = G_BM * G_BK * 2;
+    static constexpr int B_BYTES = (BN / 2) * G_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 6 : 8;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
+gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                              GemmShape sh, GemmEpi epi) {
+    using Cfg = Gemm2Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint8_t* tiles = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty = full + Cfg::STAGES;
+    uint64_t* tmem_full = empty + Cfg::STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();          // 0 = leader
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int num_tiles = sh.num_m * sh.num_n;        // num_m counts 256-row tiles here
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < Cfg::STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 2 * G_EPI_WARPS);   // the epilogue warps of both CTAs of the pair
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish_2cta();
+    }
+    tc_fence_before();
+    cluster_sync_all();                               // barriers of both CTAs initialised, TMEM allocated
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        int stage = 0, phase = 0;
+        for (int t = pair; t < num_tiles; t += num_pairs) {
+            const int m_blk = t % sh.num_m, n_blk = t / sh.num_m;
+            const int a_row = m_blk * (2 * G_BM) + rank * G_BM;
+            const int b_row = n_blk * BN + rank * (BN / 2);
+            for (int kb = 0; kb < sh.num_k; ++kb) {
+                mbar_wait_cluster(&empty[stage], phase ^ 1);
+                uint8_t* a_dst = tiles + stage * Cfg::STAGE_BYTES;
+                uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+                const uint32_t full_leader = mapa_shared(smem_u32(&full[stage]), 0);
+                if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+                tma_load_2d_2cta(a_dst, &tmA, kb * G_BK, a_row, full_leader);
+                tma_load_2d_2cta(b_dst, &tmB, kb * G_BK, b_row, full_leader);
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ------------------------------------------------------------------ MMA issuer (leader only)
+        constexpr uint32_t idesc = umma_idesc_bf16(2 * G_BM, BN);
+        int stage = 0, phase = 0;
+        int acc = 0, acc_phase = 0;
+        for (int t = pair; t < num_tiles; t += num_pairs) {
+            mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < sh.num_k; ++kb) {
+                mbar_wait_cluster(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
+                const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+                const uint64_t a_desc = umma_desc_k_sw128(a_addr);
+                const uint64_t b_desc = umma_desc_k_sw128(b_addr);
+#pragma unroll
+                for (int k = 0; k < G_BK / 16; ++k)
+                    tc_mma_f16_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                tc_commit_2cta(&empty[stage], 3);
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+            tc_commit_2cta(&tmem_full[acc], 3);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= G_EPI_WARP0) {
+        // ------------------------------------------------------------------ epilogue (both CTAs, own rows)
+        const int quarter = warp & 3;
+        int acc = 0, acc_phase = 0;
+        for (int t = pair; t < num_tiles; t += num_pairs) {
+            const int m_blk = t % sh.num_m, n_blk = t / sh.num_m;
+            const int row = m_blk * (2 * G_BM) + rank * G_BM + quarter * 32 + lane;
+            mbar_wait_cluster(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+            epilogue_tile<BN>(epi, sh, t_addr, row, n_blk, (warp - G_EPI_WARP0) >> 2);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                               // the pair's MMAs, TMA writes and remote arrivals are done
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -400,6 +525,29 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     return DRAG_OK;
 }
 
+
+template <int BN>
+static int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& sh, const GemmEpi& epi,
+                            cudaStream_t st) {
+    using Cfg = Gemm2Cfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DRAG_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM));
+        attr_set = true;
+    }
+    int sms = device_sm_count();
+    if (sms <= 0) sms = 148;
+    const int pairs_max = sms / 2;
+    const int tiles = sh.num_m * sh.num_n;
+    const int pairs = tiles < pairs_max ? tiles : pairs_max;
+    gemm_bf16_tcgen05_2cta_kernel<BN><<<2 * pairs, G_THREADS, Cfg::SMEM, st>>>(tmA, tmB, sh, epi);
+    DRAG_CUDA(cudaGetLastError());
+    return DRAG_OK;
+}
+
+int g_gemm_force_1cta = 0;   // drag_debug_set key 3: 1 = always use the single-CTA kernel (A/B comparisons)
+
 int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
               const GemmEpi& epi, cudaStream_t st) {
     DRAG_REQUIRE(A && W, "gemm: null operand");
@@ -423,6 +571,24 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
         DRAG_REQUIRE(epi.out || epi.out_f32, "gemm: null output");
         if (N % 256 != 0 || N <= 256) bn = (N % 128 == 0 && N > 128) ? 128 : 64;
         if (N % bn != 0 && N > bn) bn = 64;   // N % 32 == 0: tail columns masked per 32-column chunk
+    }
+    // CTA pairs (256-row tiles) whenever there is more than one 128-row tile of work and N tiles evenly
+    const bool pair_ok = !g_gemm_force_1cta && M > G_BM && (bn == 256 || bn == 128) && N % bn == 0;
+    if (pair_ok) {
+        GemmShape sh;
+        sh.M = M; sh.N = N; sh.K = K;
+        sh.num_m = ceil_div(M, 2 * G_BM);
+        sh.num_n = N / bn;
+        sh.num_k = ceil_div(K, G_BK);
+        CUtensorMap tmA, tmB;
+        int rc = make_tmap_bf16_2d(&tmA, A, M, K, lda, G_BM);
+        if (rc) return rc;
+        rc = make_tmap_bf16_2d(&tmB, W, N, K, ldw, bn / 2);
+        if (rc) return rc;
+        const int slot = prof_begin(PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
+        rc = (bn == 256) ? launch_gemm_2cta<256>(tmA, tmB, sh, epi, st) : launch_gemm_2cta<128>(tmA, tmB, sh, epi, st);
+        prof_end(slot, st);
+        return rc;
     }
     GemmShape sh;
     sh.M = M; sh.N = N; sh.K = K;

@@ -152,7 +152,8 @@ int drag_flux_forward(drag_flux_t* h, const void* x, int ldx, const void* ctx, c
 int drag_prof_enable(int on);
 int drag_prof_collect(double* ms, double* work, int* count, int n_classes);
 
-/* Debug knobs for bring-up (key 1/2: MN-major V descriptor leading/stride byte offsets of the attention). */
+/* Debug knobs for bring-up and A/B comparisons (key 1/2: unused; key 3: 1 = force the single-CTA GEMM kernel
+ * instead of the CTA-pair cta_group::2 kernel). */
 int drag_debug_set(int key, int value);
 
 #ifdef __cplusplus

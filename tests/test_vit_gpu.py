@@ -34,8 +34,9 @@ def test_preprocess_matches_clip_transform(lib):
     im = Image.fromarray((np.random.default_rng(0).random((300, 420, 3)) * 255).astype(np.uint8))
     t = preprocess(im)
     assert t.shape == (3, 224, 224) and t.dtype == torch.float32
-    ref = torch.from_numpy(np.asarray(im.resize((int(round(420 * 224 / 300)), 224), Image.BICUBIC))).permute(2, 0, 1)
-    off = (ref.shape[2] - 224) // 2
+    # torchvision Resize truncates the long side (int(224 * 420 / 300) = 313); CenterCrop rounds the offset
+    ref = torch.from_numpy(np.asarray(im.resize((int(420 * 224 / 300), 224), Image.BICUBIC)).copy()).permute(2, 0, 1)
+    off = int(round((ref.shape[2] - 224) / 2.0))
     ref = ref[:, :, off:off + 224].float() / 255
     ref = (ref - torch.tensor(clip.CLIP_MEAN)[:, None, None]) / torch.tensor(clip.CLIP_STD)[:, None, None]
     assert float((t - ref).abs().max()) < 0.05
