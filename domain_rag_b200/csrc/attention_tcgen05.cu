@@ -233,7 +233,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
     }
     } else {
-    setmaxnreg_inc<208>();
+    setmaxnreg_inc<200>();
     if (warp < 8 || has_b) {
         // ------------------------------------------------------------------ softmax + epilogue
         const int x = (warp >= 8) ? 1 : 0;                 // query tile of this warpgroup

@@ -9,6 +9,7 @@
 #include "flux_engine.cuh"
 #include "flux_ops.cuh"
 #include "gemm.cuh"
+#include "vae_ops.cuh"
 #include "index.cuh"
 
 namespace drag {
@@ -358,6 +359,66 @@ int drag_prof_enable(int on) { return prof_enable(on); }
 int drag_prof_collect(double* ms, double* work, int* count, int n_classes) {
     DRAG_REQUIRE(ms && work && count && n_classes >= 1, "drag_prof_collect: bad arguments");
     return prof_collect(ms, work, count, n_classes);
+}
+
+// ------------------------------------------------------------------------------------ VAE path
+int drag_conv2d_nhwc(const void* in, int B, int H, int W, int C_in, const void* w, int C_out, int ksize, int stride,
+                     int pad, int Ho, int Wo, int epi_mode, const void* bias, void* out, const void* resid, void* stream) {
+    DRAG_REQUIRE(epi_mode == EPI_BIAS || epi_mode == EPI_SILU || epi_mode == EPI_GATE_RESID || epi_mode == EPI_BIAS_F32,
+                 "drag_conv2d_nhwc: epi_mode must be 0 (bias), 3 (silu), 4 (+residual) or 6 (fp32 out)");
+    GemmEpi e;
+    e.mode = epi_mode;
+    e.bias = static_cast<const __nv_bfloat16*>(bias);
+    if (epi_mode == EPI_BIAS_F32) e.out_f32 = static_cast<float*>(out);
+    else e.out = static_cast<__nv_bfloat16*>(out);
+    e.ldo = C_out;
+    e.resid = static_cast<const __nv_bfloat16*>(resid);
+    e.ldr = C_out;
+    if (epi_mode == EPI_GATE_RESID) DRAG_REQUIRE(resid, "drag_conv2d_nhwc: residual mode needs resid");
+    return conv2d_nhwc_bf16(static_cast<const __nv_bfloat16*>(in), B, H, W, C_in, static_cast<const __nv_bfloat16*>(w), C_out,
+                            ksize, stride, pad, Ho, Wo, e, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int drag_groupnorm_nhwc(const void* x, void* y, int B, int HW, int C, int groups, const void* gamma, const void* beta,
+                        float eps, int silu, float* workspace, int64_t workspace_floats, void* stream) {
+    return groupnorm_nhwc(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), B, HW, C, groups,
+                          static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta), eps, silu,
+                          workspace, static_cast<size_t>(workspace_floats), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int drag_upsample2x_nhwc(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+    return upsample2x_nhwc(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), B, H, W, C,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+int drag_softmax_rows(const float* s, int64_t ld_s, void* p, int64_t ld_p, int rows, int cols, void* stream) {
+    return softmax_rows(s, static_cast<size_t>(ld_s), static_cast<__nv_bfloat16*>(p), static_cast<size_t>(ld_p), rows, cols,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+int drag_nchw_to_nhwc_pad(const void* in, int in_is_f32, void* out, int B, int C, int H, int W, int C_pad, float scale,
+                          float shift, void* stream) {
+    return nchw_to_nhwc_pad(in, in_is_f32, static_cast<__nv_bfloat16*>(out), B, C, H, W, C_pad, scale, shift,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+int drag_nhwc_to_nchw_f32(const void* in, int in_is_f32, int ld, float* out, int B, int C, int H, int W, float scale,
+                          float shift, void* stream) {
+    return nhwc_to_nchw_f32(in, in_is_f32, ld, out, B, C, H, W, scale, shift, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int drag_image_postprocess_u8(const float* in, int ld, uint8_t* out, int64_t pixels, void* stream) {
+    return image_postprocess_u8(in, ld, out, static_cast<size_t>(pixels), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int drag_image_preprocess_u8(const uint8_t* in, const uint8_t* mask, void* out, int64_t pixels, int C_pad, void* stream) {
+    return image_preprocess_u8(in, mask, static_cast<__nv_bfloat16*>(out), static_cast<size_t>(pixels), C_pad,
+                               reinterpret_cast<cudaStream_t>(stream));
+}
+
+int drag_axpby_bf16(const void* x, const void* y, float a, float b, void* out, int64_t n, void* stream) {
+    return axpby_bf16(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(y), a, b,
+                      static_cast<__nv_bfloat16*>(out), static_cast<size_t>(n), reinterpret_cast<cudaStream_t>(stream));
 }
 
 int drag_debug_set(int key, int value) {

@@ -47,4 +47,8 @@ struct GemmEpi {
 int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
               const GemmEpi& epi, cudaStream_t st);
 
+// Implicit-GEMM convolution on the same kernels (A tiles fetched as 4-D TMA boxes of the NHWC activation).
+int conv2d_nhwc_bf16(const __nv_bfloat16* in, int B, int H, int W, int C_in, const __nv_bfloat16* w, int C_out,
+                     int ksize, int stride, int pad, int Ho, int Wo, const GemmEpi& epi, cudaStream_t st);
+
 }  // namespace drag

@@ -42,7 +42,42 @@ struct GemmCfg {
 struct GemmShape {
     int M, N, K;
     int num_m, num_n, num_k;
+    // Implicit-GEMM convolution over an NHWC activation (conv = 0: plain row-major A). The A tile of 128 output
+    // pixels is one 4-D TMA box (64 channels x tw x th pixels) at a tap-dependent offset; image borders are the
+    // TMA out-of-bounds zero fill. K runs over taps x channel blocks (weights [C_out][tap][C_in]).
+    int conv, cblocks, ksize, stride, pad;      // cblocks = C_in / 64
+    int Wo, Ho, tw, th, tiles_x, tiles_y;       // output size, pixel tile, tiles per image row / per image column
 };
+
+// First output row (linear pixel index) and number of valid rows of 128-row A tile `mt`.
+__device__ __forceinline__ void tile_rows(const GemmShape& sh, int mt, int& base, int& count, int& b, int& y0, int& x0) {
+    if (!sh.conv) {
+        base = mt * 128;
+        count = sh.M - base;
+        b = y0 = x0 = 0;
+        return;
+    }
+    const int per_img = sh.tiles_x * sh.tiles_y;
+    b = mt / per_img;
+    const int r = mt - b * per_img;
+    const int ty = r / sh.tiles_x, tx = r - ty * sh.tiles_x;
+    y0 = ty * sh.th;
+    x0 = tx * sh.tw;
+    base = (b * sh.Ho + y0) * sh.Wo + x0;       // th > 1 only with tw == Wo: the tile is th full rows, still linear
+    count = (sh.th > 1) ? min(128, (sh.Ho - y0) * sh.Wo) : min(sh.tw, sh.Wo - x0);
+    if (b * sh.Ho * sh.Wo >= sh.M) count = 0;
+}
+
+__device__ __forceinline__ void load_a_tile(const GemmShape& sh, const CUtensorMap* tmA, void* dst, int kb, int m_row,
+                                            int b, int y0, int x0, uint64_t* bar) {
+    if (!sh.conv) {
+        tma_load_2d(dst, tmA, kb * 64, m_row, bar);
+    } else {
+        const int tap = kb / sh.cblocks, cb = kb - tap * sh.cblocks;
+        const int dy = tap / sh.ksize, dx = tap - dy * sh.ksize;
+        tma_load_4d(dst, tmA, cb * 64, x0 * sh.stride + dx - sh.pad, y0 * sh.stride + dy - sh.pad, b, bar);
+    }
+}
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
     const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
@@ -143,7 +178,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, float (&v)[32],
 // t_addr: TMEM address of this warp's lane quarter at column 0 of the accumulator.
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, const GemmShape& sh, uint32_t t_addr, int row,
-                                              int n_blk, int half) {
+                                              bool row_ok, int n_blk, int half) {
     if (epi.mode == EPI_QKV_ROPE) {
         // BN covers BN/128 whole heads (one per warp group at BN = 256); columns [0,H*128) q, [H*128,2H*128) k, rest v.
         // The whole 128-wide head row lives in registers: one TMEM pass for sum of squares, RMSNorm, RoPE and store.
@@ -173,7 +208,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, const GemmShap
                 ss = fmaf(xv, xv, ss);
             }
         }
-        if (row >= sh.M) return;
+        if (!row_ok) return;
         __nv_bfloat16* dst = dst_base + ((static_cast<size_t>(b) * epi.heads + head) * epi.s_total + pos) * hd;
         if (which < 2) {
             const float inv_rms = rsqrtf(ss * (1.f / hd) + epi.rms_eps);
@@ -216,7 +251,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, const GemmShap
             uint32_t (&nxt)[32] = (i & 1) ? ra : rb;
             if (i + 1 < NC) tmem_ld_32x32(t_addr + c0 + (i + 1) * 32, nxt);
             const int col0 = n_blk * BN + c0 + i * 32;
-            if (row < sh.M && col0 < sh.N) {
+            if (row_ok && col0 < sh.N) {
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]);
@@ -271,12 +306,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         int stage = 0, phase = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int m_blk = t % sh.num_m, n_blk = t / sh.num_m;
+            int base, count, ib, iy, ix;
+            tile_rows(sh, m_blk, base, count, ib, iy, ix);
             for (int kb = 0; kb < sh.num_k; ++kb) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* a_dst = tiles + stage * Cfg::STAGE_BYTES;
                 uint8_t* b_dst = a_dst + Cfg::A_BYTES;
                 mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                tma_load_2d(a_dst, &tmA, kb * G_BK, m_blk * G_BM, &full[stage]);
+                load_a_tile(sh, &tmA, a_dst, kb, m_blk * G_BM, ib, iy, ix, &full[stage]);
                 tma_load_2d(b_dst, &tmB, kb * G_BK, n_blk * BN, &full[stage]);
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
@@ -314,11 +351,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         int acc = 0, acc_phase = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int m_blk = t % sh.num_m, n_blk = t / sh.num_m;
-            const int row = m_blk * G_BM + quarter * 32 + lane;
+            int base, count, ib, iy, ix;
+            tile_rows(sh, m_blk, base, count, ib, iy, ix);
+            const int r_in = quarter * 32 + lane;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-            epilogue_tile<BN>(epi, sh, t_addr, row, n_blk, (warp - G_EPI_WARP0) >> 2);
+            epilogue_tile<BN>(epi, sh, t_addr, base + r_in, r_in < count, n_blk, (warp - G_EPI_WARP0) >> 2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -401,13 +440,22 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             const int m_blk = t % sh.num_m, n_blk = t / sh.num_m;
             const int a_row = m_blk * (2 * G_BM) + rank * G_BM;
             const int b_row = n_blk * BN + rank * (BN / 2);
+            int base, count, ib, iy, ix;
+            tile_rows(sh, m_blk * 2 + rank, base, count, ib, iy, ix);
             for (int kb = 0; kb < sh.num_k; ++kb) {
                 mbar_wait_cluster(&empty[stage], phase ^ 1);
                 uint8_t* a_dst = tiles + stage * Cfg::STAGE_BYTES;
                 uint8_t* b_dst = a_dst + Cfg::A_BYTES;
                 const uint32_t full_leader = mapa_shared(smem_u32(&full[stage]), 0);
                 if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
-                tma_load_2d_2cta(a_dst, &tmA, kb * G_BK, a_row, full_leader);
+                if (!sh.conv) {
+                    tma_load_2d_2cta(a_dst, &tmA, kb * G_BK, a_row, full_leader);
+                } else {
+                    const int tap = kb / sh.cblocks, cb = kb - tap * sh.cblocks;
+                    const int dy = tap / sh.ksize, dx = tap - dy * sh.ksize;
+                    tma_load_4d_2cta(a_dst, &tmA, cb * 64, ix * sh.stride + dx - sh.pad, iy * sh.stride + dy - sh.pad, ib,
+                                     full_leader);
+                }
                 tma_load_2d_2cta(b_dst, &tmB, kb * G_BK, b_row, full_leader);
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
@@ -443,11 +491,13 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         int acc = 0, acc_phase = 0;
         for (int t = pair; t < num_tiles; t += num_pairs) {
             const int m_blk = t % sh.num_m, n_blk = t / sh.num_m;
-            const int row = m_blk * (2 * G_BM) + rank * G_BM + quarter * 32 + lane;
+            int base, count, ib, iy, ix;
+            tile_rows(sh, m_blk * 2 + rank, base, count, ib, iy, ix);
+            const int r_in = quarter * 32 + lane;
             mbar_wait_cluster(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-            epilogue_tile<BN>(epi, sh, t_addr, row, n_blk, (warp - G_EPI_WARP0) >> 2);
+            epilogue_tile<BN>(epi, sh, t_addr, base + r_in, r_in < count, n_blk, (warp - G_EPI_WARP0) >> 2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
@@ -506,6 +556,24 @@ int make_tmap_bf16_3d(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d
     return DRAG_OK;
 }
 
+// 4-D bf16 NHWC activation [B][H][W][C]: box = 64 channels x tw x th pixels of one image, traversal stride `stride`
+// along W and H (strided convolutions), SWIZZLE_128B, out-of-bounds elements read as zero (= the conv padding).
+int make_tmap_bf16_nhwc(CUtensorMap* map, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t tw,
+                        uint32_t th, uint32_t stride) {
+    std::call_once(g_encode_once, load_encode);
+    if (!g_encode) return fail(DRAG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {C, W, H, B};
+    cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+    cuuint32_t box[4] = {64, tw * stride, th * stride, 1};
+    cuuint32_t estr[4] = {1, stride, stride, 1};
+    if (box[1] > 256 || box[2] > 256) return fail(DRAG_ERR_INVALID, "conv2d: pixel tile too large for a TMA box");
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DRAG_ERR_CUDA, "cuTensorMapEncodeTiled(nhwc) failed: " + std::to_string(r));
+    return DRAG_OK;
+}
+
 template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& sh, const GemmEpi& epi,
                        cudaStream_t st) {
@@ -546,7 +614,39 @@ static int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     return DRAG_OK;
 }
 
+
 int g_gemm_force_1cta = 0;   // drag_debug_set key 3: 1 = always use the single-CTA kernel (A/B comparisons)
+
+// Shared launch logic: builds the operand tensor maps (A from a row-major matrix unless a ready map is given) and
+// picks the CTA-pair kernel whenever there is more than one 128-row tile of work and N tiles evenly.
+static int dispatch_gemm(const __nv_bfloat16* A, const CUtensorMap* tmA_ready, int M, int K, int lda,
+                         const __nv_bfloat16* W, int ldw, GemmShape sh, int bn, int m_tiles, const GemmEpi& epi,
+                         cudaStream_t st) {
+    const int N = sh.N;
+    const bool pair_ok = !g_gemm_force_1cta && m_tiles > 1 && (bn == 256 || bn == 128) && N % bn == 0;
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (tmA_ready) tmA = *tmA_ready;
+    else if ((rc = make_tmap_bf16_2d(&tmA, A, M, K, lda, G_BM))) return rc;
+    const int slot = prof_begin(PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
+    if (pair_ok) {
+        sh.num_m = ceil_div(m_tiles, 2);
+        sh.num_n = N / bn;
+        if ((rc = make_tmap_bf16_2d(&tmB, W, N, K, ldw, bn / 2))) return rc;
+        rc = (bn == 256) ? launch_gemm_2cta<256>(tmA, tmB, sh, epi, st) : launch_gemm_2cta<128>(tmA, tmB, sh, epi, st);
+    } else {
+        sh.num_m = m_tiles;
+        sh.num_n = ceil_div(N, bn);
+        if ((rc = make_tmap_bf16_2d(&tmB, W, N, K, ldw, bn))) return rc;
+        switch (bn) {
+            case 256: rc = launch_gemm<256>(tmA, tmB, sh, epi, st); break;
+            case 128: rc = launch_gemm<128>(tmA, tmB, sh, epi, st); break;
+            default:  rc = launch_gemm<64>(tmA, tmB, sh, epi, st); break;
+        }
+    }
+    prof_end(slot, st);
+    return rc;
+}
 
 int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
               const GemmEpi& epi, cudaStream_t st) {
@@ -572,42 +672,42 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
         if (N % 256 != 0 || N <= 256) bn = (N % 128 == 0 && N > 128) ? 128 : 64;
         if (N % bn != 0 && N > bn) bn = 64;   // N % 32 == 0: tail columns masked per 32-column chunk
     }
-    // CTA pairs (256-row tiles) whenever there is more than one 128-row tile of work and N tiles evenly
-    const bool pair_ok = !g_gemm_force_1cta && M > G_BM && (bn == 256 || bn == 128) && N % bn == 0;
-    if (pair_ok) {
-        GemmShape sh;
-        sh.M = M; sh.N = N; sh.K = K;
-        sh.num_m = ceil_div(M, 2 * G_BM);
-        sh.num_n = N / bn;
-        sh.num_k = ceil_div(K, G_BK);
-        CUtensorMap tmA, tmB;
-        int rc = make_tmap_bf16_2d(&tmA, A, M, K, lda, G_BM);
-        if (rc) return rc;
-        rc = make_tmap_bf16_2d(&tmB, W, N, K, ldw, bn / 2);
-        if (rc) return rc;
-        const int slot = prof_begin(PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
-        rc = (bn == 256) ? launch_gemm_2cta<256>(tmA, tmB, sh, epi, st) : launch_gemm_2cta<128>(tmA, tmB, sh, epi, st);
-        prof_end(slot, st);
-        return rc;
-    }
-    GemmShape sh;
+    GemmShape sh{};
     sh.M = M; sh.N = N; sh.K = K;
-    sh.num_m = ceil_div(M, G_BM);
-    sh.num_n = ceil_div(N, bn);
     sh.num_k = ceil_div(K, G_BK);
-    CUtensorMap tmA, tmB;
-    int rc = make_tmap_bf16_2d(&tmA, A, M, K, lda, G_BM);
-    if (rc) return rc;
-    rc = make_tmap_bf16_2d(&tmB, W, N, K, ldw, bn);
-    if (rc) return rc;
-    const int slot = prof_begin(PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
-    switch (bn) {
-        case 256: rc = launch_gemm<256>(tmA, tmB, sh, epi, st); break;
-        case 128: rc = launch_gemm<128>(tmA, tmB, sh, epi, st); break;
-        default:  rc = launch_gemm<64>(tmA, tmB, sh, epi, st); break;
+    return dispatch_gemm(A, nullptr, M, K, lda, W, ldw, sh, bn, ceil_div(M, G_BM), epi, st);
+}
+
+// Implicit-GEMM convolution: out[b][y][x][:] = epilogue(sum_{tap,c} in[b][y*s+dy-pad][x*s+dx-pad][c] * w[:][tap][c]).
+// in bf16 NHWC [B][H][W][C_in] (C_in % 64 == 0), w bf16 [C_out][ksize*ksize][C_in], out NHWC [B][Ho][Wo][C_out]
+// written through the usual epilogues with row = linear output pixel. ksize 1 or 3; stride 1 or 2; pad = left/top
+// padding (right/bottom are the zero fill of whatever the window reaches past the border).
+int conv2d_nhwc_bf16(const __nv_bfloat16* in, int B, int H, int W, int C_in, const __nv_bfloat16* w, int C_out,
+                     int ksize, int stride, int pad, int Ho, int Wo, const GemmEpi& epi, cudaStream_t st) {
+    DRAG_REQUIRE(in && w, "conv2d: null operand");
+    DRAG_REQUIRE(B >= 1 && H >= 1 && W >= 1 && Ho >= 1 && Wo >= 1, "conv2d: empty problem");
+    DRAG_REQUIRE(C_in % 64 == 0 && C_out % 32 == 0, "conv2d: C_in must be a multiple of 64, C_out of 32");
+    DRAG_REQUIRE((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "conv2d: ksize 1|3, stride 1|2");
+    DRAG_REQUIRE(epi.mode != EPI_QKV_ROPE && epi.mode != EPI_QKV_SPLIT, "conv2d: unsupported epilogue");
+    DRAG_REQUIRE(epi.out || epi.out_f32, "conv2d: null output");
+    GemmShape sh{};
+    sh.M = B * Ho * Wo; sh.N = C_out; sh.K = ksize * ksize * C_in;
+    sh.num_k = sh.K / G_BK;
+    sh.conv = 1; sh.cblocks = C_in / 64; sh.ksize = ksize; sh.stride = stride; sh.pad = pad;
+    sh.Wo = Wo; sh.Ho = Ho;
+    if (Wo < 128 && 128 % Wo == 0) {           // th full rows per tile
+        sh.tw = Wo; sh.th = 128 / Wo; sh.tiles_x = 1; sh.tiles_y = ceil_div(Ho, sh.th);
+    } else {                                     // one row segment of up to 128 pixels per tile
+        sh.tw = 128; sh.th = 1; sh.tiles_x = ceil_div(Wo, 128); sh.tiles_y = Ho;
     }
-    prof_end(slot, st);
-    return rc;
+    const int m_tiles = B * sh.tiles_x * sh.tiles_y;
+    int bn = 256;
+    if (C_out % 256 != 0 || C_out <= 256) bn = (C_out % 128 == 0 && C_out > 128) ? 128 : 64;
+    if (C_out % bn != 0 && C_out > bn) bn = 64;
+    CUtensorMap tmA;
+    int rc = make_tmap_bf16_nhwc(&tmA, in, B, H, W, C_in, sh.tw, sh.th, stride);
+    if (rc) return rc;
+    return dispatch_gemm(nullptr, &tmA, sh.M, sh.K, 0, w, sh.K, sh, bn, m_tiles, epi, st);
 }
 
 }  // namespace drag

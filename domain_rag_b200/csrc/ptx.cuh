@@ -84,6 +84,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* m
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* map, int c0, int c1,
+                                            int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst_smem)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -255,6 +263,15 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* dst_smem, const CUtensorM
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
         " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst_smem)),
         "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d_2cta(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2,
+                                                 int c3, uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst_smem)),
+        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 

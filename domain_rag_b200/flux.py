@@ -217,18 +217,32 @@ def redux_blend(txt_tokens, img_tokens, pooled, s_embed, s_pool):
 
 @dataclass
 class PipelineOutput:
-    latents: torch.Tensor                      # [B,16,H/8,W/8] bf16 (unpacked)
-    images: Optional[list] = None              # PIL images once the VAE decoder is built
+    latents: torch.Tensor                      # [B,16,H/8,W/8] bf16 (unpacked, sampler space)
+    images: Optional[list] = None              # PIL images when the pipeline owns a VAE and output_type == "pil"
     steps_run: int = 0
 
 
-class FluxPipeline:
-    """Mirror of the diffusers pipeline call the reference makes (kwargs, CPU generator semantics,
-    schedule, Euler update). Text/image encoders and the VAE are outside this round's scope: the
-    caller passes prompt_embeds / pooled_prompt_embeds (e.g. from redux_blend) and receives latents."""
+def axpby_(x: torch.Tensor, y: torch.Tensor, a: float, b: float) -> torch.Tensor:
+    """a * x + b * y on contiguous bf16 tensors (drag_axpby_bf16)."""
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().drag_axpby_bf16(_lib.ptr(x), _lib.ptr(y), float(a), float(b), _lib.ptr(out), x.numel(),
+                                           _lib.current_stream_ptr(x.device)), "drag_axpby_bf16")
+    return out
 
-    def __init__(self, transformer: FluxTransformer):
+
+def executed_range(num_inference_steps: int, strength: float) -> int:
+    """First executed step index of an img2img-style call: T - min(int(T * strength), T) (diffusers get_timesteps)."""
+    return num_inference_steps - int(min(num_inference_steps * strength, num_inference_steps))
+
+
+class FluxPipeline:
+    """Mirror of the diffusers pipeline call the reference makes (kwargs, CPU generator semantics, schedule, Euler
+    update): batch_generate_flux_kshot.py:467-474. Prompt tensors come from FluxPriorReduxPipeline (redux.py); with a
+    `vae` the call returns `.images` (PIL), otherwise latents (output_type="latent")."""
+
+    def __init__(self, transformer: FluxTransformer, vae=None):
         self.transformer = transformer
+        self.vae = vae
         self._rope_cache = {}
 
     def _rope(self, h2, w2, s_txt, device):
@@ -246,40 +260,111 @@ class FluxPipeline:
         z = torch.randn((batch, 16, h, w), generator=generator, dtype=torch.bfloat16)
         return pack_latents(z).contiguous().pin_memory().to(device, non_blocking=True), h, w
 
-    def __call__(self, prompt_embeds, pooled_prompt_embeds, guidance_scale=3.5, num_inference_steps=28, height=1024,
-                 width=1024, generator=None, latents=None, extra_cond=None, strength=1.0, image_latents=None,
-                 output_type="latent"):
+    def _denoise(self, latents, h, w, prompt_embeds, pooled_prompt_embeds, guidance_scale, num_inference_steps, start,
+                 extra_cond):
+        """Steps [start, T) of the flow-match Euler loop on packed latents [B,S,64]; returns packed latents."""
         tr = self.transformer
         dev = tr.device
-        B = prompt_embeds.shape[0]
-        if latents is None:
-            latents, h, w = self.prepare_latents(B, height, width, generator, dev)
-        else:
-            h, w = 2 * (int(height) // 16), 2 * (int(width) // 16)
-        S_img = latents.shape[1]
+        B, S_img, c_lat = latents.shape
         sig = flow_match_sigmas(num_inference_steps, S_img)
         cos, sin = self._rope(h // 2, w // 2, prompt_embeds.shape[1], dev)
-        # img2img / fill: run only the last int(T*strength) steps from a noised image (reference strength tables)
-        start = 0
-        if strength < 1.0:
-            start = num_inference_steps - int(min(num_inference_steps * strength, num_inference_steps))
-            if image_latents is not None:
-                latents = (sig[start] * latents.float() + (1.0 - sig[start]) * image_latents.float()).bfloat16()
-        c_lat = latents.shape[2]
         if extra_cond is not None:       # Fill: x lives in the first 64 channels of a persistent [B,S,384] buffer
             buf = torch.cat([latents, extra_cond.to(latents.dtype)], dim=-1).contiguous()
         else:
             buf = latents.contiguous()
         x_view = buf[:, :, :c_lat]
         ctx = prompt_embeds.to(dev, torch.bfloat16).contiguous()
+        if ctx.shape[0] != B:
+            ctx = ctx.expand(B, -1, -1).contiguous()
         pooled = pooled_prompt_embeds.to(dev, torch.bfloat16).contiguous()
+        if pooled.shape[0] != B:
+            pooled = pooled.expand(B, -1).contiguous()
         g = torch.full((B,), float(guidance_scale), dtype=torch.float32, device=dev) if tr.cfg.guidance else None
         t_all = torch.tensor(sig[:-1], dtype=torch.float32, device=dev)[:, None].expand(-1, B).contiguous()
         v = torch.empty((B, S_img, tr.cfg.out_channels), dtype=torch.bfloat16, device=dev)
         for i in range(start, num_inference_steps):
             tr.forward(buf, ctx, pooled, t_all[i], g, cos, sin, out=v)
             euler_step_(x_view, v, sig[i + 1] - sig[i])
-        lat = unpack_latents(x_view.contiguous(), h, w)
-        if output_type != "latent":
-            raise NotImplementedError("VAE decode is the next scope row (SURVEY 8f N1); use output_type='latent'")
-        return PipelineOutput(latents=lat, images=None, steps_run=num_inference_steps - start)
+        return x_view.contiguous(), sig
+
+    def _finish(self, packed, h, w, steps_run, output_type):
+        lat = unpack_latents(packed, h, w)
+        if output_type == "latent":
+            return PipelineOutput(latents=lat, images=None, steps_run=steps_run)
+        if self.vae is None:
+            raise RuntimeError("this pipeline was built without a VAE: pass vae=FluxVAE(...) or output_type='latent'")
+        return PipelineOutput(latents=lat, images=self.vae.decode(lat, output_type="pil"), steps_run=steps_run)
+
+    def __call__(self, prompt_embeds, pooled_prompt_embeds, guidance_scale=3.5, num_inference_steps=28, height=1024,
+                 width=1024, generator=None, latents=None, extra_cond=None, strength=1.0, image_latents=None,
+                 output_type=None):
+        dev = self.transformer.device
+        output_type = output_type or ("pil" if self.vae is not None else "latent")
+        B = prompt_embeds.shape[0]
+        if latents is None:
+            latents, h, w = self.prepare_latents(B, height, width, generator, dev)
+        else:
+            h, w = 2 * (int(height) // 16), 2 * (int(width) // 16)
+        start = 0
+        if strength < 1.0:           # img2img: run only the last int(T*strength) steps from a noised image
+            start = executed_range(num_inference_steps, strength)
+            if image_latents is not None:
+                s0 = flow_match_sigmas(num_inference_steps, latents.shape[1])[start]
+                latents = axpby_(latents.contiguous(), image_latents.to(dev, torch.bfloat16).contiguous(), s0, 1.0 - s0)
+        packed, _ = self._denoise(latents, h, w, prompt_embeds, pooled_prompt_embeds, guidance_scale, num_inference_steps,
+                                  start, extra_cond)
+        return self._finish(packed, h, w, num_inference_steps - start, output_type)
+
+
+def pack_mask(mask: torch.Tensor) -> torch.Tensor:
+    """Binary mask [B,H,W] -> [B,(H/16)(W/16),256]: each latent pixel carries its 8x8 block of mask pixels as 64
+    channels (FluxFillPipeline.prepare_mask_latents), then the 2x2 latent packing. Data movement only."""
+    B, H, W = mask.shape
+    m = mask.view(B, H // 8, 8, W // 8, 8).permute(0, 2, 4, 1, 3).reshape(B, 64, H // 8, W // 8)
+    return pack_latents(m)
+
+
+class FluxFillPipeline(FluxPipeline):
+    """Mirror of the FluxFillPipeline call of the composition script (outpainting_updown_sampling_redux.py:1246-1257):
+    pipe_fill(image=, mask_image=, height=, width=, guidance_scale=, num_inference_steps=50, prompt_embeds=,
+    pooled_prompt_embeds=, generator=, strength=).images[0]. The transformer is the Fill variant (in_channels 384 =
+    64 latent + 64 masked-image latent + 256 mask channels). Host work: PIL resize to multiples of 16 (Lanczos, like
+    VaeImageProcessor), mask binarisation at 0.5. Generator draws, in order: VAE sample of the image, the initial noise
+    (bf16, CPU generator), VAE sample of the masked image."""
+
+    def __call__(self, prompt_embeds, pooled_prompt_embeds, image=None, mask_image=None, height=None, width=None,
+                 guidance_scale=30.0, num_inference_steps=50, generator=None, strength=1.0, output_type=None):
+        import numpy as np
+        from PIL import Image
+        if self.vae is None:
+            raise RuntimeError("FluxFillPipeline needs a VAE (image and masked image are encoded)")
+        if image is None or mask_image is None:
+            raise ValueError("image and mask_image are required")
+        dev = self.transformer.device
+        output_type = output_type or "pil"
+        height = image.height if height is None else int(height)
+        width = image.width if width is None else int(width)
+        H, W = 16 * (height // 16), 16 * (width // 16)
+        img = image.convert("RGB")
+        if img.size != (W, H):
+            img = img.resize((W, H), Image.LANCZOS)
+        msk = mask_image.convert("L")
+        if msk.size != (W, H):
+            msk = msk.resize((W, H), Image.LANCZOS)
+        img_u8 = torch.from_numpy(np.asarray(img).copy())[None].pin_memory().to(dev, non_blocking=True)
+        mask_u8 = torch.from_numpy((np.asarray(msk) >= 128).astype(np.uint8))[None].pin_memory().to(dev, non_blocking=True)
+        B = 1
+        start = executed_range(num_inference_steps, strength)
+        if start >= num_inference_steps:
+            raise ValueError(f"After adjusting the num_inference_steps by strength parameter: {strength}, the number of "
+                             "pipeline steps is 0 which is < 1")
+        h, w = H // 8, W // 8
+        image_latents = pack_latents(self.vae.encode(img_u8, generator=generator)).contiguous()
+        noise, _, _ = self.prepare_latents(B, H, W, generator, dev)
+        s0 = flow_match_sigmas(num_inference_steps, noise.shape[1])[start]
+        latents = axpby_(noise.contiguous(), image_latents, s0, 1.0 - s0)
+        masked = pack_latents(self.vae.encode(img_u8, generator=generator, mask=mask_u8))
+        cond = torch.cat([masked, pack_mask(mask_u8).to(torch.bfloat16)], dim=-1).contiguous()      # [B,S,320]
+        packed, _ = self._denoise(latents, h, w, prompt_embeds, pooled_prompt_embeds, guidance_scale, num_inference_steps,
+                                  start, cond)
+        return self._finish(packed, h, w, num_inference_steps - start, output_type)

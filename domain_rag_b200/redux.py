@@ -1,0 +1,115 @@
+"""FluxPriorReduxPipeline mirror - the image-prompt call the reference makes before each generation:
+
+    pipe_prior_output = pipe_prior_redux([img_a, img_b], prompt=[...], prompt_2=[...],
+                                         prompt_embeds_scale=[0.8, 1.0], pooled_prompt_embeds_scale=[1.0, 1.0])
+    pipe(..., **pipe_prior_output)                       # batch_generate_flux_kshot.py:459-473
+    pipe_prior_redux([bg], prompt=redux_prompt, prompt_2="", prompt_embeds_scale=[s], pooled_prompt_embeds_scale=[1.0])
+                                                         # outpainting_updown_sampling_redux.py:1237-1243
+
+Semantics kept from diffusers 0.33.1: one row per image; text tokens (T5, 512 x 4096) and image tokens
+(SigLIP -> Redux embedder, 729 x 4096) concatenated per row, each row scaled, rows SUMMED (so the pooled vector of
+the two-image generation call is 2 x CLIP("")). The output object works as `**kwargs` and by attribute.
+
+The image half runs on the sm_100a kernels (siglip.py). The text half is a per-prompt CONSTANT (the reference only
+ever passes "" or one fixed sentence per dataset): it is looked up in a `TextEmbeddingTable` that is filled once per
+process - from a file of precomputed T5 / CLIP-text outputs, from caller-provided encoder callables (e.g.
+transformers T5EncoderModel / CLIPTextModel, library code off the hot path), or, with no checkpoints offline, from a
+seeded synthetic generator. SURVEY 8f N2: "T5("")/CLIP("") computed once per process".
+"""
+from __future__ import annotations
+
+import hashlib
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import flux as F
+from . import siglip as S
+
+T5_TOKENS, T5_DIM, POOLED_DIM = 512, 4096, 768
+
+
+class ReduxOutput(dict):
+    """FluxPriorReduxPipelineOutput: `.prompt_embeds`, `.pooled_prompt_embeds`, and usable as **kwargs."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+class TextEmbeddingTable:
+    """prompt string -> (T5 tokens bf16 [512, 4096], CLIP pooled bf16 [768]); each distinct prompt is encoded once."""
+
+    def __init__(self, device="cuda", t5_encode: Optional[Callable[[str], torch.Tensor]] = None,
+                 clip_encode: Optional[Callable[[str], torch.Tensor]] = None, txt_dim: int = T5_DIM,
+                 pooled_dim: int = POOLED_DIM, tokens: int = T5_TOKENS):
+        self.device = torch.device(device)
+        self.t5_encode, self.clip_encode = t5_encode, clip_encode
+        self.txt_dim, self.pooled_dim, self.tokens = txt_dim, pooled_dim, tokens
+        self._table: Dict[Tuple[str, str], Tuple[torch.Tensor, torch.Tensor]] = {}
+
+    def load_file(self, path: str) -> None:
+        """{"prompts": [[prompt, prompt_2], ...], "t5": [n,512,4096], "pooled": [n,768]} saved with torch.save."""
+        d = torch.load(path, map_location="cpu", weights_only=True)
+        for (p1, p2), t5, pooled in zip(d["prompts"], d["t5"], d["pooled"]):
+            self._table[(p1, p2)] = (t5.to(self.device, torch.bfloat16), pooled.to(self.device, torch.bfloat16))
+
+    def _synthetic(self, key: Tuple[str, str]):
+        seed = int.from_bytes(hashlib.sha256(repr(key).encode()).digest()[:4], "little")
+        g = torch.Generator().manual_seed(seed)
+        t5 = (0.1 * torch.randn(self.tokens, self.txt_dim, generator=g)).bfloat16()
+        pooled = torch.randn(self.pooled_dim, generator=g).bfloat16()
+        return t5.to(self.device), pooled.to(self.device)
+
+    def lookup(self, prompt: str, prompt_2: Optional[str]):
+        """diffusers: prompt goes to CLIP (pooled), prompt_2 (default = prompt) to T5."""
+        key = (prompt or "", prompt if prompt_2 is None else prompt_2)
+        if key not in self._table:
+            if self.t5_encode is not None and self.clip_encode is not None:
+                t5 = self.t5_encode(key[1]).to(self.device, torch.bfloat16).reshape(self.tokens, self.txt_dim)
+                pooled = self.clip_encode(key[0]).to(self.device, torch.bfloat16).reshape(self.pooled_dim)
+                self._table[key] = (t5, pooled)
+            else:
+                self._table[key] = self._synthetic(key)
+        return self._table[key]
+
+
+class FluxPriorReduxPipeline:
+    def __init__(self, image_encoder: S.SiglipVisionTower, image_embedder: S.ReduxImageEncoder,
+                 text_table: Optional[TextEmbeddingTable] = None):
+        self.image_encoder, self.image_embedder = image_encoder, image_embedder
+        self.device = image_encoder.device
+        self.text_table = text_table
+        self.image_size = image_encoder.cfg.image
+
+    @torch.no_grad()
+    def encode_image(self, images: Sequence) -> torch.Tensor:
+        """PIL images -> Redux image-prompt tokens bf16 [B, 729, 4096]."""
+        px = S.preprocess(images, self.image_size).pin_memory().to(self.device, non_blocking=True)
+        return self.image_embedder(self.image_encoder.last_hidden_state(px))
+
+    @torch.no_grad()
+    def __call__(self, image, prompt: Union[str, List[str], None] = None, prompt_2: Union[str, List[str], None] = None,
+                 prompt_embeds_scale: Union[float, List[float]] = 1.0,
+                 pooled_prompt_embeds_scale: Union[float, List[float]] = 1.0) -> ReduxOutput:
+        images = list(image) if isinstance(image, (list, tuple)) else [image]
+        B = len(images)
+        prompts = [prompt] * B if (prompt is None or isinstance(prompt, str)) else list(prompt)
+        prompts2 = [prompt_2] * B if (prompt_2 is None or isinstance(prompt_2, str)) else list(prompt_2)
+        if len(prompts) != B or len(prompts2) != B:
+            raise ValueError("number of prompts must be equal to number of images")
+        se = [prompt_embeds_scale] * B if isinstance(prompt_embeds_scale, (int, float)) else list(prompt_embeds_scale)
+        sp = ([pooled_prompt_embeds_scale] * B if isinstance(pooled_prompt_embeds_scale, (int, float))
+              else list(pooled_prompt_embeds_scale))
+        img_tokens = self.encode_image(images)
+        if self.text_table is not None:
+            rows = [self.text_table.lookup(a if a is not None else "", b) for a, b in zip(prompts, prompts2)]
+            txt = torch.stack([r[0] for r in rows]).contiguous()
+            pooled = torch.stack([r[1] for r in rows]).contiguous()
+        else:      # pipeline loaded without text encoders: diffusers substitutes zeros
+            txt = torch.zeros((B, T5_TOKENS, img_tokens.shape[2]), dtype=torch.bfloat16, device=self.device)
+            pooled = torch.zeros((B, POOLED_DIM), dtype=torch.bfloat16, device=self.device)
+        pe, pp = F.redux_blend(txt, img_tokens.contiguous(), pooled, [float(x) for x in se], [float(x) for x in sp])
+        return ReduxOutput(prompt_embeds=pe, pooled_prompt_embeds=pp)

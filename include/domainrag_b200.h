@@ -146,6 +146,35 @@ int drag_flux_forward(drag_flux_t* h, const void* x, int ldx, const void* ctx, c
                       const float* g_dev, const float* rope_cos, const float* rope_sin, int B, int S_img, void* v_out,
                       int ldv, int n_double_run, int n_single_run, void* stream);
 
+/* ---- Flux VAE path (AutoencoderKL decode after / encode before the sampling loop, and VaeImageProcessor) --------
+ * What `pipe(...).images` and `pipe_fill(image=..., mask_image=...)` run around the transformer
+ * (batch_generate_flux_kshot.py:467-474, outpainting_updown_sampling_redux.py:1246-1257). Activations are bf16 NHWC.
+ * Convolution as implicit GEMM on the tcgen05 core: in [B][H][W][C_in] (C_in % 64 == 0), w [C_out][ksize*ksize][C_in]
+ * (tap-major), out [B][Ho][Wo][C_out]; ksize 1|3, stride 1|2, pad = left/top padding (the rest is zero fill).
+ * epi_mode: 0 bias, 3 silu, 4 out = resid + (acc + bias), 6 fp32 output. */
+int drag_conv2d_nhwc(const void* in, int B, int H, int W, int C_in, const void* w, int C_out, int ksize, int stride,
+                     int pad, int Ho, int Wo, int epi_mode, const void* bias, void* out, const void* resid, void* stream);
+/* GroupNorm over [HW x C/groups] per image and group, affine, optional SiLU. workspace: fp32 scratch of at least
+ * B*1024*2*C + B*groups*2 floats. */
+int drag_groupnorm_nhwc(const void* x, void* y, int B, int HW, int C, int groups, const void* gamma, const void* beta,
+                        float eps, int silu, float* workspace, int64_t workspace_floats, void* stream);
+int drag_upsample2x_nhwc(const void* x, void* y, int B, int H, int W, int C, void* stream);
+/* p[r][:] = softmax(s[r][:]) (fp32 scores -> bf16 probabilities), cols % 4 == 0. */
+int drag_softmax_rows(const float* s, int64_t ld_s, void* p, int64_t ld_p, int rows, int cols, void* stream);
+/* out[b][y][x][c] = in[b][c][y][x] * scale + shift (c < C), 0 for padded channels; in fp32 or bf16. */
+int drag_nchw_to_nhwc_pad(const void* in, int in_is_f32, void* out, int B, int C, int H, int W, int C_pad, float scale,
+                          float shift, void* stream);
+/* out fp32 [B][C][H][W] = in[b][y][x][c] * scale + shift from NHWC rows of ld elements (fp32 or bf16). */
+int drag_nhwc_to_nchw_f32(const void* in, int in_is_f32, int ld, float* out, int B, int C, int H, int W, float scale,
+                          float shift, void* stream);
+/* uint8 RGB [pixels][3] = round(clamp(x / 2 + 0.5, 0, 1) * 255) from fp32 NHWC rows of ld floats. */
+int drag_image_postprocess_u8(const float* in, int ld, uint8_t* out, int64_t pixels, void* stream);
+/* bf16 NHWC [pixels][C_pad] = u8 / 255 * 2 - 1 (channels >= 3 zero). mask (optional, uint8 per pixel): non-zero pixels
+ * are written as 0 = init_image * (1 - mask) of FluxFillPipeline. */
+int drag_image_preprocess_u8(const uint8_t* in, const uint8_t* mask, void* out, int64_t pixels, int C_pad, void* stream);
+/* out = a * x + b * y (bf16, fp32 arithmetic): scheduler.scale_noise of the img2img / fill pipelines. */
+int drag_axpby_bf16(const void* x, const void* y, float a, float b, void* out, int64_t n, void* stream);
+
 /* Per-launch CUDA-event timing of the heavy kernels on their launching stream (bench.py roofline):
  * class 0 = tcgen05 GEMM (work = 2*M*N*K flops), class 1 = attention (work = 4*B*H*S*S*128 flops).
  * drag_prof_collect synchronises, returns summed milliseconds / work / launch counts per class, and resets. */

@@ -1,0 +1,71 @@
+"""Oracle: the three diffusers pipeline calls of the reference composed from the oracle modules (PyTorch fp32, CPU).
+TEST INFRASTRUCTURE ONLY.
+
+  redux_prior   FluxPriorReduxPipeline.__call__   batch_generate_flux_kshot.py:459-465, outpainting_...:1237-1243
+  generate      FluxPipeline.__call__             batch_generate_flux_kshot.py:467-474
+  fill          FluxFillPipeline.__call__         outpainting_updown_sampling_redux.py:1246-1257
+diffusers==0.33.1 is not in /root/reference and not installable offline: PARITY UNPINNED by the reference; the
+control flow below restates the published pipelines (preprocess -> VAE encode -> scale_noise -> mask packing ->
+flow-match Euler loop over the steps kept by `strength` -> VAE decode -> postprocess).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import flux as OF
+from . import siglip as OS
+from . import vae as OV
+
+
+def redux_prior(siglip_state, siglip_cfg, redux_state, images, txt_tokens, pooled, s_embed, s_pool):
+    """images: PIL list; txt_tokens [B,512,D], pooled [B,P] (the constant text half). -> (prompt_embeds, pooled)."""
+    px = OS.preprocess(images, siglip_cfg.image)
+    img_tokens = OS.redux_embed(redux_state, OS.last_hidden_state(siglip_state, siglip_cfg, px))
+    return OF.redux_blend(txt_tokens.float(), img_tokens, pooled.float(), torch.tensor(s_embed, dtype=torch.float32),
+                          torch.tensor(s_pool, dtype=torch.float32))
+
+
+def executed_start(num_steps: int, strength: float) -> int:
+    return num_steps - int(min(num_steps * strength, num_steps))
+
+
+def pack_mask(mask: torch.Tensor) -> torch.Tensor:
+    B, H, W = mask.shape
+    m = mask.view(B, H // 8, 8, W // 8, 8).permute(0, 2, 4, 1, 3).reshape(B, 64, H // 8, W // 8)
+    return OF.pack_latents(m)
+
+
+def generate(p_flux, cfg, p_vae, prompt_embeds, pooled, guidance, num_steps, height, width, generator):
+    h, w = 2 * (height // 16), 2 * (width // 16)
+    z = torch.randn((1, 16, h, w), generator=generator, dtype=torch.bfloat16)
+    x = OF.sample(p_flux, cfg, OF.pack_latents(z).float(), prompt_embeds.float(), pooled.float(), guidance, num_steps,
+                  h // 2, w // 2)
+    lat = OF.unpack_latents(x, h, w)
+    return lat, OV.postprocess_u8(OV.decode_latents(lat, p_vae))
+
+
+def fill(p_flux, cfg, p_vae, image_u8: np.ndarray, mask_bool: np.ndarray, prompt_embeds, pooled, guidance, num_steps,
+         strength, generator):
+    """image_u8 [H,W,3], mask_bool [H,W] (True = repaint), H and W multiples of 16. -> (latents, image uint8 [1,H,W,3])."""
+    H, W = mask_bool.shape
+    h, w = H // 8, W // 8
+    img = OV.preprocess_image(torch.from_numpy(image_u8)[None])
+    mask = torch.from_numpy(mask_bool.astype(np.float32))[None]
+    start = executed_start(num_steps, strength)
+
+    def vae_sample(x):
+        mean, logvar = OV.encoder(x, p_vae).chunk(2, dim=1)
+        noise = torch.randn(mean.shape, generator=generator, dtype=torch.bfloat16).float()
+        return ((mean + torch.exp(0.5 * logvar.clamp(-30.0, 20.0)) * noise) - OV.SHIFT_FACTOR) * OV.SCALE_FACTOR
+
+    image_latents = OF.pack_latents(vae_sample(img))
+    noise = OF.pack_latents(torch.randn((1, 16, h, w), generator=generator, dtype=torch.bfloat16)).float()
+    s0 = float(OF.flow_match_sigmas(num_steps, noise.shape[1])[start])
+    latents = s0 * noise + (1.0 - s0) * image_latents
+    masked = OF.pack_latents(vae_sample(img * (1.0 - mask[:, None])))
+    cond = torch.cat([masked, pack_mask(mask)], dim=-1)
+    x = OF.sample(p_flux, cfg, latents, prompt_embeds.float(), pooled.float(), guidance, num_steps, h // 2, w // 2,
+                  extra_cond=cond, start_step=start)
+    lat = OF.unpack_latents(x, h, w)
+    return lat, OV.postprocess_u8(OV.decode_latents(lat, p_vae))

@@ -1,0 +1,96 @@
+"""GPU parity: the three pipeline mirrors (FluxPriorReduxPipeline, FluxPipeline with VAE output, FluxFillPipeline)
+end to end at reduced size vs the CPU fp32 oracle composition (oracle/pipelines.py) on the same bf16-rounded
+weights, same CPU generator."""
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from oracle import flux as OF
+from oracle import pipelines as OP
+from oracle import siglip as OS
+from oracle import vae as OV
+
+pytestmark = pytest.mark.gpu
+
+FLUX_SMALL = dict(d=256, heads=2, n_double=2, n_single=2, txt_dim=64, pooled_dim=32, out_channels=64, guidance=True)
+
+
+def rel_l2(got, want):
+    return ((got.float() - want.float()).norm() / want.float().norm().clamp_min(1e-12)).item()
+
+
+def synth_image(seed, h, w):
+    g = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.stack([np.sin(xx / 7 + c) * np.cos(yy / 9 - c) for c in range(3)], -1) * 0.4 + 0.5
+    img += g.normal(0, 0.05, img.shape)
+    return Image.fromarray((img.clip(0, 1) * 255).astype(np.uint8))
+
+
+def bf(p):
+    return {k: v.bfloat16().float() for k, v in p.items()}
+
+
+def test_redux_prior_matches_oracle(lib):
+    from domain_rag_b200 import redux as R
+    from domain_rag_b200 import siglip as S
+    cfgd = dict(hidden=144, layers=2, heads=2, mlp=272, patch=14, image=56)
+    st = bf(OS.init_state(OS.SiglipConfig(**cfgd), seed=6000))
+    rd = bf(OS.init_redux(seed=6100, d_in=144, d_hidden=192, d_out=64))
+    table = R.TextEmbeddingTable(txt_dim=64, pooled_dim=32, tokens=24)
+    pipe = R.FluxPriorReduxPipeline(S.SiglipVisionTower(S.SiglipConfig(**cfgd), st), S.ReduxImageEncoder(rd), table)
+    imgs = [synth_image(1, 80, 120), synth_image(2, 64, 64)]
+    out = pipe(imgs, prompt=["", "a b"], prompt_2=["", "a b"], prompt_embeds_scale=[0.8, 1.0], pooled_prompt_embeds_scale=[1.0, 1.0])
+    assert set(out.keys()) == {"prompt_embeds", "pooled_prompt_embeds"} and out.prompt_embeds.shape == (1, 24 + 16, 64)
+    rows = [table.lookup("", ""), table.lookup("a b", "a b")]
+    txt = torch.stack([r[0] for r in rows]).float().cpu()
+    pooled = torch.stack([r[1] for r in rows]).float().cpu()
+    want_e, want_p = OP.redux_prior(st, OS.SiglipConfig(**cfgd), rd, imgs, txt, pooled, [0.8, 1.0], [1.0, 1.0])
+    assert rel_l2(out.prompt_embeds.cpu(), want_e) < 2e-2
+    assert rel_l2(out.pooled_prompt_embeds.cpu(), want_p) < 1e-2
+    assert torch.equal(table.lookup("", None)[0], table.lookup("", "")[0])         # one constant per prompt
+    single = pipe(imgs[0], prompt="", prompt_2="", prompt_embeds_scale=[1.2], pooled_prompt_embeds_scale=[1.0])
+    assert single["prompt_embeds"].shape == (1, 40, 64)
+
+
+def test_generate_and_fill_match_oracle(lib):
+    from domain_rag_b200 import flux as F
+    from domain_rag_b200.vae import FluxVAE
+    p_vae = bf(OV.init_params(seed=5000, ch=32))
+    vae = FluxVAE(p_vae)
+    g = torch.Generator().manual_seed(5)
+    ctx, pooled = torch.randn(1, 24, 64, generator=g).bfloat16(), torch.randn(1, 32, generator=g).bfloat16()
+    H, W, T = 64, 96, 3
+
+    # FluxPipeline -> images
+    ocfg, cfg = OF.FluxConfig(in_channels=64, **FLUX_SMALL), F.FluxConfig(in_channels=64, **FLUX_SMALL)
+    p = bf(OF.init_params(ocfg, seed=3001))
+    pipe = F.FluxPipeline(F.FluxTransformer(cfg, p, max_batch=1, max_img_tokens=(H // 16) * (W // 16), txt_tokens=24), vae)
+    out = pipe(prompt_embeds=ctx, pooled_prompt_embeds=pooled, guidance_scale=2.5, num_inference_steps=T, height=H, width=W,
+               generator=torch.Generator("cpu").manual_seed(0))
+    want_lat, want_img = OP.generate(p, ocfg, p_vae, ctx, pooled, 2.5, T, H, W, torch.Generator("cpu").manual_seed(0))
+    assert len(out.images) == 1 and out.images[0].size == (W, H) and out.steps_run == T
+    assert rel_l2(out.latents.cpu(), want_lat) < 3e-2
+    diff = np.abs(np.asarray(out.images[0]).astype(np.int32) - want_img[0].numpy().astype(np.int32))
+    assert diff.mean() < 3.0, diff.mean()
+
+    # FluxFillPipeline (strength 0.7 of 3 steps -> 2 executed steps), image 70x100 -> resized to 64x96
+    ocfg, cfg = OF.FluxConfig(in_channels=384, **FLUX_SMALL), F.FluxConfig(in_channels=384, **FLUX_SMALL)
+    p = bf(OF.init_params(ocfg, seed=3002))
+    fill = F.FluxFillPipeline(F.FluxTransformer(cfg, p, max_batch=1, max_img_tokens=(H // 16) * (W // 16), txt_tokens=24), vae)
+    image = synth_image(3, 70, 100)
+    from domain_rag_b200.hostlogic import generate_outpaint_mask
+    mask, _ = generate_outpaint_mask(image, [(30, 20, 25, 30)])
+    res = fill(prompt_embeds=ctx, pooled_prompt_embeds=pooled, image=image, mask_image=mask, height=image.height,
+               width=image.width, guidance_scale=30.0, num_inference_steps=T, generator=torch.Generator("cpu").manual_seed(7),
+               strength=0.7)
+    assert res.steps_run == 2 and res.images[0].size == (W, H)
+    img_r = np.asarray(image.convert("RGB").resize((W, H), Image.LANCZOS))
+    mask_r = np.asarray(mask.resize((W, H), Image.LANCZOS)) >= 128
+    want_lat, want_img = OP.fill(p, ocfg, p_vae, img_r, mask_r, ctx, pooled, 30.0, T, 0.7, torch.Generator("cpu").manual_seed(7))
+    assert rel_l2(res.latents.cpu(), want_lat) < 4e-2, rel_l2(res.latents.cpu(), want_lat)
+    diff = np.abs(np.asarray(res.images[0]).astype(np.int32) - want_img[0].numpy().astype(np.int32))
+    assert diff.mean() < 3.0, diff.mean()
+    with pytest.raises(ValueError):
+        fill(prompt_embeds=ctx, pooled_prompt_embeds=pooled, image=image, mask_image=mask, num_inference_steps=3, strength=0.1)
