@@ -1,0 +1,142 @@
+"""CPU: file surface and host logic of the generation / composition entry points with stub
+pipelines in place of the GPU ones - flags equal the reference's, output trees and JSON records have the reference's
+names, bbox scaling / mask / resolution restore follow the reference's integer rules."""
+import json
+import os
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from domain_rag_b200 import compose_cli as CC
+from domain_rag_b200 import generate_cli as GC
+from domain_rag_b200 import hostlogic as H
+
+
+class _Out(dict):
+    __getattr__ = dict.__getitem__
+
+
+class StubPrior:
+    def __init__(self):
+        self.calls = []
+
+    def __call__(self, image, prompt=None, prompt_2=None, prompt_embeds_scale=1.0, pooled_prompt_embeds_scale=1.0):
+        self.calls.append(dict(n=len(image), prompt=prompt, prompt_2=prompt_2, se=prompt_embeds_scale, sp=pooled_prompt_embeds_scale))
+        return _Out(prompt_embeds="PE", pooled_prompt_embeds="PP")
+
+
+class StubPipe:
+    def __init__(self):
+        self.calls = []
+
+    def __call__(self, **kw):
+        self.calls.append(kw)
+        w, h = kw.get("width", 64), kw.get("height", 64)
+        return _Out(images=[Image.new("RGB", (16 * (w // 16), 16 * (h // 16)), (10, 200, 30))])
+
+
+class Pipes:
+    def __init__(self):
+        self.prior_redux, self.pipe, self.pipe_fill = StubPrior(), StubPipe(), StubPipe()
+
+
+def rand_img(path, w, h, seed=0):
+    Image.fromarray((np.random.default_rng(seed).random((h, w, 3)) * 255).astype(np.uint8)).save(path)
+
+
+def test_generate_cli_file_surface(tmp_path):
+    ns = vars(GC.build_parser().parse_args([]))
+    assert (ns["dataset"], ns["shots"], ns["output_dir"], ns["database"], ns["dataset_group"]) == (None, None, "result", "coco", None)
+    shot = tmp_path / "lamainpaint" / "DIOR" / "5_shot"
+    shot.mkdir(parents=True)
+    refs = tmp_path / "coco"
+    refs.mkdir()
+    rand_img(shot / "airport_1.jpg", 100, 70)
+    rand_img(shot / "bridge_2.jpg", 90, 90, 1)
+    sims = []
+    for r in range(1, 8):
+        rand_img(refs / f"r{r}.jpg", 40, 40, r)
+        sims.append({"rank": r, "similarity": 1.0 / (1 + r), "image_path": str(refs / f"r{r}.jpg"), "source_dataset": "coco"})
+    results = {"airport_1": [{"sample_id": "airport_1", "image_path": str(shot / "airport_1.jpg"), "category": "airport_1",
+                              "similar_images": sims}]}
+    pipes = Pipes()
+    base = GC.process_kshot_dataset_with_retrieval("DIOR", pipes.prior_redux, pipes.pipe, results, 5, str(tmp_path / "result"),
+                                                   str(tmp_path / "lamainpaint"))
+    assert os.path.basename(os.path.dirname(base)) == "DIOR_5shot_retrieval"
+    assert os.path.basename(base).startswith("results_coco_0.8_target_1.0_cocotext_1.0_targettext_1.0_")
+    files = set(os.listdir(os.path.join(base, "airport_1")))
+    assert {f"generated_image_rank{r}.png" for r in range(1, 6)} <= files and "generated_image_rank6.png" not in files
+    assert {"params.txt", "target_input.png", "ref_inputrank1.jpg", "ref_inforank1_sim0.5000.txt"} <= files   # no separator (sic)
+    assert os.listdir(os.path.join(base, "bridge_2")) == ["error.txt"]
+    bp = open(os.path.join(base, "batch_params.txt")).read()
+    assert "成功处理样本数: 1" in bp and "失败处理样本数: 1" in bp and "总共生成图像数: 5" in bp and "生成图像尺寸统计:\n\n完成时间" in bp
+    c = pipes.prior_redux.calls[0]
+    assert c == dict(n=2, prompt=["", ""], prompt_2=["", ""], se=[0.8, 1.0], sp=[1.0, 1.0])
+    k = pipes.pipe.calls[0]
+    assert (k["guidance_scale"], k["num_inference_steps"], k["height"], k["width"]) == (2.5, 50, 1024, 1024)
+    assert k["generator"].initial_seed() == 0 and k["prompt_embeds"] == "PE"
+    assert "生成图像尺寸: 96x64" in open(os.path.join(base, "airport_1", "params.txt")).read()
+
+
+def test_compose_cli_file_surface(tmp_path):
+    ns = vars(CC.build_parser().parse_args([]))
+    for k, v in dict(dataset=None, dataset_group="all", sample_id=None, shot=1, min_dimension=1024, custom_upscale=None,
+                     process_id=None, collect_only=False, multi_bbox=False, resume=False, log_file=None, failed_only=False,
+                     multi_gpu=False, num_gpus=None).items():
+        assert ns[k] == v, k
+    ds_dir = tmp_path / "datasets" / "DIOR"
+    (ds_dir / "annotations").mkdir(parents=True)
+    (ds_dir / "train").mkdir()
+    rand_img(ds_dir / "train" / "airport_1.jpg", 640, 480)
+    json.dump({"images": [{"id": 7, "file_name": "airport_1.jpg"}], "categories": [{"id": 3, "name": "airport"}],
+               "annotations": [{"image_id": 7, "category_id": 3, "bbox": [100.5, 50, 200, 120]},
+                               {"image_id": "7", "category_id": 3, "bbox": [10, 400, 50, 60]}]},
+              open(ds_dir / "annotations" / "5_shot.json", "w"))
+    sdir = tmp_path / "result" / "DIOR_5shot_retrieval" / "results_x" / "airport_1"
+    sdir.mkdir(parents=True)
+    for r in (1, 2):
+        rand_img(sdir / f"generated_image_rank{r}.png", 64, 64, r)
+    pipes = Pipes()
+    log = CC.process_sample_hires("DIOR", "airport_1", pipes, "PID", shot_number=5, datasets_dir=str(tmp_path / "datasets"),
+                                  result_dir=str(tmp_path / "result"), outpaint_base=str(tmp_path / "outpaint_hires"),
+                                  seed_fn=lambda: 123)
+    assert log["status"] == "completed", log["error"]
+    out = tmp_path / "outpaint_hires" / "process_PID" / "DIOR" / "5_shot" / "airport_1"
+    p = "DIOR_airport_1_5shot"
+    want = {f"{p}_original.png", f"{p}_bbox1_original.jpg", f"{p}_bbox2_original.jpg", f"{p}_upscaled_bg.png"}
+    for r in (1, 2):
+        want |= {f"{p}_mask_{r}.png", f"{p}_bg_{r}_original.png", f"{p}_hires_result_{r}.png", f"{p}_final_result_{r}.png",
+                 f"{p}_params_{r}.json"}
+    assert want <= set(os.listdir(out))
+    # 640x480 -> upsampled by 1024/480 to 1365x1024 (int truncation), bbox scaled with int(); final restored to int(size / f)
+    f = 1024 / 480
+    assert log["up_scale_factor"] == pytest.approx(f) and tuple(log["upscaled_resolution"]) == (int(640 * f), 1024)
+    prm = json.load(open(out / f"{p}_params_1.json"))
+    assert prm["processed_bbox_coords_list"] == [[int(c * f) for c in [100.5, 50, 200, 120]], [int(c * f) for c in [10, 400, 50, 60]]]
+    assert (prm["strength"], prm["guidance_scale"], prm["seed"], prm["num_bbox"], prm["categories"]) == (0.8, 30.0, 123, 2, ["airport", "airport"])
+    k = pipes.pipe_fill.calls[0]
+    assert (k["width"], k["height"], k["strength"], k["guidance_scale"], k["num_inference_steps"]) == (1365, 1024, 0.8, 30.0, 50)
+    assert k["generator"].initial_seed() == 123
+    mask = np.array(Image.open(out / f"{p}_mask_1.png"))
+    want_mask, _ = H.generate_outpaint_mask(Image.new("RGB", (1365, 1024)), prm["processed_bbox_coords_list"])
+    np.testing.assert_array_equal(mask, np.array(want_mask))
+    hires = Image.open(out / f"{p}_hires_result_1.png")
+    final = Image.open(out / f"{p}_final_result_1.png")
+    assert hires.size == (1360, 1024) and final.size == (int(1360 / f), int(1024 / f))
+    assert pipes.prior_redux.calls[0] == dict(n=1, prompt="", prompt_2="", se=[1.0], sp=[1.0])
+    # result JSON, merge, collection, resume log
+    res = CC.formatted_result_json("DIOR", [log], 5, "PID")
+    path = CC.save_formatted_result_json("DIOR", res, 5, "PID", str(tmp_path / "outpaint_hires"))
+    assert path.endswith("DIOR/5_shot/outpaint_results_5shot.json") and json.load(open(path))["successful_samples"] == 1
+    merged = CC.merge_gpu_results("DIOR", [dict(res, gpu_process_id="a"), dict(res, gpu_process_id="b")], 5, "PID")
+    assert merged["multi_gpu"] and merged["num_gpus"] == 2 and len(merged["samples"]) == 2 and merged["gpu_process_ids"] == ["a", "b"]
+    coll = CC.copy_final_results_to_collection("PID", 5, str(tmp_path / "outpaint_hires"), str(tmp_path / "final_results"))
+    assert sorted(os.listdir(os.path.join(coll, "DIOR", "5_shot"))) == [f"{p}_final_result_1.png", f"{p}_final_result_2.png"]
+    logf = tmp_path / "run.log"
+    logf.write_text("样本 a 处理完成，耗时 1.00 秒\n样本 b 处理失败，耗时 2.00 秒\n处理样本 c 时出错: boom\n样本 c 处理完成，耗时 3 秒\n")
+    assert CC.parse_resume_log(str(logf)) == ({"a", "c"}, {"b"})
+    # a sample with neither annotation nor backgrounds is an error record, not an exception
+    bad = CC.process_sample_hires("DIOR", "nope", pipes, "PID", shot_number=5, datasets_dir=str(tmp_path / "datasets"),
+                                  result_dir=str(tmp_path / "result"), outpaint_base=str(tmp_path / "outpaint_hires"))
+    assert bad["status"] == "error" and bad["error"]
