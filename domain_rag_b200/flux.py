@@ -368,3 +368,58 @@ class FluxFillPipeline(FluxPipeline):
         packed, _ = self._denoise(latents, h, w, prompt_embeds, pooled_prompt_embeds, guidance_scale, num_inference_steps,
                                   start, cond)
         return self._finish(packed, h, w, num_inference_steps - start, output_type)
+
+
+def from_diffusers_state_dict(sd: Dict[str, torch.Tensor], cfg: FluxConfig) -> Dict[str, torch.Tensor]:
+    """FluxTransformer2DModel (diffusers) checkpoint keys -> the fused layout of `param_shapes` (data movement only):
+    q/k/v projections stacked into one [3d, d] matrix, the single blocks' proj_mlp kept separate from qkv, every
+    AdaLN modulation Linear stacked into `mod.w` in block order (img then txt per double block; diffusers' chunk
+    order shift/scale/gate and, for the final layer, scale/shift is already the order the engine reads)."""
+    out: Dict[str, torch.Tensor] = {}
+
+    def lin(dst_w, dst_b, src):
+        out[dst_w], out[dst_b] = sd[src + ".weight"], sd[src + ".bias"]
+
+    lin("x_in.w", "x_in.b", "x_embedder")
+    lin("ctx_in.w", "ctx_in.b", "context_embedder")
+    for dst, src in (("t_in", "timestep_embedder"), ("g_in", "guidance_embedder"), ("p_in", "text_embedder")):
+        if dst == "g_in" and not cfg.guidance:
+            continue
+        lin(f"{dst}.w1", f"{dst}.b1", f"time_text_embed.{src}.linear_1")
+        lin(f"{dst}.w2", f"{dst}.b2", f"time_text_embed.{src}.linear_2")
+    mod_w, mod_b = [], []
+    for i in range(cfg.n_double):
+        b = f"transformer_blocks.{i}."
+        for st, norm, q, k, v, o, nq, nk, ff in (
+                ("img", "norm1", "attn.to_q", "attn.to_k", "attn.to_v", "attn.to_out.0", "attn.norm_q", "attn.norm_k", "ff"),
+                ("txt", "norm1_context", "attn.add_q_proj", "attn.add_k_proj", "attn.add_v_proj", "attn.to_add_out",
+                 "attn.norm_added_q", "attn.norm_added_k", "ff_context")):
+            p = f"double.{i}.{st}."
+            mod_w.append(sd[b + norm + ".linear.weight"])
+            mod_b.append(sd[b + norm + ".linear.bias"])
+            out[p + "qkv.w"] = torch.cat([sd[b + n + ".weight"] for n in (q, k, v)], 0)
+            out[p + "qkv.b"] = torch.cat([sd[b + n + ".bias"] for n in (q, k, v)], 0)
+            out[p + "qnorm"], out[p + "knorm"] = sd[b + nq + ".weight"], sd[b + nk + ".weight"]
+            lin(p + "out.w", p + "out.b", b + o)
+            lin(p + "mlp1.w", p + "mlp1.b", b + ff + ".net.0.proj")
+            lin(p + "mlp2.w", p + "mlp2.b", b + ff + ".net.2")
+    for i in range(cfg.n_single):
+        b, p = f"single_transformer_blocks.{i}.", f"single.{i}."
+        mod_w.append(sd[b + "norm.linear.weight"])
+        mod_b.append(sd[b + "norm.linear.bias"])
+        out[p + "qkv.w"] = torch.cat([sd[b + f"attn.to_{n}.weight"] for n in "qkv"], 0)
+        out[p + "qkv.b"] = torch.cat([sd[b + f"attn.to_{n}.bias"] for n in "qkv"], 0)
+        out[p + "qnorm"], out[p + "knorm"] = sd[b + "attn.norm_q.weight"], sd[b + "attn.norm_k.weight"]
+        lin(p + "mlp.w", p + "mlp.b", b + "proj_mlp")
+        lin(p + "out.w", p + "out.b", b + "proj_out")
+    mod_w.append(sd["norm_out.linear.weight"])
+    mod_b.append(sd["norm_out.linear.bias"])
+    out["mod.w"], out["mod.b"] = torch.cat(mod_w, 0), torch.cat(mod_b, 0)
+    lin("final.w", "final.b", "proj_out")
+    missing = [n for n in param_shapes(cfg) if n not in out]
+    if missing:
+        raise KeyError(f"checkpoint lacks parameters for: {missing[:4]}")
+    for n, shape in param_shapes(cfg).items():
+        if tuple(out[n].shape) != tuple(shape):
+            raise ValueError(f"{n}: checkpoint shape {tuple(out[n].shape)} != expected {tuple(shape)}")
+    return out
