@@ -209,6 +209,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=["compose", "scan"])
+    ap.add_argument("--scope", default="full", choices=["full", "loop"],
+                    help="compose: full = prior + Fill pipeline + VAE per image; loop = blend + 50 denoising steps only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     workload = args.workload or default_workload()

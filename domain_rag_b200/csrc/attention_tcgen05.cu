@@ -10,7 +10,7 @@
 //                 past the sequence end zero-filled by TMA);
 //   warp 1        MMA issuer (one thread): S_X = Q_X K_j^T (UMMA 128x128x16, SS) into TMEM, and
 //                 O_X += P_X V_j with P read straight from TMEM (TS form) and V consumed MN-major from
-//                 its row-major tile (UMMA 128x64x16 per 64-wide half of the head dim);
+//                 its row-major tile (one UMMA 128xHDx16 per 16 keys, the 64-wide halves chained by the descriptor LBO);
 //   warps 4-7 / 8-11  softmax warpgroup of tile A / B: thread = query row. Pass 1 reads the score row
 //                 from TMEM for the running max, lazy rescale of the TMEM-resident O (only when the max
 //                 grew by > 8 in the exp2 domain), pass 2 re-reads the scores, exponentiates and writes
@@ -150,65 +150,81 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     if (warp < 4) {
     setmaxnreg_dec<96>();
 
-    if (warp == 0 && lane == 0) {
+    // Both loops run on all 32 lanes with warp-uniform control flow; only the TMA / MMA / commit instructions are
+    // predicated on one elected lane, so shared-memory addresses and UMMA descriptors stay in uniform registers. A
+    // single-lane issuer paid ~4 R2UR per MMA and, with 32-64-cycle MMAs, was the bottleneck of the whole kernel.
+    if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        mbar_arrive_expect_tx(q_full, (has_b ? 2 : 1) * TILE_BYTES);
+        if (elect_one()) {
+            mbar_arrive_expect_tx(q_full, (has_b ? 2 : 1) * TILE_BYTES);
 #pragma unroll
-        for (int hf = 0; hf < Cfg::NH; ++hf) {
-            tma_load_3d(smem + Cfg::Q_OFF + hf * AT_HALF_BYTES, &tmQ, hf * 64, q0, bh, q_full);
-            if (has_b)
-                tma_load_3d(smem + Cfg::Q_OFF + TILE_BYTES + hf * AT_HALF_BYTES, &tmQ, hf * 64, q0 + AT_TILE, bh, q_full);
+            for (int hf = 0; hf < Cfg::NH; ++hf) {
+                tma_load_3d(smem + Cfg::Q_OFF + hf * AT_HALF_BYTES, &tmQ, hf * 64, q0, bh, q_full);
+                if (has_b)
+                    tma_load_3d(smem + Cfg::Q_OFF + TILE_BYTES + hf * AT_HALF_BYTES, &tmQ, hf * 64, q0 + AT_TILE, bh, q_full);
+            }
         }
+        __syncwarp();
         for (int j = 0; j < n_tiles; ++j) {
             const int st = j & 1, par = (j >> 1) & 1;
             uint8_t* kd = smem + Cfg::K_OFF + st * TILE_BYTES;
             uint8_t* vd = smem + Cfg::V_OFF + st * TILE_BYTES;
             mbar_wait(&k_empty[st], par ^ 1);
-            mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
 #pragma unroll
-            for (int hf = 0; hf < Cfg::NH; ++hf)
-                tma_load_3d(kd + hf * AT_HALF_BYTES, &tmK, hf * 64, j * AT_TILE, bh, &k_full[st]);
+                for (int hf = 0; hf < Cfg::NH; ++hf)
+                    tma_load_3d(kd + hf * AT_HALF_BYTES, &tmK, hf * 64, j * AT_TILE, bh, &k_full[st]);
+            }
+            __syncwarp();
             mbar_wait(&v_empty[st], par ^ 1);
-            mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
 #pragma unroll
-            for (int hf = 0; hf < Cfg::NH; ++hf)
-                tma_load_3d(vd + hf * AT_HALF_BYTES, &tmV, hf * 64, j * AT_TILE, bh, &v_full[st]);
+                for (int hf = 0; hf < Cfg::NH; ++hf)
+                    tma_load_3d(vd + hf * AT_HALF_BYTES, &tmV, hf * 64, j * AT_TILE, bh, &v_full[st]);
+            }
+            __syncwarp();
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);   // A = P from TMEM (K-major), B = V MN-major
-        const uint32_t q_addr = smem_u32(smem + Cfg::Q_OFF);
+        // O_x += P_x V: A = P from TMEM (K-major), B = V consumed MN-major from its row-major tile. One UMMA of N = HD
+        // per 16 keys: the two 64-wide halves of V are consecutive MN atoms AT_HALF_BYTES apart (descriptor LBO).
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD, 0, 1);
+        const uint64_t q_desc0 = umma_desc_k_sw128(smem_u32(smem + Cfg::Q_OFF));
+        const uint64_t k_desc0 = umma_desc_k_sw128(smem_u32(smem + Cfg::K_OFF));
+        const uint64_t v_desc0 = umma_desc_mn_sw128(smem_u32(smem + Cfg::V_OFF), Cfg::NH > 1 ? AT_HALF_BYTES : 0, 1024);
         auto issue_qk = [&](int x, int st) {     // S_x = Q_x K^T  (K tile already waited for)
-            const uint32_t k_addr = smem_u32(smem + Cfg::K_OFF + st * TILE_BYTES);
+            const uint64_t qd = q_desc0 + ((x * TILE_BYTES) >> 4), kd = k_desc0 + ((st * TILE_BYTES) >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < HD / 16; ++ks) {
-                const uint32_t off = (ks >> 2) * AT_HALF_BYTES + (ks & 3) * 32;
-                tc_mma_f16(tmem_base + x * 128, umma_desc_k_sw128(q_addr + x * TILE_BYTES + off),
-                           umma_desc_k_sw128(k_addr + off), idesc_qk, ks != 0);
+                for (int ks = 0; ks < HD / 16; ++ks) {
+                    const uint32_t off = ((ks >> 2) * AT_HALF_BYTES + (ks & 3) * 32) >> 4;
+                    tc_mma_f16(tmem_base + x * 128, qd + off, kd + off, idesc_qk, ks != 0);
+                }
+                tc_commit(&s_full[x]);
             }
-            tc_commit(&s_full[x]);
+            __syncwarp();
         };
         auto issue_pv = [&](int x, int st, int j) {   // O_x += P_x V   (P_x: packed bf16 in S_x columns [0,64))
-            const uint32_t v_addr = smem_u32(smem + Cfg::V_OFF + st * TILE_BYTES);
+            const uint64_t vd = v_desc0 + ((st * TILE_BYTES) >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < AT_TILE / 16; ++ks) {
-#pragma unroll
-                for (int nh = 0; nh < Cfg::NH; ++nh) {
-                    // V half nh: [128 kv rows][64 hd], 128-byte rows; 16 kv rows per k-step = 2048 B; SBO = 1024
-                    const uint64_t vdsc = umma_desc_mn_sw128(v_addr + nh * AT_HALF_BYTES + ks * 2048, 0, 1024);
-                    tc_mma_f16_ts(tmem_base + 256 + x * 128 + nh * 64, tmem_base + x * 128 + ks * 8, vdsc, idesc_pv,
+                for (int ks = 0; ks < AT_TILE / 16; ++ks)      // 16 kv rows per k-step = 2048 B inside each half
+                    tc_mma_f16_ts(tmem_base + 256 + x * 128, tmem_base + x * 128 + ks * 8, vd + ((ks * 2048) >> 4), idesc_pv,
                                   (j | ks) != 0);
-                }
+                tc_commit(&pv_done[x]);
             }
-            tc_commit(&pv_done[x]);
+            __syncwarp();
         };
         mbar_wait(q_full, 0);
         mbar_wait(&k_full[0], 0);
         tc_fence_after();
         issue_qk(0, 0);
         if (has_b) issue_qk(1, 0);
-        tc_commit(&k_empty[0]);
+        if (elect_one()) tc_commit(&k_empty[0]);
+        __syncwarp();
         for (int j = 0; j < n_tiles; ++j) {
             const int st = j & 1, par = (j >> 1) & 1;
             const int nst = (j + 1) & 1, npar = ((j + 1) >> 1) & 1;
@@ -228,8 +244,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 issue_pv(1, st, j);
                 if (more) issue_qk(1, nst);
             }
-            tc_commit(&v_empty[st]);
-            if (more) tc_commit(&k_empty[nst]);
+            if (elect_one()) {
+                tc_commit(&v_empty[st]);
+                if (more) tc_commit(&k_empty[nst]);
+            }
+            __syncwarp();
         }
     }
     } else {

@@ -234,7 +234,8 @@ __global__ void vit_patchify_kernel(const float* __restrict__ img, __nv_bfloat16
     out[i] = __float2bfloat16(v);
 }
 int vit_patchify(const float* img, __nv_bfloat16* out, int B, int R, int p, int kpad, cudaStream_t st) {
-    DRAG_REQUIRE(img && out && B >= 1 && R % p == 0 && kpad >= 3 * p * p && kpad % 8 == 0, "vit_patchify: bad arguments");
+    DRAG_REQUIRE(img && out && B >= 1 && p >= 1 && R >= p && kpad >= 3 * p * p && kpad % 8 == 0, "vit_patchify: bad arguments");
+    // stride == kernel, no padding: floor(R / p) patches per side, trailing pixels unused (SigLIP 384 / 14 = 27)
     const int g = R / p;
     const int64_t total = static_cast<int64_t>(B) * g * g * kpad;
     vit_patchify_kernel<<<ceil_div(total, 256), 256, 0, st>>>(img, out, B, R, p, g, kpad);

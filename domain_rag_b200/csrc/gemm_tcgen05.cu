@@ -79,12 +79,26 @@ __device__ __forceinline__ void load_a_tile(const GemmShape& sh, const CUtensorM
     }
 }
 
-__device__ __forceinline__ float gelu_tanh_f(float x) {
-    const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-    const float t = 1.f - 2.f / (__expf(2.f * u) + 1.f);
-    return 0.5f * x * (1.f + t);
+// Activations of the epilogues with one MUFU.EX2 and one MUFU.RCP each and no IEEE-division sequence (which costs
+// ~10 instructions and a slow-path branch per element and slowed the GELU GEMM by 14 %).
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float ex2_approx_f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// gelu_tanh(x) = 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3); with e = exp(2u): = x - x / (e + 1).
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+    const float k1 = 2.f * 0.7978845608028654f * 1.4426950408889634f;      // 2 sqrt(2/pi) log2(e)
+    const float k3 = k1 * 0.044715f;
+    const float e = ex2_approx_f(x * fmaf(k3, x * x, k1));
+    return fmaf(-x, rcp_approx(e + 1.f), x);
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx(1.f + ex2_approx_f(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
@@ -301,7 +315,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
+    // The producer and issuer loops run on ALL lanes of their warp with warp-uniform control flow and only the
+    // asynchronous instruction itself is predicated on one elected lane: addresses, descriptors and coordinates then
+    // live in uniform registers (UTMALDG / UTCHMMA take UR operands) instead of costing an R2UR each, which is what
+    // bounds a single-lane issuer at ~70 % tensor occupancy.
+    if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         int stage = 0, phase = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -312,13 +330,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* a_dst = tiles + stage * Cfg::STAGE_BYTES;
                 uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-                mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                load_a_tile(sh, &tmA, a_dst, kb, m_blk * G_BM, ib, iy, ix, &full[stage]);
-                tma_load_2d(b_dst, &tmB, kb * G_BK, n_blk * BN, &full[stage]);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    load_a_tile(sh, &tmA, a_dst, kb, m_blk * G_BM, ib, iy, ix, &full[stage]);
+                    tma_load_2d(b_dst, &tmB, kb * G_BK, n_blk * BN, &full[stage]);
+                }
+                __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = umma_idesc_bf16(G_BM, BN);
         int stage = 0, phase = 0;
@@ -334,15 +355,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 const uint32_t b_addr = a_addr + Cfg::A_BYTES;
                 const uint64_t a_desc = umma_desc_k_sw128(a_addr);
                 const uint64_t b_desc = umma_desc_k_sw128(b_addr);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < G_BK / 16; ++k) {
-                    // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the addr>>4 field
-                    tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < G_BK / 16; ++k) {
+                        // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the addr>>4 field
+                        tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    tc_commit(&empty[stage]);          // slot reusable once these MMAs have read it
                 }
-                tc_commit(&empty[stage]);          // slot reusable once these MMAs have read it
+                __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
-            tc_commit(&tmem_full[acc]);            // accumulator complete
+            if (elect_one()) tc_commit(&tmem_full[acc]);            // accumulator complete
+            __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= G_EPI_WARP0) {
@@ -433,8 +458,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
-        // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs; warp-uniform, see above)
         int stage = 0, phase = 0;
         for (int t = pair; t < num_tiles; t += num_pairs) {
             const int m_blk = t % sh.num_m, n_blk = t / sh.num_m;
@@ -447,21 +472,24 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
                 uint8_t* a_dst = tiles + stage * Cfg::STAGE_BYTES;
                 uint8_t* b_dst = a_dst + Cfg::A_BYTES;
                 const uint32_t full_leader = mapa_shared(smem_u32(&full[stage]), 0);
-                if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
-                if (!sh.conv) {
-                    tma_load_2d_2cta(a_dst, &tmA, kb * G_BK, a_row, full_leader);
-                } else {
+                int c1 = a_row, c2 = 0, c3 = 0, c0 = kb * G_BK;
+                if (sh.conv) {
                     const int tap = kb / sh.cblocks, cb = kb - tap * sh.cblocks;
                     const int dy = tap / sh.ksize, dx = tap - dy * sh.ksize;
-                    tma_load_4d_2cta(a_dst, &tmA, cb * 64, ix * sh.stride + dx - sh.pad, iy * sh.stride + dy - sh.pad, ib,
-                                     full_leader);
+                    c0 = cb * 64; c1 = ix * sh.stride + dx - sh.pad; c2 = iy * sh.stride + dy - sh.pad; c3 = ib;
                 }
-                tma_load_2d_2cta(b_dst, &tmB, kb * G_BK, b_row, full_leader);
+                if (elect_one()) {
+                    if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+                    if (!sh.conv) tma_load_2d_2cta(a_dst, &tmA, c0, c1, full_leader);
+                    else tma_load_4d_2cta(a_dst, &tmA, c0, c1, c2, c3, full_leader);
+                    tma_load_2d_2cta(b_dst, &tmB, kb * G_BK, b_row, full_leader);
+                }
+                __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0 && rank == 0) {
-        // ------------------------------------------------------------------ MMA issuer (leader only)
+    } else if (warp == 1 && rank == 0) {
+        // ------------------------------------------------------------------ MMA issuer (leader only; warp-uniform)
         constexpr uint32_t idesc = umma_idesc_bf16(2 * G_BM, BN);
         int stage = 0, phase = 0;
         int acc = 0, acc_phase = 0;
@@ -476,13 +504,17 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
                 const uint32_t b_addr = a_addr + Cfg::A_BYTES;
                 const uint64_t a_desc = umma_desc_k_sw128(a_addr);
                 const uint64_t b_desc = umma_desc_k_sw128(b_addr);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < G_BK / 16; ++k)
-                    tc_mma_f16_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-                tc_commit_2cta(&empty[stage], 3);
+                    for (int k = 0; k < G_BK / 16; ++k)
+                        tc_mma_f16_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    tc_commit_2cta(&empty[stage], 3);
+                }
+                __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
-            tc_commit_2cta(&tmem_full[acc], 3);
+            if (elect_one()) tc_commit_2cta(&tmem_full[acc], 3);
+            __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= G_EPI_WARP0) {

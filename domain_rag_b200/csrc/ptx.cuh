@@ -207,23 +207,15 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t ran
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// Arrive (count 1) on an mbarrier addressed in the shared::cluster window (possibly the peer CTA's).
+// Arrive (count 1) on an mbarrier addressed in the shared::cluster window (possibly the peer CTA's). Default
+// (.release.cta) semantics like CUTLASS' ClusterBarrier::arrive(cta_id): a cluster-scope release costs a membar
+// (SASS ERRBAR) per arrival and the data it would order here travels through TMEM / TMA, not through memory.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// try_wait with cluster-scope acquire: the arrivals come from the peer CTA / the pair's tensor core.
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred P1;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, P1;\n\t}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    }
-}
+// Waits on barriers whose arrivals come from the peer CTA, TMA or the pair's tensor core use the plain CTA-scope
+// try_wait: the cluster-scope acquire form makes ptxas emit an L1 invalidate (CCTL.IVALL) in every spin iteration.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                  "r"(ncols)

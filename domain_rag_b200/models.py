@@ -49,7 +49,7 @@ def load_model(device="cuda", want=("dev", "fill"), weights_dir: Optional[str] =
     tiny = size == "tiny"
     print("正在加载模型...")
     # --- image prompt path
-    scfg = S.SiglipConfig(hidden=144, layers=2, heads=2, mlp=272, patch=14, image=56) if tiny else S.SiglipConfig()
+    scfg = S.SiglipConfig(hidden=160, layers=2, heads=2, mlp=272, patch=14, image=60) if tiny else S.SiglipConfig()
     sstate = _maybe_load(weights_dir, "siglip.pt")
     rstate = _maybe_load(weights_dir, "redux.pt")
     txt_dim, pooled_dim, t5_tokens = (64, 32, 24) if tiny else (4096, 768, 512)
@@ -69,7 +69,7 @@ def load_model(device="cuda", want=("dev", "fill"), weights_dir: Optional[str] =
     vstate = _maybe_load(weights_dir, "vae.pt")
     if vstate is None:
         print("警告: 未找到VAE权重, 使用随机初始化")
-        vstate = _vae_random(seed + 3, 32 if tiny else 128)
+        vstate = _vae_random(seed + 3, 64 if tiny else 128)
     vae = FluxVAE(vstate, dev)
     # --- transformers
     base = dict(d=256, heads=2, n_double=2, n_single=2, txt_dim=txt_dim, pooled_dim=pooled_dim) if tiny else {}

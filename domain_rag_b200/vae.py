@@ -62,6 +62,9 @@ class FluxVAE:
                 self.conv[base] = _Conv(p[name], p[base + ".b"], self.device)
             elif name.endswith(".w") and p[name].dim() == 1:
                 base = name[:-2]
+                if p[name].numel() % 64:
+                    raise ValueError(f"{base}: {p[name].numel()} channels - the NHWC kernels need multiples of 64 "
+                                     "(FLUX.1 VAE: 128/256/512)")
                 self.norm[base] = (p[name].to(self.device, torch.bfloat16), p[base + ".b"].to(self.device, torch.bfloat16))
         for side in ("enc", "dec"):
             a = f"{side}.mid.attn"

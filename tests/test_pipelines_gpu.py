@@ -35,9 +35,9 @@ def bf(p):
 def test_redux_prior_matches_oracle(lib):
     from domain_rag_b200 import redux as R
     from domain_rag_b200 import siglip as S
-    cfgd = dict(hidden=144, layers=2, heads=2, mlp=272, patch=14, image=56)
+    cfgd = dict(hidden=160, layers=2, heads=2, mlp=272, patch=14, image=60)
     st = bf(OS.init_state(OS.SiglipConfig(**cfgd), seed=6000))
-    rd = bf(OS.init_redux(seed=6100, d_in=144, d_hidden=192, d_out=64))
+    rd = bf(OS.init_redux(seed=6100, d_in=160, d_hidden=192, d_out=64))
     table = R.TextEmbeddingTable(txt_dim=64, pooled_dim=32, tokens=24)
     pipe = R.FluxPriorReduxPipeline(S.SiglipVisionTower(S.SiglipConfig(**cfgd), st), S.ReduxImageEncoder(rd), table)
     imgs = [synth_image(1, 80, 120), synth_image(2, 64, 64)]
@@ -57,7 +57,7 @@ def test_redux_prior_matches_oracle(lib):
 def test_generate_and_fill_match_oracle(lib):
     from domain_rag_b200 import flux as F
     from domain_rag_b200.vae import FluxVAE
-    p_vae = bf(OV.init_params(seed=5000, ch=32))
+    p_vae = bf(OV.init_params(seed=5000, ch=64))
     vae = FluxVAE(p_vae)
     g = torch.Generator().manual_seed(5)
     ctx, pooled = torch.randn(1, 24, 64, generator=g).bfloat16(), torch.randn(1, 32, generator=g).bfloat16()

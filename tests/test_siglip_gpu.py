@@ -12,7 +12,7 @@ def rel_l2(got, want):
     return ((got.float() - want.float()).norm() / want.float().norm().clamp_min(1e-12)).item()
 
 
-@pytest.mark.parametrize("cfgd,B", [(dict(hidden=144, layers=2, heads=2, mlp=272, patch=14, image=56), 3),
+@pytest.mark.parametrize("cfgd,B", [(dict(hidden=160, layers=2, heads=2, mlp=272, patch=14, image=60), 3),
                                     (dict(hidden=1152, layers=2, heads=16, mlp=4304, patch=14, image=384), 1)])
 def test_siglip_tower_matches_oracle(lib, cfgd, B):
     from domain_rag_b200 import siglip as S

@@ -41,9 +41,9 @@ def test_conv2d_matches_torch(lib, B, H, W, Cin, Cout, k, stride):
     want = want.permute(0, 2, 3, 1)
     wt = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous().cuda()
     out = torch.full((B, Ho, Wo, Cout), 7.0, dtype=torch.bfloat16, device="cuda")
-    xc = x.cuda()
+    xc, bc = x.cuda(), bias.cuda()
     _lib.check(lib.drag_conv2d_nhwc(_lib.ptr(xc), B, H, W, Cin, _lib.ptr(wt), Cout, k, stride, pad, Ho, Wo, 0,
-                                    _lib.ptr(bias.cuda()), _lib.ptr(out), None, _lib.current_stream_ptr(xc.device)), "conv")
+                                    _lib.ptr(bc), _lib.ptr(out), None, _lib.current_stream_ptr(xc.device)), "conv")
     torch.cuda.synchronize()
     assert rel_l2(out.cpu(), want) < 1e-2
     assert (out.cpu().float() - want).abs().max().item() < 3e-2 * max(1.0, want.abs().max().item())
@@ -51,7 +51,7 @@ def test_conv2d_matches_torch(lib, B, H, W, Cin, Cout, k, stride):
     res = rnd((B, Ho, Wo, Cout), 4).cuda()
     out2 = torch.empty_like(out)
     _lib.check(lib.drag_conv2d_nhwc(_lib.ptr(xc), B, H, W, Cin, _lib.ptr(wt), Cout, k, stride, pad, Ho, Wo, 4,
-                                    _lib.ptr(bias.cuda()), _lib.ptr(out2), _lib.ptr(res), _lib.current_stream_ptr(xc.device)), "conv")
+                                    _lib.ptr(bc), _lib.ptr(out2), _lib.ptr(res), _lib.current_stream_ptr(xc.device)), "conv")
     torch.cuda.synchronize()
     assert rel_l2(out2.cpu(), want + res.cpu().float()) < 1e-2
 
@@ -68,7 +68,8 @@ def test_groupnorm_silu_matches_torch(lib, B, HW, C, silu):
     ws = torch.empty(B * 1024 * 2 * C + B * 64, dtype=torch.float32, device="cuda")
     out = torch.empty((B, HW, C), dtype=torch.bfloat16, device="cuda")
     xc = x.cuda()
-    _lib.check(lib.drag_groupnorm_nhwc(_lib.ptr(xc), _lib.ptr(out), B, HW, C, 32, _lib.ptr(g.cuda()), _lib.ptr(b.cuda()), 1e-6,
+    gc, bc = g.cuda(), b.cuda()          # keep the device copies alive for the launch
+    _lib.check(lib.drag_groupnorm_nhwc(_lib.ptr(xc), _lib.ptr(out), B, HW, C, 32, _lib.ptr(gc), _lib.ptr(bc), 1e-6,
                                        int(silu), _lib.ptr(ws), ws.numel(), _lib.current_stream_ptr(xc.device)), "gn")
     torch.cuda.synchronize()
     assert (out.cpu().float() - want).abs().max().item() < 3e-2
@@ -103,7 +104,7 @@ def test_upsample_softmax_layout_pixels(lib):
     assert (back[..., :3].float() - (u8.float() / 255 * 2 - 1)).abs().max().item() < 4e-3 and float(back[..., 3:].abs().max()) == 0
 
 
-@pytest.mark.parametrize("ch,h,w", [(32, 8, 12), (64, 16, 16)])
+@pytest.mark.parametrize("ch,h,w", [(64, 8, 12), (64, 16, 16)])
 def test_vae_decode_encode_match_oracle(lib, ch, h, w):
     from domain_rag_b200.vae import FluxVAE
     p = {k: v.bfloat16().float() for k, v in OV.init_params(seed=5000, ch=ch).items()}
