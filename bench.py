@@ -6,6 +6,7 @@
 Prints ONE JSON line on rank 0. Workloads:
   compose  (default once built) composed 1024^2 images/sec, 50 Flux-Redux steps per image.
   scan     corpus cosine-top-k: 1M x 512 fp32 embeddings per GPU, top-100, achieved HBM GB/s.
+  retrieve BASELINE config C2: 10k-image corpus -> CLIP ViT-L/14 embed -> resident index -> top-100 -> style re-rank.
 `--impl reference` times the CPU oracle (the reference's algorithm; its own third-party packages are
 not installable offline) on the host cores for the same metric/config.
 """
@@ -205,16 +206,23 @@ def run_scan_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="default: 4 (compose: 4 x --batch images), 20 (scan)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=["compose", "scan"])
+    ap.add_argument("--workload", default=None, choices=["compose", "scan", "retrieve"])
     ap.add_argument("--scope", default="full", choices=["full", "loop"],
                     help="compose: full = prior + Fill pipeline + VAE per image; loop = blend + 50 denoising steps only")
+    ap.add_argument("--batch", type=int, default=4,
+                    help="compose: compositions per GPU and step, run as one batch (C4: 32 compositions / 8 GPUs = 4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     workload = args.workload or default_workload()
-    if args.impl == "reference":
+    if args.steps is None:
+        args.steps = {"scan": 20, "retrieve": 3}.get(workload, 4)
+    if workload == "retrieve":
+        import bench_retrieve
+        out = bench_retrieve.run_reference(args) if args.impl == "reference" else bench_retrieve.run(args)
+    elif args.impl == "reference":
         out = run_scan_reference(args) if workload == "scan" else run_compose_reference(args)
     else:
         out = run_scan(args) if workload == "scan" else run_compose(args)

@@ -39,27 +39,36 @@ def prof_collect():
     return [(ms[i], work[i], cnt[i]) for i in range(2)]
 
 
-def build_model(device, seed=3000, in_channels=384):
+def build_model(device, seed=3000, in_channels=384, max_batch=1):
     import torch
 
     from domain_rag_b200.flux import FluxConfig, FluxPipeline, FluxTransformer, init_params_device
     cfg = FluxConfig(in_channels=in_channels, d=D, heads=HEADS, n_double=N_DOUBLE, n_single=N_SINGLE)
     params = init_params_device(cfg, seed=seed, device=device)
-    tr = FluxTransformer(cfg, params, max_batch=1, max_img_tokens=(HEIGHT // 16) * (WIDTH // 16), txt_tokens=S_TXT,
+    tr = FluxTransformer(cfg, params, max_batch=max_batch, max_img_tokens=(HEIGHT // 16) * (WIDTH // 16), txt_tokens=S_TXT,
                          device=device)
     return cfg, tr, FluxPipeline(tr)
 
 
-def synth_inputs(seed: int):
+def synth_inputs(seed: int, batch: int = 1):
     """Host-side (pinned) synthetic stand-ins for what the encoders / VAE would hand to the pipeline."""
     import torch
     g = torch.Generator().manual_seed(seed)
     s_img = (HEIGHT // 16) * (WIDTH // 16)
-    t5 = torch.randn(1, N_T5, 4096, generator=g).bfloat16().pin_memory()
-    redux = torch.randn(1, N_REDUX, 4096, generator=g).bfloat16().pin_memory()
-    pooled = torch.randn(1, 768, generator=g).bfloat16().pin_memory()
-    cond = torch.randn(1, s_img, 320, generator=g).bfloat16().pin_memory()   # masked-image latents (64) + mask (256)
+    t5 = torch.randn(batch, N_T5, 4096, generator=g).bfloat16().pin_memory()
+    redux = torch.randn(batch, N_REDUX, 4096, generator=g).bfloat16().pin_memory()
+    pooled = torch.randn(batch, 768, generator=g).bfloat16().pin_memory()
+    cond = torch.randn(batch, s_img, 320, generator=g).bfloat16().pin_memory()   # masked-image latents (64) + mask (256)
     return t5, redux, pooled, cond
+
+
+def blend_rows(redux_blend, t5, redux, pooled):
+    """One Redux blend per composition (each has its own background image) -> prompt tensors [B,1241,4096], [B,768]."""
+    import torch
+    outs = [redux_blend(t5[i:i + 1], redux[i:i + 1], pooled[i:i + 1], [1.0], [1.0]) for i in range(t5.shape[0])]
+    if len(outs) == 1:
+        return outs[0]
+    return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
 
 
 def run(args):
@@ -74,20 +83,21 @@ def run(args):
     rank, world, local = B.dist_setup(args.gpus)
     dev = torch.device("cuda", local)
     lib = _lib.load()
-    cfg, tr, pipe = build_model(dev)
-    t5_h, redux_h, pooled_h, cond_h = synth_inputs(3000 + rank)
+    Bc = max(1, int(getattr(args, "batch", 1)))
+    cfg, tr, pipe = build_model(dev, max_batch=Bc)
+    t5_h, redux_h, pooled_h, cond_h = synth_inputs(3000 + rank, Bc)
     t5, redux, pooled, cond = (t.to(dev) for t in (t5_h, redux_h, pooled_h, cond_h))
     s_img = (HEIGHT // 16) * (WIDTH // 16)
     gen = torch.Generator("cpu")
 
     def compose_device(seed):
         """Inputs already resident in HBM: blend -> 50 steps -> final latents (stay on the device)."""
-        pe, pp = redux_blend(t5, redux, pooled, [1.0], [1.0])
+        pe, pp = blend_rows(redux_blend, t5, redux, pooled)
         lat, _, _ = latents_cache[seed % len(latents_cache)]
         return pipe(prompt_embeds=pe, pooled_prompt_embeds=pp, guidance_scale=GUIDANCE, num_inference_steps=STEPS,
                     height=HEIGHT, width=WIDTH, latents=lat.clone(), extra_cond=cond)
 
-    latents_cache = [pipe.prepare_latents(1, HEIGHT, WIDTH, gen.manual_seed(s), dev) for s in range(2)]
+    latents_cache = [pipe.prepare_latents(Bc, HEIGHT, WIDTH, gen.manual_seed(s), dev) for s in range(2)]
     torch.cuda.synchronize()
 
     for i in range(args.warmup):
@@ -119,12 +129,12 @@ def run(args):
     # with the CPU generator, D2H of the final latents, every image
     def compose_e2e(seed):
         t5d, rd, pd, cd = (t.to(dev, non_blocking=True) for t in (t5_h, redux_h, pooled_h, cond_h))
-        pe, pp = redux_blend(t5d, rd, pd, [1.0], [1.0])
+        pe, pp = blend_rows(redux_blend, t5d, rd, pd)
         o = pipe(prompt_embeds=pe, pooled_prompt_embeds=pp, guidance_scale=GUIDANCE, num_inference_steps=STEPS,
                  height=HEIGHT, width=WIDTH, generator=gen.manual_seed(seed), extra_cond=cd)
         return o.latents.cpu()
 
-    n_e2e = max(1, min(args.steps, 3))
+    n_e2e = max(1, min(args.steps, 2))
     compose_e2e(0)
     B.barrier(world)
     t0 = time.perf_counter()
@@ -142,19 +152,20 @@ def run(args):
     kernels_per_forward = 12 + N_DOUBLE * 13 + N_SINGLE * 5 + 2   # see flux_engine.cu
     out = {
         "metric": "composed images/sec (1024^2, 50-step Flux-Redux, device-timed)",
-        "value": round(world / (ms_per_step * 1e-3), 5), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "value": round(Bc * world / (ms_per_step * 1e-3), 5), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "C4 per-GPU slice: Flux-Redux composition 1024^2, 50 steps, batch 1 per GPU "
-                               "(Fill-shaped MMDiT C_in=384, 19+38 blocks, S=1241+4096, guidance 30), random-init "
-                               "weights, synthetic T5/Redux tokens; VAE + encoders outside the timed region",
+        "config": {"workload": f"C4 per-GPU slice, denoising loop only: {Bc} Flux-Redux compositions per step and GPU as one "
+                               "batch, 1024^2, 50 steps (Fill-shaped MMDiT C_in=384, 19+38 blocks, S=1241+4096, guidance "
+                               "30), random-init weights, synthetic T5/Redux tokens; VAE + encoders outside the timed region",
+                   "batch_per_gpu": Bc,
                    "l2_policy": "23.8 GB of weights + 0.4 GB of activations stream per denoising step (>> 126 MB L2)",
                    "flops_per_image": STEPS * (gemm_fl + attn_fl),
-                   "achieved_tflops": round(STEPS * (gemm_fl + attn_fl) / (ms_per_step * 1e-3) / 1e12, 1)},
-        "e2e": {"value": round(world / e2e_s, 5), "unit": "images/s",
-                "h2d_bytes_per_step": int(sum(t.numel() * 2 for t in (t5_h, redux_h, pooled_h, cond_h)) + s_img * 64 * 2),
+                   "achieved_tflops": round(Bc * STEPS * (gemm_fl + attn_fl) / (ms_per_step * 1e-3) / 1e12, 1)},
+        "e2e": {"value": round(Bc * world / e2e_s, 5), "unit": "images/s",
+                "h2d_bytes_per_step": int(sum(t.numel() * 2 for t in (t5_h, redux_h, pooled_h, cond_h)) + Bc * s_img * 64 * 2),
                 "d2h_bytes_per_step": int(lat_h.numel() * 2)},
-        "gpu_launches": args.steps * (STEPS * (kernels_per_forward + 1) + 1),
+        "gpu_launches": args.steps * (STEPS * (kernels_per_forward + 1) + Bc),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": round(g_fl / (g_ms * 1e-3) / 1e12, 1), "peak": peak,
                      "unit": "TFLOP/s", "frac": round(g_fl / (g_ms * 1e-3) / 1e12 / peak, 4), "traffic": None,
@@ -225,10 +236,11 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------ full composition
 def run_full(args):
-    """One bench step = one COMPLETE composition per GPU through the pipeline mirrors: Redux prior (SigLIP so400m tower +
-    Redux embedder + blend with the constant text tokens) -> FluxFillPipeline at 1024^2 (VAE encode of the image and of the
-    masked image, 8x8 mask packing, 50 MMDiT steps at strength 1.0, VAE decode, uint8 pixels). `value`: inputs resident in
-    HBM; `e2e`: the public calls with PIL inputs (host preprocessing, pinned H2D, D2H of the image) inside the timed region."""
+    """One bench step = the C4 per-GPU slice (`--batch` COMPLETE compositions, default 4 = 32 compositions / 8 GPUs) run as
+    one batch through the pipeline mirrors: Redux prior per composition (SigLIP so400m tower + Redux embedder + blend with
+    the constant text tokens) -> FluxFillPipeline at 1024^2 (VAE encode of the images and of the masked images, 8x8 mask
+    packing, 50 MMDiT steps at strength 1.0, VAE decode, uint8 pixels). `value`: inputs resident in HBM; `e2e`: the public
+    calls with PIL inputs (host preprocessing, pinned H2D, D2H of the images) inside the timed region."""
     import numpy as np
     import torch
     from PIL import Image
@@ -243,31 +255,34 @@ def run_full(args):
     rank, world, local = B.dist_setup(args.gpus)
     dev = torch.device("cuda", local)
     lib = _lib.load()
-    pipes = load_model(device=dev, want=("fill",), weights_dir=None, size="full", max_side=HEIGHT, seed=3000)
+    Bc = max(1, int(getattr(args, "batch", 4)))
+    pipes = load_model(device=dev, want=("fill",), weights_dir=None, size="full", max_side=HEIGHT, seed=3000, max_batch=Bc)
     prior, fill = pipes.prior_redux, pipes.pipe_fill
     vae = fill.vae
     rng = np.random.default_rng(1000 + rank)
     yy, xx = np.mgrid[0:HEIGHT, 0:WIDTH].astype(np.float32)
     base = np.stack([np.sin(xx / (40 + 7 * c)) * np.cos(yy / (55 - 6 * c)) for c in range(3)], -1) * 0.35 + 0.5
-    target = Image.fromarray(((base + rng.normal(0, 0.04, base.shape)).clip(0, 1) * 255).astype(np.uint8))
-    background = Image.fromarray((rng.random((640, 640, 3)) * 255).astype(np.uint8))
-    mask, _ = H.generate_outpaint_mask(target, [(int(WIDTH * 0.35), int(HEIGHT * 0.35), int(WIDTH * 0.3), int(HEIGHT * 0.3))])
+    targets = [Image.fromarray(((base + rng.normal(0, 0.04, base.shape)).clip(0, 1) * 255).astype(np.uint8)) for _ in range(Bc)]
+    backgrounds = [Image.fromarray((rng.random((640, 640, 3)) * 255).astype(np.uint8)) for _ in range(Bc)]
+    masks = [H.generate_outpaint_mask(targets[i], [(int(WIDTH * (0.30 + 0.02 * i)), int(HEIGHT * 0.35), int(WIDTH * 0.3),
+                                                     int(HEIGHT * 0.3))])[0] for i in range(Bc)]
     gen = torch.Generator("cpu")
     s_img = (HEIGHT // 16) * (WIDTH // 16)
 
     # device-resident inputs of the `value` leg
-    px_dev = S.preprocess([background], prior.image_size).to(dev)
-    img_u8 = torch.from_numpy(np.asarray(target).copy())[None].to(dev)
-    mask_u8 = torch.from_numpy((np.asarray(mask) >= 128).astype(np.uint8))[None].to(dev)
+    px_dev = S.preprocess(backgrounds, prior.image_size).to(dev)
+    img_u8 = torch.from_numpy(np.stack([np.asarray(t) for t in targets])).to(dev)
+    mask_u8 = torch.from_numpy(np.stack([(np.asarray(m) >= 128).astype(np.uint8) for m in masks])).to(dev)
     txt_row = prior.text_table.lookup("", "")
     txt, pooled = txt_row[0][None].contiguous(), txt_row[1][None].contiguous()
-    noise_cache = [fill.prepare_latents(1, HEIGHT, WIDTH, gen.manual_seed(s), dev)[0] for s in range(2)]
+    noise_cache = [fill.prepare_latents(Bc, HEIGHT, WIDTH, gen.manual_seed(s), dev)[0] for s in range(2)]
     vgen = torch.Generator(device=dev)
     torch.cuda.synchronize()
 
     def compose_device(seed):
-        img_tokens = prior.image_embedder(prior.image_encoder.last_hidden_state(px_dev))
-        pe, pp = F.redux_blend(txt, img_tokens.contiguous(), pooled, [1.0], [1.0])
+        img_tokens = prior.image_embedder(prior.image_encoder.last_hidden_state(px_dev)).contiguous()
+        rows = [F.redux_blend(txt, img_tokens[i:i + 1], pooled, [1.0], [1.0]) for i in range(Bc)]
+        pe, pp = torch.cat([r[0] for r in rows]), torch.cat([r[1] for r in rows])
         vgen.manual_seed(seed)
         image_latents = F.pack_latents(vae.encode(img_u8, generator=vgen)).contiguous()
         sig0 = F.flow_match_sigmas(STEPS, s_img)[0]
@@ -278,9 +293,12 @@ def run_full(args):
         return vae.decode(F.unpack_latents(packed, HEIGHT // 8, WIDTH // 8), output_type="u8")
 
     def compose_e2e(seed):
-        out = prior([background], prompt="", prompt_2="", prompt_embeds_scale=[1.0], pooled_prompt_embeds_scale=[1.0])
-        return fill(image=target, mask_image=mask, height=HEIGHT, width=WIDTH, guidance_scale=GUIDANCE,
-                    num_inference_steps=STEPS, generator=gen.manual_seed(seed), strength=1.0, **out).images[0]
+        outs = [prior([bg], prompt="", prompt_2="", prompt_embeds_scale=[1.0], pooled_prompt_embeds_scale=[1.0])
+                for bg in backgrounds]
+        return fill(image=targets, mask_image=masks, height=HEIGHT, width=WIDTH, guidance_scale=GUIDANCE,
+                    num_inference_steps=STEPS, generator=gen.manual_seed(seed), strength=1.0,
+                    prompt_embeds=torch.cat([o.prompt_embeds for o in outs]),
+                    pooled_prompt_embeds=torch.cat([o.pooled_prompt_embeds for o in outs])).images
 
     for i in range(args.warmup):
         compose_device(i)
@@ -306,15 +324,15 @@ def run_full(args):
     (g_ms, g_fl, g_n), (a_ms, a_fl, a_n) = prof_collect()
     lib.drag_prof_enable(0)
 
-    n_e2e = max(1, min(args.steps, 3))
+    n_e2e = max(1, min(args.steps, 2))
     compose_e2e(0)
     B.barrier(world)
     t0 = time.perf_counter()
     for i in range(n_e2e):
-        img = compose_e2e(i)
+        imgs = compose_e2e(i)
     B.barrier(world)
     e2e_s = B.max_over_ranks(time.perf_counter() - t0, world) / n_e2e
-    assert img.size == (WIDTH, HEIGHT)
+    assert len(imgs) == Bc and imgs[0].size == (WIDTH, HEIGHT)
 
     if rank != 0:
         return None
@@ -322,23 +340,25 @@ def run_full(args):
     gemm_fl, attn_fl = flops_per_forward(s_img)
     peaks = B.measured_peaks()
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-    h2d = HEIGHT * WIDTH * 3 + HEIGHT * WIDTH + 3 * prior.image_size ** 2 * 4 + s_img * 64 * 2
+    h2d = Bc * (HEIGHT * WIDTH * 3 + HEIGHT * WIDTH + 3 * prior.image_size ** 2 * 4 + s_img * 64 * 2)
     return {
         "metric": "composed images/sec (1024^2, 50-step Flux-Redux, device-timed)",
-        "value": round(world / (ms_per_step * 1e-3), 5), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "value": round(Bc * world / (ms_per_step * 1e-3), 5), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "C4 per-GPU slice: one full Flux-Redux composition at 1024^2 per step and GPU, batch 1 like the "
-                               "reference: Redux prior (SigLIP so400m + Redux embedder + blend) -> Flux-Fill (VAE encode of image "
-                               "and masked image, mask packing, 50 MMDiT steps, C_in=384, 19+38 blocks, S=1241+4096, guidance 30, "
-                               "strength 1.0) -> VAE decode -> uint8 pixels; random-init weights, synthetic images; text tokens "
-                               "are per-prompt constants (T5/CLIP-text not on the path); LaMa out of scope",
+        "config": {"workload": f"C4 per-GPU slice (32 compositions / 8 GPUs): {Bc} full Flux-Redux compositions at 1024^2 per "
+                               "step and GPU, run as one batch: Redux prior per composition (SigLIP so400m + Redux embedder + "
+                               "blend) -> Flux-Fill (VAE encode of images and masked images, mask packing, 50 MMDiT steps, "
+                               "C_in=384, 19+38 blocks, S=1241+4096, guidance 30, strength 1.0) -> VAE decode -> uint8 pixels; "
+                               "random-init weights, synthetic images; text tokens are per-prompt constants (T5/CLIP-text not "
+                               "on the path); LaMa out of scope",
+                   "batch_per_gpu": Bc,
                    "l2_policy": "23.8 GB of weights + 0.4 GB of activations stream per denoising step (>> 126 MB L2)",
                    "flops_per_image": STEPS * (gemm_fl + attn_fl),
                    "flops_note": "denoising loop only; SigLIP/Redux/VAE (~8 TFLOP) are timed but not counted",
-                   "achieved_tflops": round(STEPS * (gemm_fl + attn_fl) / (ms_per_step * 1e-3) / 1e12, 1)},
-        "e2e": {"value": round(world / e2e_s, 5), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(HEIGHT * WIDTH * 3)},
+                   "achieved_tflops": round(Bc * STEPS * (gemm_fl + attn_fl) / (ms_per_step * 1e-3) / 1e12, 1)},
+        "e2e": {"value": round(Bc * world / e2e_s, 5), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(Bc * HEIGHT * WIDTH * 3)},
         "gpu_launches": int(g_n + a_n) * args.steps,
         "gpu_launches_note": "tcgen05 GEMM/conv + attention launches only (counted live); ~25 % more row kernels on top",
         "clocks": clocks,

@@ -1,0 +1,221 @@
+"""Retrieve workload of bench.py (BASELINE config C2): embed a 10 000-image synthetic corpus with the CLIP
+ViT-L/14 image tower (+ L2 normalise), keep the embeddings resident as the inner-product index of the GPU that made them,
+embed the 7 one-shot ArTaxOr queries, exact top-100, then the ResNet-50-stem style re-rank of the 7 x (1 + 100) images.
+
+Reference path this replaces (retrieval/clip100_resnet_style_all_shots.py): compute_coco_clip_features :270-296
+(batch-1 encode_image + normalise per image), clip_first_stage_retrieval :396-451 (faiss IndexFlatIP rebuilt per query),
+resnet_second_stage_rerank :454-497 (101 batch-1 stem passes per query).
+
+One bench "step" = the whole C2 job on every GPU (weak scaling: every rank embeds its own 10 000-image shard; the index
+is row-sharded, a search = local scan x top-k -> all-gather of the per-shard top-k -> merge). `value`: preprocessed
+images resident in HBM; `e2e`: pinned host tensors, H2D per batch, D2H of the ranked results. Roofline: the encoder is
+tensor-bound, 162.0 GFLOP per ViT-L/14 image.
+"""
+from __future__ import annotations
+
+import os
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+
+N_CORPUS, N_QUERY, TOP_K, EMBED_BATCH = 10_000, 7, 100, 250
+MODEL = "ViT-L/14"
+
+
+def vit_flops_per_image(cfg) -> float:
+    """per layer 2*L*d*3d (qkv) + 4*L^2*d (attention) + 2*L*d^2 (out) + 16*L*d^2 (MLP); + patch embed + proj."""
+    L, d, g = cfg.tokens, cfg.width, cfg.grid
+    layer = 2.0 * L * d * 3 * d + 4.0 * L * L * d + 2.0 * L * d * d + 16.0 * L * d * d
+    return cfg.layers * layer + 2.0 * g * g * (3 * cfg.patch ** 2) * d + 2.0 * d * cfg.out_dim
+
+
+def synth_images(n, res, seed, device, chunk=500):
+    """Preprocessed image tensors fp32 [n,3,res,res] (what `preprocess(PIL)` stacks to), generated on the device:
+    low-frequency structure + noise so embeddings are spread out."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = torch.empty((n, 3, res, res), dtype=torch.float32, device=device)
+    for i in range(0, n, chunk):
+        m = min(chunk, n - i)
+        low = torch.randn((m, 3, 8, 8), generator=g, device=device)
+        out[i:i + m] = torch.nn.functional.interpolate(low, size=(res, res), mode="bilinear") \
+            + 0.3 * torch.randn((m, 3, res, res), generator=g, device=device)
+    return out
+
+
+def run(args):
+    import numpy as np
+    import torch
+
+    from domain_rag_b200 import _lib, clip
+    from domain_rag_b200 import benchutil as B
+    from domain_rag_b200.index import ShardedIndexFlatIP
+    from domain_rag_b200.resnet import ResNetEncoder
+    from domain_rag_b200.retrieval import rerank_by_style
+
+    rank, world, local = B.dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    model, _ = clip.load(MODEL, device=dev, seed=2000)
+    cfg = clip.CONFIGS[MODEL]
+    stem = ResNetEncoder(seed=2000).to(dev).eval()
+    corpus = synth_images(N_CORPUS, cfg.image, 1001 + rank, dev)
+    queries = synth_images(N_QUERY, cfg.image, 1002, dev)
+    style_imgs = synth_images(N_QUERY * (1 + TOP_K), 256, 1003, dev).mul_(0.2).add_(0.5).clamp_(0, 1)  # [707,3,256,256] in [0,1]
+    torch.cuda.synchronize()
+
+    def job(corpus_src, query_src, style_src, to_host):
+        """The C2 job. *_src are device tensors (value leg) or pinned host tensors (e2e leg)."""
+        emb = torch.empty((N_CORPUS, cfg.out_dim), dtype=torch.float32, device=dev)
+        for i in range(0, N_CORPUS, EMBED_BATCH):
+            x = corpus_src[i:i + EMBED_BATCH].to(dev, non_blocking=True)
+            emb[i:i + EMBED_BATCH] = model.encode_image(x, normalize=True)
+        ix = ShardedIndexFlatIP(cfg.out_dim, rank, world, device=local)
+        ix.add_local(emb, lo=rank * N_CORPUS, ntotal_global=N_CORPUS * world)     # zero-copy: embeddings ARE the shard
+        q = model.encode_image(query_src.to(dev, non_blocking=True), normalize=True)
+        D, I = ix.search(q, TOP_K)
+        feats = stem.style_features(style_src.to(dev, non_blocking=True))          # one launch for all 707 images
+        if not to_host:
+            return D, I, feats
+        Dh, Ih, fh = D.cpu().numpy(), I.cpu().numpy(), feats.cpu().numpy()
+        ranked = []
+        for qi in range(N_QUERY):                                                    # host sort exactly as the reference
+            first = [{"similarity": float(Dh[qi, j]), "image_path": str(int(Ih[qi, j])), "source_dataset": "coco"}
+                     for j in range(TOP_K)]
+            base = qi * (1 + TOP_K)
+            ranked.append(rerank_by_style(fh[base], list(fh[base + 1: base + 1 + TOP_K]), first))
+        return Dh, Ih, ranked
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        job(corpus, queries, style_imgs, False)
+    B.barrier(world)
+    sampler = B.ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    B.barrier(world)
+    torch.cuda.cudart().cudaProfilerStart()
+    e0.record()
+    for _ in range(args.steps):
+        job(corpus, queries, style_imgs, False)
+    e1.record()
+    torch.cuda.cudart().cudaProfilerStop()
+    B.barrier(world)
+    total_ms = B.max_over_ranks(e0.elapsed_time(e1), world)
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # dominant kernels: event bracket around every GEMM / attention launch of one more job (same stream)
+    import ctypes as C
+    lib.drag_prof_enable(1)
+    job(corpus, queries, style_imgs, False)
+    torch.cuda.synchronize()
+    ms, work, cnt = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_int * 2)()
+    _lib.check(lib.drag_prof_collect(ms, work, cnt, 2), "drag_prof_collect")
+    lib.drag_prof_enable(0)
+    (g_ms, g_fl, g_n), (a_ms, a_fl, a_n) = [(ms[i], work[i], cnt[i]) for i in range(2)]
+
+    # end to end: pinned host tensors in, ranked lists out
+    corpus_h = torch.empty(corpus.shape, dtype=torch.float32, pin_memory=True)
+    corpus_h.copy_(corpus)
+    queries_h, style_h = queries.cpu().pin_memory(), style_imgs.cpu().pin_memory()
+    job(corpus_h, queries_h, style_h, True)
+    B.barrier(world)
+    n_e2e = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        Dh, Ih, ranked = job(corpus_h, queries_h, style_h, True)
+    B.barrier(world)
+    e2e_s = B.max_over_ranks(time.perf_counter() - t0, world) / n_e2e
+    assert len(ranked) == N_QUERY and len(ranked[0]) == TOP_K and ranked[0][0]["rank"] == 1
+
+    if rank != 0:
+        return None
+    ms_per_step = total_ms / args.steps
+    n_img = N_CORPUS + N_QUERY
+    flops = vit_flops_per_image(cfg) * n_img
+    peaks = B.measured_peaks()
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    h2d = (corpus_h.numel() + queries_h.numel() + style_h.numel()) * 4
+    return {
+        "metric": "C2 retrieval: corpus images embedded + indexed + queried per second (ViT-L/14, top-100, style re-rank)",
+        "value": round(n_img * world / (ms_per_step * 1e-3), 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"C2 per GPU: {N_CORPUS} synthetic 224^2 images -> CLIP {MODEL} embed (batches of {EMBED_BATCH}) + "
+                               f"L2 normalise -> resident fp32 index shard; {N_QUERY} queries -> exact top-{TOP_K} "
+                               f"(sharded: all-gather of per-shard top-k) -> ResNet-50-stem style statistics of "
+                               f"{N_QUERY}x(1+{TOP_K}) 256^2 images; random-init weights",
+                   "l2_policy": "6 GB of images stream through per step (>> 126 MB L2)",
+                   "flops_per_image": vit_flops_per_image(cfg),
+                   "achieved_tflops": round(flops / (ms_per_step * 1e-3) / 1e12, 1)},
+        "e2e": {"value": round(n_img * world / e2e_s, 1), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(N_QUERY * TOP_K * 12 + N_QUERY * (1 + TOP_K) * 128 * 4)},
+        "gpu_launches": int(g_n + a_n) * args.steps,
+        "gpu_launches_note": "tcgen05 GEMM + attention launches (counted live); LayerNorm / patchify / scan / stem kernels on top",
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": round(g_fl / (g_ms * 1e-3) / 1e12, 1), "peak": peak, "unit": "TFLOP/s",
+                     "frac": round(g_fl / (g_ms * 1e-3) / 1e12 / peak, 4), "traffic": None,
+                     "kernel": "gemm_bf16_tcgen05_2cta_kernel (all GEMM launches of one C2 job)",
+                     "kernel_ms": round(g_ms / max(g_n, 1), 4), "launches": g_n, "share_of_step": round(g_ms / ms_per_step, 4),
+                     "peak_source": peaks["source"] + " (sustained)",
+                     "attention": {"achieved": round(a_fl / (a_ms * 1e-3) / 1e12, 1), "kernel_ms": round(a_ms / max(a_n, 1), 4),
+                                   "launches": a_n, "share_of_step": round(a_ms / ms_per_step, 4)}},
+        "cpu_baseline": cpu_baseline(),
+    }
+
+
+def cpu_baseline(n_sample: int = 16):
+    """Oracle on the host cores: ViT-L/14 fp32 embed of a bounded sample, scaled linearly to the corpus (the scan and
+    the stem statistics are < 1 % of the CPU time at C2 sizes and are timed on their full sizes)."""
+    import numpy as np
+    import torch
+
+    from oracle import ip_topk as OI
+    from oracle import stem as OS
+    from oracle import vit as OV
+    torch.set_num_threads(os.cpu_count())
+    cfg = OV.CONFIGS[MODEL]
+    state = OV.init_state(cfg, 2000)
+    x = torch.randn(n_sample, 3, cfg.image, cfg.image, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        OV.embed(state, cfg, x[:2])
+        t0 = time.perf_counter()
+        OV.embed(state, cfg, x)
+        t_img = (time.perf_counter() - t0) / n_sample
+    g = np.random.default_rng(1)
+    X = g.standard_normal((N_CORPUS, cfg.out_dim)).astype(np.float32)
+    q = g.standard_normal((N_QUERY, cfg.out_dim)).astype(np.float32)
+    t0 = time.perf_counter()
+    OI.ip_topk(X, q, TOP_K)
+    t_scan = time.perf_counter() - t0
+    from domain_rag_b200.resnet import random_stem_state
+    imgs = torch.rand(32, 3, 256, 256, generator=torch.Generator().manual_seed(2))
+    t0 = time.perf_counter()
+    OS.style_features(imgs, random_stem_state(2000))
+    t_stem = (time.perf_counter() - t0) / 32 * N_QUERY * (1 + TOP_K)
+    total = t_img * (N_CORPUS + N_QUERY) + t_scan + t_stem
+    return {"value": round((N_CORPUS + N_QUERY) / total, 2), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"oracle.vit.embed fp32 on {n_sample} images ({t_img * 1e3:.0f} ms/img) scaled to {N_CORPUS + N_QUERY}; "
+                      f"oracle.ip_topk full size ({t_scan * 1e3:.0f} ms); oracle.stem on 32 images scaled to "
+                      f"{N_QUERY * (1 + TOP_K)} ({t_stem:.1f} s)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    vals, cb = [], None
+    for _ in range(max(1, min(args.steps, 2))):
+        cb = cpu_baseline()
+        vals.append(cb["value"])
+    val = sum(vals) / len(vals)
+    cb["value"] = val
+    return {"impl": "reference",
+            "metric": "C2 retrieval: corpus images embedded + indexed + queried per second (ViT-L/14, top-100, style re-rank)",
+            "value": val, "unit": "images/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round((N_CORPUS + N_QUERY) / val * 1e3, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C2 per GPU: {N_CORPUS} images, CLIP {MODEL}, top-{TOP_K}, style re-rank (CPU oracle, bounded "
+                                   "sample scaled linearly)"},
+            "cpu_baseline": cb, "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

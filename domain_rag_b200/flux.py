@@ -327,7 +327,9 @@ def pack_mask(mask: torch.Tensor) -> torch.Tensor:
 class FluxFillPipeline(FluxPipeline):
     """Mirror of the FluxFillPipeline call of the composition script (outpainting_updown_sampling_redux.py:1246-1257):
     pipe_fill(image=, mask_image=, height=, width=, guidance_scale=, num_inference_steps=50, prompt_embeds=,
-    pooled_prompt_embeds=, generator=, strength=).images[0]. The transformer is the Fill variant (in_channels 384 =
+    pooled_prompt_embeds=, generator=, strength=).images[0]. `image` / `mask_image` may also be equally long lists
+    (one composition per entry, prompt tensors [B,...] or [1,...] broadcast; the C4 per-GPU slice runs its 4
+    compositions as one batch). The transformer is the Fill variant (in_channels 384 =
     64 latent + 64 masked-image latent + 256 mask channels). Host work: PIL resize to multiples of 16 (Lanczos, like
     VaeImageProcessor), mask binarisation at 0.5. Generator draws, in order: VAE sample of the image, the initial noise
     (bf16, CPU generator), VAE sample of the masked image."""
@@ -342,18 +344,28 @@ class FluxFillPipeline(FluxPipeline):
             raise ValueError("image and mask_image are required")
         dev = self.transformer.device
         output_type = output_type or "pil"
-        height = image.height if height is None else int(height)
-        width = image.width if width is None else int(width)
+        images = list(image) if isinstance(image, (list, tuple)) else [image]
+        masks = list(mask_image) if isinstance(mask_image, (list, tuple)) else [mask_image]
+        if len(masks) != len(images):
+            raise ValueError("image and mask_image must have the same length")
+        B = len(images)
+        if B > self.transformer.max_batch:
+            raise ValueError(f"batch {B} exceeds the transformer's max_batch {self.transformer.max_batch}")
+        height = images[0].height if height is None else int(height)
+        width = images[0].width if width is None else int(width)
         H, W = 16 * (height // 16), 16 * (width // 16)
-        img = image.convert("RGB")
-        if img.size != (W, H):
-            img = img.resize((W, H), Image.LANCZOS)
-        msk = mask_image.convert("L")
-        if msk.size != (W, H):
-            msk = msk.resize((W, H), Image.LANCZOS)
-        img_u8 = torch.from_numpy(np.asarray(img).copy())[None].pin_memory().to(dev, non_blocking=True)
-        mask_u8 = torch.from_numpy((np.asarray(msk) >= 128).astype(np.uint8))[None].pin_memory().to(dev, non_blocking=True)
-        B = 1
+        img_np, msk_np = [], []
+        for im, mk in zip(images, masks):       # every image of a batch is resized to the same (W, H), like diffusers
+            im = im.convert("RGB")
+            if im.size != (W, H):
+                im = im.resize((W, H), Image.LANCZOS)
+            mk = mk.convert("L")
+            if mk.size != (W, H):
+                mk = mk.resize((W, H), Image.LANCZOS)
+            img_np.append(np.asarray(im))
+            msk_np.append((np.asarray(mk) >= 128).astype(np.uint8))
+        img_u8 = torch.from_numpy(np.stack(img_np)).pin_memory().to(dev, non_blocking=True)
+        mask_u8 = torch.from_numpy(np.stack(msk_np)).pin_memory().to(dev, non_blocking=True)
         start = executed_range(num_inference_steps, strength)
         if start >= num_inference_steps:
             raise ValueError(f"After adjusting the num_inference_steps by strength parameter: {strength}, the number of "

@@ -44,7 +44,7 @@ def _vae_random(seed: int, ch: int):
 
 
 def load_model(device="cuda", want=("dev", "fill"), weights_dir: Optional[str] = None, size: str = "full",
-               max_side: int = 1024, seed: int = 3000) -> Pipelines:
+               max_side: int = 1024, seed: int = 3000, max_batch: int = 1) -> Pipelines:
     dev = torch.device(device)
     tiny = size == "tiny"
     print("正在加载模型...")
@@ -84,6 +84,6 @@ def load_model(device="cuda", want=("dev", "fill"), weights_dir: Optional[str] =
         if params is None:
             print(f"警告: 未找到{fname}, 使用随机初始化")
             params = F.init_params_device(cfg, seed=seed + (10 if kind == "dev" else 20), device=dev)
-        tr = F.FluxTransformer(cfg, params, max_batch=1, max_img_tokens=max_tokens, txt_tokens=s_txt, device=dev)
+        tr = F.FluxTransformer(cfg, params, max_batch=max_batch, max_img_tokens=max_tokens, txt_tokens=s_txt, device=dev)
         pipes[kind] = F.FluxPipeline(tr, vae) if kind == "dev" else F.FluxFillPipeline(tr, vae)
     return Pipelines(prior, pipes.get("dev"), pipes.get("fill"))

@@ -47,11 +47,16 @@ def generate(p_flux, cfg, p_vae, prompt_embeds, pooled, guidance, num_steps, hei
 
 def fill(p_flux, cfg, p_vae, image_u8: np.ndarray, mask_bool: np.ndarray, prompt_embeds, pooled, guidance, num_steps,
          strength, generator):
-    """image_u8 [H,W,3], mask_bool [H,W] (True = repaint), H and W multiples of 16. -> (latents, image uint8 [1,H,W,3])."""
-    H, W = mask_bool.shape
+    """image_u8 [H,W,3] or [B,H,W,3], mask_bool [H,W] or [B,H,W] (True = repaint), H and W multiples of 16.
+    -> (latents, image uint8 [B,H,W,3]). A batch shares one generator: each draw covers the whole batch."""
+    if image_u8.ndim == 3:
+        image_u8, mask_bool = image_u8[None], mask_bool[None]
+    B, H, W = mask_bool.shape
     h, w = H // 8, W // 8
-    img = OV.preprocess_image(torch.from_numpy(image_u8)[None])
-    mask = torch.from_numpy(mask_bool.astype(np.float32))[None]
+    img = OV.preprocess_image(torch.from_numpy(np.ascontiguousarray(image_u8)))
+    mask = torch.from_numpy(mask_bool.astype(np.float32))
+    if prompt_embeds.shape[0] != B:
+        prompt_embeds, pooled = prompt_embeds.expand(B, -1, -1), pooled.expand(B, -1)
     start = executed_start(num_steps, strength)
 
     def vae_sample(x):
@@ -60,7 +65,7 @@ def fill(p_flux, cfg, p_vae, image_u8: np.ndarray, mask_bool: np.ndarray, prompt
         return ((mean + torch.exp(0.5 * logvar.clamp(-30.0, 20.0)) * noise) - OV.SHIFT_FACTOR) * OV.SCALE_FACTOR
 
     image_latents = OF.pack_latents(vae_sample(img))
-    noise = OF.pack_latents(torch.randn((1, 16, h, w), generator=generator, dtype=torch.bfloat16)).float()
+    noise = OF.pack_latents(torch.randn((B, 16, h, w), generator=generator, dtype=torch.bfloat16)).float()
     s0 = float(OF.flow_match_sigmas(num_steps, noise.shape[1])[start])
     latents = s0 * noise + (1.0 - s0) * image_latents
     masked = OF.pack_latents(vae_sample(img * (1.0 - mask[:, None])))

@@ -94,3 +94,33 @@ def test_generate_and_fill_match_oracle(lib):
     assert diff.mean() < 3.0, diff.mean()
     with pytest.raises(ValueError):
         fill(prompt_embeds=ctx, pooled_prompt_embeds=pooled, image=image, mask_image=mask, num_inference_steps=3, strength=0.1)
+
+
+def test_fill_batch_of_compositions_matches_oracle(lib):
+    """C4's per-GPU slice runs its compositions as ONE batch: lists of images / masks, per-composition prompt tensors,
+    one generator whose draws cover the whole batch (diffusers semantics)."""
+    from domain_rag_b200 import flux as F
+    from domain_rag_b200.hostlogic import generate_outpaint_mask
+    from domain_rag_b200.vae import FluxVAE
+    p_vae = bf(OV.init_params(seed=5000, ch=64))
+    vae = FluxVAE(p_vae)
+    g = torch.Generator().manual_seed(6)
+    ctx, pooled = torch.randn(2, 24, 64, generator=g).bfloat16(), torch.randn(2, 32, generator=g).bfloat16()
+    H, W, T = 64, 96, 3
+    ocfg, cfg = OF.FluxConfig(in_channels=384, **FLUX_SMALL), F.FluxConfig(in_channels=384, **FLUX_SMALL)
+    p = bf(OF.init_params(ocfg, seed=3002))
+    fill = F.FluxFillPipeline(F.FluxTransformer(cfg, p, max_batch=2, max_img_tokens=(H // 16) * (W // 16), txt_tokens=24), vae)
+    images = [synth_image(3, H, W), synth_image(4, H, W)]
+    masks = [generate_outpaint_mask(images[0], [(30, 20, 25, 30)])[0], generate_outpaint_mask(images[1], [(10, 8, 40, 40)])[0]]
+    res = fill(prompt_embeds=ctx, pooled_prompt_embeds=pooled, image=images, mask_image=masks, height=H, width=W,
+               guidance_scale=30.0, num_inference_steps=T, generator=torch.Generator("cpu").manual_seed(9), strength=1.0)
+    assert res.steps_run == T and len(res.images) == 2 and res.latents.shape[0] == 2
+    img_r = np.stack([np.asarray(im) for im in images])
+    mask_r = np.stack([np.asarray(m) >= 128 for m in masks])
+    want_lat, want_img = OP.fill(p, ocfg, p_vae, img_r, mask_r, ctx, pooled, 30.0, T, 1.0, torch.Generator("cpu").manual_seed(9))
+    assert rel_l2(res.latents.cpu(), want_lat) < 4e-2, rel_l2(res.latents.cpu(), want_lat)
+    for i in range(2):
+        diff = np.abs(np.asarray(res.images[i]).astype(np.int32) - want_img[i].numpy().astype(np.int32))
+        assert diff.mean() < 3.0, diff.mean()
+    with pytest.raises(ValueError):
+        fill(prompt_embeds=ctx, pooled_prompt_embeds=pooled, image=images * 2, mask_image=masks * 2, num_inference_steps=T)
