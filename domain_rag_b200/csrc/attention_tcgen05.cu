@@ -75,6 +75,30 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
+// Packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): one issue slot for two row elements. The softmax warps are
+// issue-bound (two of them share every SM sub-partition while the tensor core waits for P), so halving the FMA /
+// ADD instruction count shortens the S -> P latency directly.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 splat2(float x) { return make_float2(x, x); }
+// ex2_poly on a pair.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+    x.x = fmaxf(x.x, -125.f);
+    x.y = fmaxf(x.y, -125.f);
+    const float2 t = fadd2(x, splat2(12582912.f));
+    const float2 r = fadd2(t, splat2(-12582912.f));            // round(x)
+    const float2 f = ffma2(r, splat2(-1.f), x);                 // x - round(x) in [-0.5, 0.5]
+    float2 p = ffma2(splat2(0.05500871315598488f), f, splat2(0.24221068620681763f));
+    p = ffma2(p, f, splat2(0.6932829022407532f));
+    p = ffma2(p, f, splat2(1.0f));
+    p.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
+    p.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
+    return p;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float2 p) {
+    __nv_bfloat162 pk = __floats2bfloat162_rn(p.x, p.y);
+    return *reinterpret_cast<uint32_t*>(&pk);
+}
 // Register re-balancing between warpgroups (all four warps of a warpgroup execute it).
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {
@@ -113,7 +137,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     uint64_t* s_full = bars + 9;    // [2] per query tile
     uint64_t* p_full = bars + 11;   // [2]
     uint64_t* pv_done = bars + 13;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    uint64_t* p_half = bars + 15;   // [2] keys [0,64) of P_x written (p_full: the whole tile)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 2 * AT_TILE;
@@ -133,6 +158,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             mbar_init(&v_empty[i], 1);
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], 4);
+            mbar_init(&p_half[i], 4);
             mbar_init(&pv_done[i], 1);
         }
         fence_mbar_init();
@@ -207,14 +233,17 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             }
             __syncwarp();
         };
-        auto issue_pv = [&](int x, int st, int j) {   // O_x += P_x V   (P_x: packed bf16 in S_x columns [0,64))
+        // O_x += P_x V, keys [half*64, half*64+64) of the tile   (P_x: packed bf16 in S_x columns [0,64))
+        auto issue_pv = [&](int x, int st, int j, int half, bool last) {
             const uint64_t vd = v_desc0 + ((st * TILE_BYTES) >> 4);
             if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < AT_TILE / 16; ++ks)      // 16 kv rows per k-step = 2048 B inside each half
+                for (int kk = 0; kk < AT_TILE / 32; ++kk) {    // 16 kv rows per k-step = 2048 B inside each half
+                    const int ks = half * (AT_TILE / 32) + kk;
                     tc_mma_f16_ts(tmem_base + 256 + x * 128, tmem_base + x * 128 + ks * 8, vd + ((ks * 2048) >> 4), idesc_pv,
                                   (j | ks) != 0);
-                tc_commit(&pv_done[x]);
+                }
+                if (last) tc_commit(&pv_done[x]);
             }
             __syncwarp();
         };
@@ -229,19 +258,25 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             const int st = j & 1, par = (j >> 1) & 1;
             const int nst = (j + 1) & 1, npar = ((j + 1) >> 1) & 1;
             const bool more = (j + 1) < n_tiles;
-            mbar_wait(&p_full[0], j & 1);
             mbar_wait(&v_full[st], par);
+            mbar_wait(&p_half[0], j & 1);
             tc_fence_after();
-            issue_pv(0, st, j);
+            issue_pv(0, st, j, 0, false);
+            mbar_wait(&p_full[0], j & 1);
+            tc_fence_after();
+            issue_pv(0, st, j, 1, true);
             if (more) {
                 mbar_wait(&k_full[nst], npar);
                 tc_fence_after();
                 issue_qk(0, nst);
             }
             if (has_b) {
+                mbar_wait(&p_half[1], j & 1);
+                tc_fence_after();
+                issue_pv(1, st, j, 0, false);
                 mbar_wait(&p_full[1], j & 1);
                 tc_fence_after();
-                issue_pv(1, st, j);
+                issue_pv(1, st, j, 1, true);
                 if (more) issue_qk(1, nst);
             }
             if (elect_one()) {
@@ -276,13 +311,20 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 for (int i = 0; i < AT_TILE; ++i)
                     if (i >= kv_valid) v[i] = 0xff800000u;   // -inf: exp2 -> 0, never the maximum
             }
+            // four independent chains (the FMNMX3 latency chain was as long as the exponential pass)
             float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
             float m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+            float m2 = fmaxf(__uint_as_float(v[4]), __uint_as_float(v[5]));
+            float m3 = fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7]));
 #pragma unroll
-            for (int i = 4; i < AT_TILE; i += 4) {
+            for (int i = 8; i < AT_TILE; i += 8) {
                 m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
                 m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                m2 = fmax3(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+                m3 = fmax3(m3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
             }
+            m0 = fmaxf(m0, m2);
+            m1 = fmaxf(m1, m3);
             const float m_new = fmaxf(m, fmaxf(m0, m1) * a.scale_log2);
             if (__any_sync(0xffffffffu, m_new > m + AT_RESCALE_THRESHOLD)) {
                 const float alpha = ex2_approx(m - m_new);   // 0 on the first tile (m = -inf)
@@ -302,27 +344,45 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 l *= alpha;
                 m = m_new;
             }
-            const float neg_m = -m;
-            float sum0 = 0.f, sum1 = 0.f;
-            // P as packed bf16 written IN PLACE over the first 64 columns of S. One exponential in four runs
-            // as a Cody-Waite + cubic polynomial on the FMA pipe, the rest on the MUFU pipe (exp2 is the
-            // co-bottleneck of the tensor core at head dim 128).
+            const float2 sc2 = splat2(a.scale_log2), nm2 = splat2(-m);
+            float2 sum_a = splat2(0.f), sum_b = splat2(0.f);
+            // P as packed bf16 written IN PLACE over the first 64 columns of S. Packed fp32x2 arithmetic throughout; of
+            // every four pairs three take their exponentials from the MUFU pipe and one from a Cody-Waite + cubic
+            // polynomial on the FMA pipe (exp2 is the co-bottleneck of the tensor core at head dim 128). The first half
+            // of the row is published on its own barrier so that the P V product of keys [0,64) starts while the second
+            // half is still being exponentiated.
 #pragma unroll
             for (int c = 0; c < AT_TILE; c += 32) {
                 uint32_t packed[16];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float x0 = fmaf(__uint_as_float(v[c + i]), a.scale_log2, neg_m);
-                    const float x1 = fmaf(__uint_as_float(v[c + i + 1]), a.scale_log2, neg_m);
-                    const float p0 = ex2_approx(x0);
-                    const float p1 = ((i & 2) == 2) ? ex2_poly(x1) : ex2_approx(x1);
-                    sum0 += p0;
-                    sum1 += p1;
-                    __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
-                    packed[i >> 1] = *reinterpret_cast<uint32_t*>(&pk);
+                for (int i = 0; i < 32; i += 8) {
+                    const float2 xa = ffma2(make_float2(__uint_as_float(v[c + i]), __uint_as_float(v[c + i + 1])), sc2, nm2);
+                    const float2 xb = ffma2(make_float2(__uint_as_float(v[c + i + 2]), __uint_as_float(v[c + i + 3])), sc2, nm2);
+                    const float2 xc = ffma2(make_float2(__uint_as_float(v[c + i + 4]), __uint_as_float(v[c + i + 5])), sc2, nm2);
+                    const float2 xd = ffma2(make_float2(__uint_as_float(v[c + i + 6]), __uint_as_float(v[c + i + 7])), sc2, nm2);
+                    const float2 pa = make_float2(ex2_approx(xa.x), ex2_approx(xa.y));
+                    const float2 pb = make_float2(ex2_approx(xb.x), ex2_approx(xb.y));
+                    const float2 pc = make_float2(ex2_approx(xc.x), ex2_approx(xc.y));
+                    const float2 pd = ex2_poly2(xd);
+                    sum_a = fadd2(sum_a, pa);
+                    sum_b = fadd2(sum_b, pb);
+                    sum_a = fadd2(sum_a, pc);
+                    sum_b = fadd2(sum_b, pd);
+                    packed[(i >> 1) + 0] = pack_bf16x2(pa);
+                    packed[(i >> 1) + 1] = pack_bf16x2(pb);
+                    packed[(i >> 1) + 2] = pack_bf16x2(pc);
+                    packed[(i >> 1) + 3] = pack_bf16x2(pd);
                 }
                 tmem_st_32x16(t_s + (c >> 1), packed);
+                if (c == 32) {                       // keys [0,64) of this tile are in TMEM
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p_half[x]);
+                }
             }
+            const float2 sum2 = fadd2(sum_a, sum_b);
+            const float sum0 = sum2.x, sum1 = sum2.y;
             l += sum0 + sum1;
             tmem_st_wait();
             tc_fence_before();

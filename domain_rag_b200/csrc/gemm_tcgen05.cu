@@ -42,12 +42,27 @@ struct GemmCfg {
 struct GemmShape {
     int M, N, K;
     int num_m, num_n, num_k;
+    int group_m;                                // tile raster: groups of group_m row tiles, see tile_coords
     // Implicit-GEMM convolution over an NHWC activation (conv = 0: plain row-major A). The A tile of 128 output
     // pixels is one 4-D TMA box (64 channels x tw x th pixels) at a tap-dependent offset; image borders are the
     // TMA out-of-bounds zero fill. K runs over taps x channel blocks (weights [C_out][tap][C_in]).
     int conv, cblocks, ksize, stride, pad;      // cblocks = C_in / 64
     int Wo, Ho, tw, th, tiles_x, tiles_y;       // output size, pixel tile, tiles per image row / per image column
 };
+
+// Tile raster. Tiles are visited in groups of `group_m` row tiles: inside a group the row tile runs fastest, then the
+// column tile, so the CTAs working at the same time cover group_m x (#CTAs / group_m) tiles, the group's A rows
+// (group_m x tile rows x K, sized by the host to ~32 MB) stay in L2 while every column tile of W streams past them
+// once. With the plain row-fastest order every column tile re-read ALL of A, which outgrows the 126 MB L2 as soon as
+// M x K x 2 B does (batched Flux steps, the K = 15360 projection): DRAM traffic of N/256 x |A| instead of |A|.
+__device__ __forceinline__ void tile_coords(const GemmShape& sh, int t, int& m_blk, int& n_blk) {
+    const int per_group = sh.group_m * sh.num_n;
+    const int g = t / per_group, r = t - g * per_group;
+    const int m0 = g * sh.group_m;
+    const int gm = min(sh.group_m, sh.num_m - m0);
+    n_blk = r / gm;
+    m_blk = m0 + (r - n_blk * gm);
+}
 
 // First output row (linear pixel index) and number of valid rows of 128-row A tile `mt`.
 __device__ __forceinline__ void tile_rows(const GemmShape& sh, int mt, int& base, int& count, int& b, int& y0, int& x0) {
@@ -323,7 +338,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // ------------------------------------------------------------------ TMA producer
         int stage = 0, phase = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const int m_blk = t % sh.num_m, n_blk = t / sh.num_m;
+            int m_blk, n_blk;
+            tile_coords(sh, t, m_blk, n_blk);
             int base, count, ib, iy, ix;
             tile_rows(sh, m_blk, base, count, ib, iy, ix);
             for (int kb = 0; kb < sh.num_k; ++kb) {
@@ -375,7 +391,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int quarter = warp & 3;              // TMEM lane quarter this warp may access
         int acc = 0, acc_phase = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const int m_blk = t % sh.num_m, n_blk = t / sh.num_m;
+            int m_blk, n_blk;
+            tile_coords(sh, t, m_blk, n_blk);
             int base, count, ib, iy, ix;
             tile_rows(sh, m_blk, base, count, ib, iy, ix);
             const int r_in = quarter * 32 + lane;
@@ -462,7 +479,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         // ------------------------------------------------------------------ TMA producer (both CTAs; warp-uniform, see above)
         int stage = 0, phase = 0;
         for (int t = pair; t < num_tiles; t += num_pairs) {
-            const int m_blk = t % sh.num_m, n_blk = t / sh.num_m;
+            int m_blk, n_blk;
+            tile_coords(sh, t, m_blk, n_blk);
             const int a_row = m_blk * (2 * G_BM) + rank * G_BM;
             const int b_row = n_blk * BN + rank * (BN / 2);
             int base, count, ib, iy, ix;
@@ -522,7 +540,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         const int quarter = warp & 3;
         int acc = 0, acc_phase = 0;
         for (int t = pair; t < num_tiles; t += num_pairs) {
-            const int m_blk = t % sh.num_m, n_blk = t / sh.num_m;
+            int m_blk, n_blk;
+            tile_coords(sh, t, m_blk, n_blk);
             int base, count, ib, iy, ix;
             tile_rows(sh, m_blk * 2 + rank, base, count, ib, iy, ix);
             const int r_in = quarter * 32 + lane;
@@ -648,6 +667,7 @@ static int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 
 
 int g_gemm_force_1cta = 0;   // drag_debug_set key 3: 1 = always use the single-CTA kernel (A/B comparisons)
+int g_gemm_group_m = 0;      // drag_debug_set key 4: > 0 = force the raster group size (1 << 20 = plain row-fastest order)
 
 // Shared launch logic: builds the operand tensor maps (A from a row-major matrix unless a ready map is given) and
 // picks the CTA-pair kernel whenever there is more than one 128-row tile of work and N tiles evenly.
@@ -661,6 +681,12 @@ static int dispatch_gemm(const __nv_bfloat16* A, const CUtensorMap* tmA_ready, i
     if (tmA_ready) tmA = *tmA_ready;
     else if ((rc = make_tmap_bf16_2d(&tmA, A, M, K, lda, G_BM))) return rc;
     const int slot = prof_begin(PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
+    // A rows kept L2-resident per raster group: ~32 MB (tile rows x K x 2 B each), at most 16 row tiles
+    const long long tile_bytes = static_cast<long long>(pair_ok ? 2 * G_BM : G_BM) * K * 2;
+    int gm = static_cast<int>((32ll << 20) / (tile_bytes > 0 ? tile_bytes : 1));
+    gm = gm < 1 ? 1 : (gm > 16 ? 16 : gm);
+    if (g_gemm_group_m > 0) gm = g_gemm_group_m;
+    sh.group_m = gm;
     if (pair_ok) {
         sh.num_m = ceil_div(m_tiles, 2);
         sh.num_n = N / bn;
