@@ -34,12 +34,20 @@ constexpr int AT_TILE = 128;
 constexpr int AT_HALF_BYTES = AT_TILE * 64 * 2;        // 16 KB: 128 rows x 64 bf16
 constexpr float AT_RESCALE_THRESHOLD = 8.0f;           // log2 domain
 
-template <int HD>
+// PP (ping-pong) = two query tiles per CTA, one CTA per SM: the long-sequence Flux shape. !PP = one query tile per
+// CTA, 256 threads, 256 TMEM columns and <= 32 K registers, so TWO CTAs share an SM: short sequences (CLIP ViT, 50-257
+// tokens = 1-3 key tiles) are a latency chain per CTA (prologue, first TMA, 3 x [QK -> softmax -> PV], epilogue), and
+// a second resident CTA overlaps all of it, including launch and drain.
+template <int HD, bool PP>
 struct AttnCfg {
     static constexpr int NH = HD / 64;
+    static constexpr int QT = PP ? 2 : 1;                          // query tiles per CTA
+    static constexpr int THREADS = PP ? AT_THREADS : 256;
+    static constexpr int TMEM_COLS = PP ? 512 : 256;
+    static constexpr int O_COL = PP ? 256 : 128;                   // first accumulator column
     static constexpr int TILE_BYTES = NH * AT_HALF_BYTES;          // one Q / K / V tile
     static constexpr int Q_OFF = 0;                                // Q_A, Q_B
-    static constexpr int K_OFF = 2 * TILE_BYTES;                   // 2 stages
+    static constexpr int K_OFF = QT * TILE_BYTES;                  // 2 stages
     static constexpr int V_OFF = K_OFF + 2 * TILE_BYTES;           // 2 stages
     static constexpr int BAR_OFF = V_OFF + 2 * TILE_BYTES;
     static constexpr int SMEM = BAR_OFF + 256 + 1024;
@@ -119,11 +127,11 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v
         : "memory");
 }
 
-template <int HD>
-__global__ void __launch_bounds__(AT_THREADS, 1)
+template <int HD, bool PP>
+__global__ void __launch_bounds__(PP ? AT_THREADS : 256, PP ? 1 : 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, AttnArgs a) {
-    using Cfg = AttnCfg<HD>;
+    using Cfg = AttnCfg<HD, PP>;
     constexpr int TILE_BYTES = Cfg::TILE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -141,10 +149,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * 2 * AT_TILE;
+    const int q0 = blockIdx.x * Cfg::QT * AT_TILE;
     const int bh = blockIdx.y;
     const int n_tiles = (a.S + AT_TILE - 1) / AT_TILE;
-    const bool has_b = (q0 + AT_TILE) < a.S;           // second query tile holds at least one row
+    const bool has_b = PP && (q0 + AT_TILE) < a.S;     // second query tile holds at least one row
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmQ);
@@ -164,7 +172,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -174,7 +182,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
     // register re-balancing: the data-movement warpgroup gives registers to the two softmax warpgroups
     if (warp < 4) {
-    setmaxnreg_dec<96>();
+    setmaxnreg_dec<PP ? 96 : 56>();
 
     // Both loops run on all 32 lanes with warp-uniform control flow; only the TMA / MMA / commit instructions are
     // predicated on one elected lane, so shared-memory addresses and UMMA descriptors stay in uniform registers. A
@@ -240,7 +248,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll
                 for (int kk = 0; kk < AT_TILE / 32; ++kk) {    // 16 kv rows per k-step = 2048 B inside each half
                     const int ks = half * (AT_TILE / 32) + kk;
-                    tc_mma_f16_ts(tmem_base + 256 + x * 128, tmem_base + x * 128 + ks * 8, vd + ((ks * 2048) >> 4), idesc_pv,
+                    tc_mma_f16_ts(tmem_base + Cfg::O_COL + x * 128, tmem_base + x * 128 + ks * 8, vd + ((ks * 2048) >> 4), idesc_pv,
                                   (j | ks) != 0);
                 }
                 if (last) tc_commit(&pv_done[x]);
@@ -295,7 +303,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const int r = quarter * 32 + lane;                 // query row inside the tile
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         const uint32_t t_s = t_lane + x * 128;             // S / P
-        const uint32_t t_o = t_lane + 256 + x * 128;       // O
+        const uint32_t t_o = t_lane + Cfg::O_COL + x * 128;  // O
         float m = -INFINITY, l = 0.f;
         for (int j = 0; j < n_tiles; ++j) {
             mbar_wait(&s_full[x], j & 1);
@@ -424,14 +432,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
-template <int HD>
+template <int HD, bool PP>
 static int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int B, int H, int S,
                             AttnArgs a, cudaStream_t st) {
-    using Cfg = AttnCfg<HD>;
+    using Cfg = AttnCfg<HD, PP>;
     CUtensorMap tq, tk, tv;
     const uint64_t bh = static_cast<uint64_t>(B) * H;
     int rc = make_tmap_bf16_3d(&tq, q, HD, S, bh, HD, static_cast<uint64_t>(S) * HD, 64, AT_TILE);
@@ -442,14 +450,17 @@ static int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, cons
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        DRAG_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        DRAG_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<HD, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM));
+        if (!PP)   // two CTAs per SM need 2 x SMEM of shared memory: ask for the largest carve-out
+            DRAG_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<HD, PP>,
+                                           cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
     a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
-    dim3 grid((S + 2 * AT_TILE - 1) / (2 * AT_TILE), static_cast<unsigned>(bh));
+    dim3 grid((S + Cfg::QT * AT_TILE - 1) / (Cfg::QT * AT_TILE), static_cast<unsigned>(bh));
     const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * H * static_cast<double>(S) * S * HD, st);
-    attention_tcgen05_kernel<HD><<<grid, AT_THREADS, Cfg::SMEM, st>>>(tq, tk, tv, a);
+    attention_tcgen05_kernel<HD, PP><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tq, tk, tv, a);
     prof_end(slot, st);
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
@@ -457,6 +468,7 @@ static int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, cons
 
 // Debug knobs kept for ABI stability (drag_debug_set keys 1/2); unused by the current kernel.
 uint32_t g_attn_v_lbo = 0, g_attn_v_sbo = 1024;
+int g_attn_force_pp = 0;      // drag_debug_set key 5: 1 = always the two-tile ping-pong kernel (A/B comparisons)
 
 int attention_bf16(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int B, int H, int S,
                    int head_dim, int split, __nv_bfloat16* out0, int ld0, __nv_bfloat16* out1, int ld1,
@@ -471,8 +483,10 @@ int attention_bf16(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bf
     a.S = S;
     a.H = H;
     a.scale_log2 = 0.f;
-    if (head_dim == 128) return launch_attention<128>(q, k, v, B, H, S, a, st);
-    return launch_attention<64>(q, k, v, B, H, S, a, st);
+    if (head_dim == 128) return launch_attention<128, true>(q, k, v, B, H, S, a, st);
+    // head dim 64 = the CLIP ViT towers: short sequences -> two single-tile CTAs per SM; long ones keep the ping-pong
+    if (S <= 4 * AT_TILE && !g_attn_force_pp) return launch_attention<64, false>(q, k, v, B, H, S, a, st);
+    return launch_attention<64, true>(q, k, v, B, H, S, a, st);
 }
 
 }  // namespace drag

@@ -30,6 +30,7 @@ int device_sm_count() {
 extern uint32_t g_attn_v_lbo, g_attn_v_sbo;
 extern int g_gemm_force_1cta;
 extern int g_gemm_group_m;
+extern int g_attn_force_pp;
 int prof_enable(int on);
 int prof_collect(double* ms, double* work, int* count, int n_classes);
 
@@ -427,6 +428,7 @@ int drag_debug_set(int key, int value) {
     else if (key == 2) g_attn_v_sbo = static_cast<uint32_t>(value);
     else if (key == 3) g_gemm_force_1cta = value;
     else if (key == 4) g_gemm_group_m = value;
+    else if (key == 5) g_attn_force_pp = value;
     else return fail(DRAG_ERR_INVALID, "drag_debug_set: unknown key");
     return DRAG_OK;
 }

@@ -41,6 +41,25 @@ def test_attention_matches_sdpa(ops, B, H, S, split):
         assert (got.float() - ref[:, split:]).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("force_pp", [0, 1])
+@pytest.mark.parametrize("B,H,S", [(3, 4, 50), (2, 16, 257), (1, 12, 197), (2, 2, 128), (1, 3, 512), (1, 2, 700)])
+def test_attention_head_dim_64_both_variants(ops, B, H, S, force_pp):
+    """CLIP ViT shapes: short sequences run the single-tile kernel (two CTAs per SM), S > 512 or drag_debug_set(5, 1)
+    the two-tile ping-pong kernel; both must agree with fp32 SDPA."""
+    q, k, v = rnd((B, H, S, 64), 21), rnd((B, H, S, 64), 22), rnd((B, H, S, 64), 23)
+    ops.debug_set(5, force_pp)
+    try:
+        _, o = ops.attention(q, k, v, 0)
+        torch.cuda.synchronize()
+    finally:
+        ops.debug_set(5, 0)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    ref = ref.permute(0, 2, 1, 3).reshape(B, S, H * 64)
+    got = o.view(B, S, -1)
+    assert rel_l2(got, ref) < 1e-2
+    assert (got.float() - ref).abs().max().item() < 2e-2
+
+
 def test_attention_large_logits(ops):
     """Running-max growth across tiles exercises the lazy O rescale."""
     B, H, S = 1, 2, 700
