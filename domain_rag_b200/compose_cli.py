@@ -112,7 +112,7 @@ def find_backgrounds(sample_dir: str) -> List[str]:
 def process_sample_hires(dataset_name, sample_id, pipes, process_id, category_name=None, sample_dir=None, shot_number=1,
                          datasets_dir=DATASETS_DIR, result_dir=RESULT_DIR, outpaint_base="./outpaint_hires",
                          upscale_override: Optional[Dict[str, int]] = None, seed_fn: Optional[Callable[[], int]] = None,
-                         num_inference_steps: int = 50) -> dict:
+                         num_inference_steps: int = 50, compose_batch: int = 1) -> dict:
     """One sample end to end; returns the reference's log record (status completed / error)."""
     from PIL import Image
     import torch
@@ -177,6 +177,10 @@ def process_sample_hires(dataset_name, sample_id, pipes, process_id, category_na
         proc_boxes = [[int(c * factor) for c in b] for b in boxes] if factor is not None else boxes
         mask_image, _ = H.generate_outpaint_mask(processed, proc_boxes)
 
+        # Every background of a sample is composed onto the SAME processed image and mask, so they run as batches of up
+        # to `compose_batch` through one FluxFillPipeline call, each composition with its own seed / CPU generator
+        # exactly as in the reference's one-at-a-time loop (outpainting...:1185-1300).
+        jobs = []
         for bg_idx, bg_path in enumerate(bg_images):
             bg_name = os.path.basename(bg_path)
             suffix = f"_{bg_name.split('rank')[1].split('.')[0]}" if "rank" in bg_name else f"_{bg_idx + 1}"
@@ -190,40 +194,60 @@ def process_sample_hires(dataset_name, sample_id, pipes, process_id, category_na
             bg_saved = os.path.join(out_dir, f"{prefix}_bg{suffix}_original.png")
             shutil.copy(bg_path, bg_saved)
             seed = seed_fn() if seed_fn else random.randint(0, 2 ** 32 - 1)
-            generator = torch.Generator("cpu").manual_seed(seed)
-            prior = pipes.prior_redux([bg_image], prompt=prm.redux_prompt, prompt_2="",
-                                      prompt_embeds_scale=[prm.image_prompt_scale], pooled_prompt_embeds_scale=[1.0])
-            result = pipes.pipe_fill(image=processed, mask_image=mask_image, height=processed.height, width=processed.width,
-                                     guidance_scale=prm.guidance_scale, num_inference_steps=num_inference_steps,
-                                     prompt_embeds=prior.prompt_embeds, pooled_prompt_embeds=prior.pooled_prompt_embeds,
-                                     generator=generator, strength=prm.strength).images[0]
-            hires_path = os.path.join(out_dir, f"{prefix}_hires_result{suffix}.png")
-            result.save(hires_path)
-            final = result
-            if was_up:
-                final = H.downscale_image(result, up)
-            elif was_down:
-                final = H.upscale_image(result, 1.0 / down)
-            final_path = os.path.join(out_dir, f"{prefix}_final_result{suffix}.png")
-            final.save(final_path)
-            params = {"categories": categories, "image_scale": 1.0, "prompt_scale": 1.0,
-                      "image_prompt_scale": prm.image_prompt_scale, "guidance_scale": prm.guidance_scale,
-                      "num_inference_steps": num_inference_steps, "strength": prm.strength, "redux_prompt": prm.redux_prompt,
-                      "seed": seed, "process_id": process_id, "shot_number": shot_number, "bg_index": bg_idx,
-                      "bg_filename": bg_name, "original_bg_path": bg_path, "copied_bg_path": bg_saved,
-                      "original_resolution": {"width": original.width, "height": original.height},
-                      "processed_resolution": {"width": processed.width, "height": processed.height},
-                      "min_dimension_used": min_dim, "up_scale_factor": up, "down_scale_factor": down,
-                      "was_upscaled": was_up, "was_downscaled": was_down, "bbox_coords_list": boxes,
-                      "processed_bbox_coords_list": proc_boxes, "image_id": image_id if image_id else "unknown",
-                      "num_bbox": len(boxes)}
-            params_path = os.path.join(out_dir, f"{prefix}_params{suffix}.json")
-            with open(params_path, "w") as f:
-                json.dump(params, f, indent=2)
-            log["outpainted_images"].append({"original_bg_path": bg_path, "copied_bg_path": bg_saved,
-                                             "hires_result_path": hires_path, "final_result_path": final_path,
-                                             "mask_path": mask_path, "params_path": params_path, "bbox_coords_list": boxes,
-                                             "processed_bbox_coords_list": proc_boxes, "params": params})
+            jobs.append(dict(bg_idx=bg_idx, bg_path=bg_path, bg_name=bg_name, suffix=suffix, mask_path=mask_path,
+                             bg_image=bg_image, bg_saved=bg_saved, seed=seed))
+        step = max(1, int(compose_batch))
+        for c0 in range(0, len(jobs), step):
+            chunk = jobs[c0:c0 + step]
+            priors = [pipes.prior_redux([j["bg_image"]], prompt=prm.redux_prompt, prompt_2="",
+                                        prompt_embeds_scale=[prm.image_prompt_scale], pooled_prompt_embeds_scale=[1.0])
+                      for j in chunk]
+            gens = [torch.Generator("cpu").manual_seed(j["seed"]) for j in chunk]
+            if len(chunk) == 1:
+                results = pipes.pipe_fill(image=processed, mask_image=mask_image, height=processed.height,
+                                          width=processed.width, guidance_scale=prm.guidance_scale,
+                                          num_inference_steps=num_inference_steps, prompt_embeds=priors[0].prompt_embeds,
+                                          pooled_prompt_embeds=priors[0].pooled_prompt_embeds, generator=gens[0],
+                                          strength=prm.strength).images
+            else:
+                results = pipes.pipe_fill(image=[processed] * len(chunk), mask_image=[mask_image] * len(chunk),
+                                          height=processed.height, width=processed.width,
+                                          guidance_scale=prm.guidance_scale, num_inference_steps=num_inference_steps,
+                                          prompt_embeds=torch.cat([p_.prompt_embeds for p_ in priors]),
+                                          pooled_prompt_embeds=torch.cat([p_.pooled_prompt_embeds for p_ in priors]),
+                                          generator=gens, strength=prm.strength).images
+            for j, result in zip(chunk, results):
+                bg_idx, bg_path, bg_name, suffix = j["bg_idx"], j["bg_path"], j["bg_name"], j["suffix"]
+                mask_path, bg_saved, seed = j["mask_path"], j["bg_saved"], j["seed"]
+                hires_path = os.path.join(out_dir, f"{prefix}_hires_result{suffix}.png")
+                result.save(hires_path)
+                final = result
+                if was_up:
+                    final = H.downscale_image(result, up)
+                elif was_down:
+                    final = H.upscale_image(result, 1.0 / down)
+                final_path = os.path.join(out_dir, f"{prefix}_final_result{suffix}.png")
+                final.save(final_path)
+                params = {"categories": categories, "image_scale": 1.0, "prompt_scale": 1.0,
+                          "image_prompt_scale": prm.image_prompt_scale, "guidance_scale": prm.guidance_scale,
+                          "num_inference_steps": num_inference_steps, "strength": prm.strength,
+                          "redux_prompt": prm.redux_prompt, "seed": seed, "process_id": process_id,
+                          "shot_number": shot_number, "bg_index": bg_idx, "bg_filename": bg_name,
+                          "original_bg_path": bg_path, "copied_bg_path": bg_saved,
+                          "original_resolution": {"width": original.width, "height": original.height},
+                          "processed_resolution": {"width": processed.width, "height": processed.height},
+                          "min_dimension_used": min_dim, "up_scale_factor": up, "down_scale_factor": down,
+                          "was_upscaled": was_up, "was_downscaled": was_down, "bbox_coords_list": boxes,
+                          "processed_bbox_coords_list": proc_boxes, "image_id": image_id if image_id else "unknown",
+                          "num_bbox": len(boxes)}
+                params_path = os.path.join(out_dir, f"{prefix}_params{suffix}.json")
+                with open(params_path, "w") as f:
+                    json.dump(params, f, indent=2)
+                log["outpainted_images"].append({"original_bg_path": bg_path, "copied_bg_path": bg_saved,
+                                                 "hires_result_path": hires_path, "final_result_path": final_path,
+                                                 "mask_path": mask_path, "params_path": params_path,
+                                                 "bbox_coords_list": boxes, "processed_bbox_coords_list": proc_boxes,
+                                                 "params": params})
         log["original_saved_path"] = orig_path
         log["status"] = "completed"
     except Exception as e:
@@ -363,6 +387,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--model_size", type=str, default="full", choices=["full", "tiny"])
     p.add_argument("--num_inference_steps", type=int, default=50)
     p.add_argument("--seed", type=int, default=None, help="fixed seed instead of a random one per composition")
+    p.add_argument("--compose_batch", type=int, default=4,
+                   help="backgrounds of one sample composed per FluxFillPipeline call (same image and mask; 1 = the "
+                        "reference's one-at-a-time loop; seeds stay per composition either way)")
     return p
 
 
@@ -387,9 +414,11 @@ def main(argv=None) -> int:
     if (args.resume or args.failed_only) and args.log_file and os.path.exists(args.log_file):
         done, failed = parse_resume_log(args.log_file)
     n_gpus = args.num_gpus or (torch.cuda.device_count() if args.multi_gpu else 1)
-    load_kwargs = dict(weights_dir=args.weights_dir, size=args.model_size, max_side=H.MAX_DIMENSION)
+    load_kwargs = dict(weights_dir=args.weights_dir, size=args.model_size, max_side=H.MAX_DIMENSION,
+                       max_batch=max(1, args.compose_batch))
     seed_fn = (lambda: args.seed) if args.seed is not None else None
-    kwargs = dict(upscale_override=upscale_override, num_inference_steps=args.num_inference_steps, seed_fn=seed_fn)
+    kwargs = dict(upscale_override=upscale_override, num_inference_steps=args.num_inference_steps, seed_fn=seed_fn,
+                  compose_batch=max(1, args.compose_batch))
     pipes = None
     for ds in datasets:
         ids = [args.sample_id] if args.sample_id else get_all_sample_ids(ds, args.shot)

@@ -33,6 +33,10 @@ constexpr int AT_THREADS = 384;                        // 12 warps (warps 2,3 id
 constexpr int AT_TILE = 128;
 constexpr int AT_HALF_BYTES = AT_TILE * 64 * 2;        // 16 KB: 128 rows x 64 bf16
 constexpr float AT_RESCALE_THRESHOLD = 8.0f;           // log2 domain
+// Which of every 8 element pairs take exp2 from the FMA-pipe polynomial instead of MUFU.EX2 (bit i = pair i). MUFU
+// issues 4 lanes / clock / sub-partition: 128 exponentials per row tile would keep the XU pipe busy for as long as the
+// tensor core needs for the tile's two MMAs. 3 of 8 balances XU time (80 x 8 cycles) against issue slots (~600).
+constexpr uint32_t AT_POLY_MASK = 0xA4;                // pairs 2, 5, 7
 
 // PP (ping-pong) = two query tiles per CTA, one CTA per SM: the long-sequence Flux shape. !PP = one query tile per
 // CTA, 256 threads, 256 TMEM columns and <= 32 K registers, so TWO CTAs share an SM: short sequences (CLIP ViT, 50-257
@@ -355,7 +359,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             const float2 sc2 = splat2(a.scale_log2), nm2 = splat2(-m);
             float2 sum_a = splat2(0.f), sum_b = splat2(0.f);
             // P as packed bf16 written IN PLACE over the first 64 columns of S. Packed fp32x2 arithmetic throughout; of
-            // every four pairs three take their exponentials from the MUFU pipe and one from a Cody-Waite + cubic
+            // every eight pairs five take their exponentials from the MUFU pipe and three from a Cody-Waite + cubic
             // polynomial on the FMA pipe (exp2 is the co-bottleneck of the tensor core at head dim 128). The first half
             // of the row is published on its own barrier so that the P V product of keys [0,64) starts while the second
             // half is still being exponentiated.
@@ -363,23 +367,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             for (int c = 0; c < AT_TILE; c += 32) {
                 uint32_t packed[16];
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    const float2 xa = ffma2(make_float2(__uint_as_float(v[c + i]), __uint_as_float(v[c + i + 1])), sc2, nm2);
-                    const float2 xb = ffma2(make_float2(__uint_as_float(v[c + i + 2]), __uint_as_float(v[c + i + 3])), sc2, nm2);
-                    const float2 xc = ffma2(make_float2(__uint_as_float(v[c + i + 4]), __uint_as_float(v[c + i + 5])), sc2, nm2);
-                    const float2 xd = ffma2(make_float2(__uint_as_float(v[c + i + 6]), __uint_as_float(v[c + i + 7])), sc2, nm2);
-                    const float2 pa = make_float2(ex2_approx(xa.x), ex2_approx(xa.y));
-                    const float2 pb = make_float2(ex2_approx(xb.x), ex2_approx(xb.y));
-                    const float2 pc = make_float2(ex2_approx(xc.x), ex2_approx(xc.y));
-                    const float2 pd = ex2_poly2(xd);
-                    sum_a = fadd2(sum_a, pa);
-                    sum_b = fadd2(sum_b, pb);
-                    sum_a = fadd2(sum_a, pc);
-                    sum_b = fadd2(sum_b, pd);
-                    packed[(i >> 1) + 0] = pack_bf16x2(pa);
-                    packed[(i >> 1) + 1] = pack_bf16x2(pb);
-                    packed[(i >> 1) + 2] = pack_bf16x2(pc);
-                    packed[(i >> 1) + 3] = pack_bf16x2(pd);
+                for (int pr = 0; pr < 16; ++pr) {            // pairs of row elements
+                    const float2 x = ffma2(make_float2(__uint_as_float(v[c + 2 * pr]), __uint_as_float(v[c + 2 * pr + 1])),
+                                           sc2, nm2);
+                    const float2 e = ((AT_POLY_MASK >> (pr & 7)) & 1) ? ex2_poly2(x)
+                                                                      : make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                    if (pr & 1) sum_b = fadd2(sum_b, e);
+                    else sum_a = fadd2(sum_a, e);
+                    packed[pr] = pack_bf16x2(e);
                 }
                 tmem_st_32x16(t_s + (c >> 1), packed);
                 if (c == 32) {                       // keys [0,64) of this tile are in TMEM

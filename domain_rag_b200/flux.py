@@ -257,7 +257,12 @@ class FluxPipeline:
         """randn([B,16,H/8,W/8]) drawn with the CPU generator in bf16, then moved to the GPU (the reference
         passes torch.Generator("cpu").manual_seed(0), batch_generate_flux_kshot.py:472); H, W floored to /16."""
         h, w = 2 * (int(height) // 16), 2 * (int(width) // 16)
-        z = torch.randn((batch, 16, h, w), generator=generator, dtype=torch.bfloat16)
+        if isinstance(generator, (list, tuple)):          # one generator per batch element: each draws its own [1,16,h,w]
+            if len(generator) != batch:
+                raise ValueError(f"got {len(generator)} generators for a batch of {batch}")
+            z = torch.cat([torch.randn((1, 16, h, w), generator=g, dtype=torch.bfloat16) for g in generator])
+        else:
+            z = torch.randn((batch, 16, h, w), generator=generator, dtype=torch.bfloat16)
         return pack_latents(z).contiguous().pin_memory().to(device, non_blocking=True), h, w
 
     def _denoise(self, latents, h, w, prompt_embeds, pooled_prompt_embeds, guidance_scale, num_inference_steps, start,
@@ -329,7 +334,9 @@ class FluxFillPipeline(FluxPipeline):
     pipe_fill(image=, mask_image=, height=, width=, guidance_scale=, num_inference_steps=50, prompt_embeds=,
     pooled_prompt_embeds=, generator=, strength=).images[0]. `image` / `mask_image` may also be equally long lists
     (one composition per entry, prompt tensors [B,...] or [1,...] broadcast; the C4 per-GPU slice runs its 4
-    compositions as one batch). The transformer is the Fill variant (in_channels 384 =
+    compositions as one batch). `generator` may be a list with one CPU generator per composition: every composition then
+    draws exactly what a batch-1 call with that generator draws, so a batch reproduces the reference's per-composition
+    seeds (outpainting...:1230-1231). The transformer is the Fill variant (in_channels 384 =
     64 latent + 64 masked-image latent + 256 mask channels). Host work: PIL resize to multiples of 16 (Lanczos, like
     VaeImageProcessor), mask binarisation at 0.5. Generator draws, in order: VAE sample of the image, the initial noise
     (bf16, CPU generator), VAE sample of the masked image."""

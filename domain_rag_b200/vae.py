@@ -238,7 +238,13 @@ class FluxVAE:
         if generator is None:
             z = mean
         else:
-            noise = torch.randn(mean.shape, generator=generator, device=generator.device, dtype=torch.bfloat16)
+            if isinstance(generator, (list, tuple)):      # one generator per batch element (diffusers randn_tensor)
+                if len(generator) != mean.shape[0]:
+                    raise ValueError("encode: need one generator per image")
+                noise = torch.cat([torch.randn(mean[i:i + 1].shape, generator=g, device=g.device, dtype=torch.bfloat16)
+                                   for i, g in enumerate(generator)])
+            else:
+                noise = torch.randn(mean.shape, generator=generator, device=generator.device, dtype=torch.bfloat16)
             z = mean + torch.exp(0.5 * logvar.clamp(-30.0, 20.0)) * noise.to(self.device).float()
         return ((z - SHIFT_FACTOR) * SCALE_FACTOR).to(torch.bfloat16)
 

@@ -59,13 +59,20 @@ def fill(p_flux, cfg, p_vae, image_u8: np.ndarray, mask_bool: np.ndarray, prompt
         prompt_embeds, pooled = prompt_embeds.expand(B, -1, -1), pooled.expand(B, -1)
     start = executed_start(num_steps, strength)
 
+    gens = list(generator) if isinstance(generator, (list, tuple)) else None   # one generator per composition
+
+    def draw(shape):
+        if gens is None:
+            return torch.randn(shape, generator=generator, dtype=torch.bfloat16)
+        return torch.cat([torch.randn((1,) + tuple(shape[1:]), generator=g, dtype=torch.bfloat16) for g in gens])
+
     def vae_sample(x):
         mean, logvar = OV.encoder(x, p_vae).chunk(2, dim=1)
-        noise = torch.randn(mean.shape, generator=generator, dtype=torch.bfloat16).float()
+        noise = draw(mean.shape).float()
         return ((mean + torch.exp(0.5 * logvar.clamp(-30.0, 20.0)) * noise) - OV.SHIFT_FACTOR) * OV.SCALE_FACTOR
 
     image_latents = OF.pack_latents(vae_sample(img))
-    noise = OF.pack_latents(torch.randn((B, 16, h, w), generator=generator, dtype=torch.bfloat16)).float()
+    noise = OF.pack_latents(draw((B, 16, h, w))).float()
     s0 = float(OF.flow_match_sigmas(num_steps, noise.shape[1])[start])
     latents = s0 * noise + (1.0 - s0) * image_latents
     masked = OF.pack_latents(vae_sample(img * (1.0 - mask[:, None])))

@@ -23,7 +23,8 @@ class StubPrior:
 
     def __call__(self, image, prompt=None, prompt_2=None, prompt_embeds_scale=1.0, pooled_prompt_embeds_scale=1.0):
         self.calls.append(dict(n=len(image), prompt=prompt, prompt_2=prompt_2, se=prompt_embeds_scale, sp=pooled_prompt_embeds_scale))
-        return _Out(prompt_embeds="PE", pooled_prompt_embeds="PP")
+        import torch
+        return _Out(prompt_embeds=torch.full((1, 3, 4), float(len(self.calls))), pooled_prompt_embeds=torch.zeros(1, 4))
 
 
 class StubPipe:
@@ -33,7 +34,8 @@ class StubPipe:
     def __call__(self, **kw):
         self.calls.append(kw)
         w, h = kw.get("width", 64), kw.get("height", 64)
-        return _Out(images=[Image.new("RGB", (16 * (w // 16), 16 * (h // 16)), (10, 200, 30))])
+        n = len(kw["image"]) if isinstance(kw.get("image"), list) else 1
+        return _Out(images=[Image.new("RGB", (16 * (w // 16), 16 * (h // 16)), (10, 200, 30)) for _ in range(n)])
 
 
 class Pipes:
@@ -75,7 +77,7 @@ def test_generate_cli_file_surface(tmp_path):
     assert c == dict(n=2, prompt=["", ""], prompt_2=["", ""], se=[0.8, 1.0], sp=[1.0, 1.0])
     k = pipes.pipe.calls[0]
     assert (k["guidance_scale"], k["num_inference_steps"], k["height"], k["width"]) == (2.5, 50, 1024, 1024)
-    assert k["generator"].initial_seed() == 0 and k["prompt_embeds"] == "PE"
+    assert k["generator"].initial_seed() == 0 and tuple(k["prompt_embeds"].shape) == (1, 3, 4)
     assert "生成图像尺寸: 96x64" in open(os.path.join(base, "airport_1", "params.txt")).read()
 
 
@@ -136,6 +138,21 @@ def test_compose_cli_file_surface(tmp_path):
     logf = tmp_path / "run.log"
     logf.write_text("样本 a 处理完成，耗时 1.00 秒\n样本 b 处理失败，耗时 2.00 秒\n处理样本 c 时出错: boom\n样本 c 处理完成，耗时 3 秒\n")
     assert CC.parse_resume_log(str(logf)) == ({"a", "c"}, {"b"})
+    # the same sample with its backgrounds composed as ONE batch: same files, one pipeline call, per-composition seeds
+    pipes_b = Pipes()
+    seeds = iter([11, 22])
+    log_b = CC.process_sample_hires("DIOR", "airport_1", pipes_b, "PIDB", shot_number=5, datasets_dir=str(tmp_path / "datasets"),
+                                    result_dir=str(tmp_path / "result"), outpaint_base=str(tmp_path / "outpaint_hires"),
+                                    seed_fn=lambda: next(seeds), compose_batch=4)
+    assert log_b["status"] == "completed", log_b["error"]
+    out_b = tmp_path / "outpaint_hires" / "process_PIDB" / "DIOR" / "5_shot" / "airport_1"
+    assert want <= set(os.listdir(out_b))
+    assert len(pipes_b.pipe_fill.calls) == 1 and len(pipes_b.prior_redux.calls) == 2
+    kb = pipes_b.pipe_fill.calls[0]
+    assert len(kb["image"]) == 2 and len(kb["mask_image"]) == 2 and kb["prompt_embeds"].shape == (2, 3, 4)
+    assert [g.initial_seed() for g in kb["generator"]] == [11, 22]
+    assert [json.load(open(out_b / f"{p}_params_{r}.json"))["seed"] for r in (1, 2)] == [11, 22]
+    assert CC.build_parser().parse_args([]).compose_batch == 4
     # a sample with neither annotation nor backgrounds is an error record, not an exception
     bad = CC.process_sample_hires("DIOR", "nope", pipes, "PID", shot_number=5, datasets_dir=str(tmp_path / "datasets"),
                                   result_dir=str(tmp_path / "result"), outpaint_base=str(tmp_path / "outpaint_hires"))

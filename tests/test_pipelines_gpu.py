@@ -124,3 +124,34 @@ def test_fill_batch_of_compositions_matches_oracle(lib):
         assert diff.mean() < 3.0, diff.mean()
     with pytest.raises(ValueError):
         fill(prompt_embeds=ctx, pooled_prompt_embeds=pooled, image=images * 2, mask_image=masks * 2, num_inference_steps=T)
+
+
+def test_fill_batch_with_generator_list_equals_sequential_calls(lib):
+    """One generator per composition: a batch draws exactly what the reference's one-at-a-time calls draw, and every
+    kernel on the path is row / image independent, so the batched latents equal the sequential ones."""
+    from domain_rag_b200 import flux as F
+    from domain_rag_b200.hostlogic import generate_outpaint_mask
+    from domain_rag_b200.vae import FluxVAE
+    vae = FluxVAE(bf(OV.init_params(seed=5000, ch=64)))
+    g = torch.Generator().manual_seed(8)
+    ctx, pooled = torch.randn(3, 24, 64, generator=g).bfloat16(), torch.randn(3, 32, generator=g).bfloat16()
+    H, W, T = 64, 96, 3
+    cfg = F.FluxConfig(in_channels=384, **FLUX_SMALL)
+    p = bf(OF.init_params(OF.FluxConfig(in_channels=384, **FLUX_SMALL), seed=3002))
+    fill = F.FluxFillPipeline(F.FluxTransformer(cfg, p, max_batch=3, max_img_tokens=(H // 16) * (W // 16), txt_tokens=24), vae)
+    image = synth_image(5, H, W)
+    mask, _ = generate_outpaint_mask(image, [(20, 16, 40, 30)])
+    seeds = [101, 202, 303]
+    kw = dict(height=H, width=W, guidance_scale=30.0, num_inference_steps=T, strength=0.7)
+    batch = fill(prompt_embeds=ctx, pooled_prompt_embeds=pooled, image=[image] * 3, mask_image=[mask] * 3,
+                 generator=[torch.Generator("cpu").manual_seed(s) for s in seeds], **kw)
+    assert batch.latents.shape[0] == 3 and len(batch.images) == 3 and batch.steps_run == 2
+    for i, s in enumerate(seeds):
+        one = fill(prompt_embeds=ctx[i:i + 1], pooled_prompt_embeds=pooled[i:i + 1], image=image, mask_image=mask,
+                   generator=torch.Generator("cpu").manual_seed(s), **kw)
+        assert rel_l2(batch.latents[i:i + 1], one.latents) < 2e-3, (i, rel_l2(batch.latents[i:i + 1], one.latents))
+        d = np.abs(np.asarray(batch.images[i]).astype(np.int32) - np.asarray(one.images[0]).astype(np.int32))
+        assert d.max() <= 2, d.max()
+    with pytest.raises(ValueError):
+        fill(prompt_embeds=ctx, pooled_prompt_embeds=pooled, image=[image] * 3, mask_image=[mask] * 3,
+             generator=[torch.Generator("cpu").manual_seed(1)], **kw)
