@@ -330,6 +330,8 @@ def run_full(args):
     (g_ms, g_fl, g_n), (a_ms, a_fl, a_n) = prof_collect()
     lib.drag_prof_enable(0)
 
+    cublas_here = B.same_box_cublas_tflops() if rank == 0 else 0.0     # hot chip, same power state as the timed region
+
     n_e2e = max(1, min(args.steps, 2))
     compose_e2e(0)
     B.barrier(world)
@@ -373,6 +375,8 @@ def run_full(args):
                      "kernel": "gemm_bf16_tcgen05_2cta_kernel (all GEMM/conv launches of one composition)",
                      "kernel_ms": round(g_ms / max(g_n, 1), 4), "launches": g_n,
                      "share_of_step": round(g_ms / (ms_per_step), 4), "peak_source": peaks["source"] + " (sustained)",
+                     "same_box_cublas_sustained_tflops": round(cublas_here, 1),
+                     "frac_of_same_box_cublas": round(g_fl / (g_ms * 1e-3) / 1e12 / max(cublas_here, 1e-9), 4),
                      "attention": {"achieved": round(a_fl / (a_ms * 1e-3) / 1e12, 1), "kernel_ms": round(a_ms / max(a_n, 1), 4),
                                    "launches": a_n, "share_of_step": round(a_ms / ms_per_step, 4)}},
         "cpu_baseline": cpu_baseline(),

@@ -106,3 +106,25 @@ def max_over_ranks(x: float, world: int) -> float:
     return float(t.item())
 
 
+
+
+def same_box_cublas_tflops(seconds: float = 2.0, n: int = 8192) -> float:
+    """Context for the roofline on a power-capped part: torch.matmul (cuBLAS) bf16 n^3 run back to back for `seconds` on
+    THIS box right after the timed region (the B200s of the pool differ by ~10 % in the clock the 1 kW cap lets them hold).
+    Library code used as a yardstick only - never on the measured path."""
+    import torch
+    a = torch.randn(n, n, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(n, n, device="cuda", dtype=torch.bfloat16)
+    c = torch.empty(n, n, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    fl = 2.0 * n ** 3
+    iters = max(10, int(seconds * 1.3e15 / fl))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        torch.matmul(a, b, out=c)
+    e1.record()
+    torch.cuda.synchronize()
+    return fl * iters / (e0.elapsed_time(e1) * 1e-3) / 1e12

@@ -35,8 +35,8 @@ constexpr int AT_HALF_BYTES = AT_TILE * 64 * 2;        // 16 KB: 128 rows x 64 b
 constexpr float AT_RESCALE_THRESHOLD = 8.0f;           // log2 domain
 // Which of every 8 element pairs take exp2 from the FMA-pipe polynomial instead of MUFU.EX2 (bit i = pair i). MUFU
 // issues 4 lanes / clock / sub-partition: 128 exponentials per row tile would keep the XU pipe busy for as long as the
-// tensor core needs for the tile's two MMAs. 3 of 8 balances XU time (80 x 8 cycles) against issue slots (~600).
-constexpr uint32_t AT_POLY_MASK = 0xA4;                // pairs 2, 5, 7
+// tensor core needs for the tile's two MMAs. Measured (S = 5337, batch 4): 2 of 8 -> 1324 TFLOP/s, 3 of 8 -> 1289.
+constexpr uint32_t AT_POLY_MASK = 0x88;                // pairs 3, 7
 
 // PP (ping-pong) = two query tiles per CTA, one CTA per SM: the long-sequence Flux shape. !PP = one query tile per
 // CTA, 256 threads, 256 TMEM columns and <= 32 K registers, so TWO CTAs share an SM: short sequences (CLIP ViT, 50-257
@@ -359,7 +359,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             const float2 sc2 = splat2(a.scale_log2), nm2 = splat2(-m);
             float2 sum_a = splat2(0.f), sum_b = splat2(0.f);
             // P as packed bf16 written IN PLACE over the first 64 columns of S. Packed fp32x2 arithmetic throughout; of
-            // every eight pairs five take their exponentials from the MUFU pipe and three from a Cody-Waite + cubic
+            // every eight pairs six take their exponentials from the MUFU pipe and two from a Cody-Waite + cubic
             // polynomial on the FMA pipe (exp2 is the co-bottleneck of the tensor core at head dim 128). The first half
             // of the row is published on its own barrier so that the P V product of keys [0,64) starts while the second
             // half is still being exponentiated.

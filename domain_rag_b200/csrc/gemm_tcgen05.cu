@@ -25,9 +25,22 @@ namespace drag {
 
 constexpr int G_BM = 128;
 constexpr int G_BK = 64;
-constexpr int G_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
+// 12 warps = 3 warpgroups: {TMA, MMA, 2 idle} + 8 epilogue warps. The idle warps buy a legal `setmaxnreg`: a 16 K-register
+// sub-partition hosts 3 warps, i.e. 168 registers each at launch; the data-movement warpgroup drops to 40 and the two
+// epilogue warpgroups take 232, enough to keep a whole 128-wide head row plus prefetched RoPE / bias operands in
+// registers (the 10-warp layout was capped at 168 for every warp and spilled as soon as the epilogue prefetched).
+constexpr int G_THREADS = 384;
 constexpr int G_EPI_WARPS = 8;
-constexpr int G_EPI_WARP0 = 2;
+constexpr int G_EPI_WARP0 = 4;
+constexpr int G_REGS_MOVE = 72, G_REGS_EPI = 216;
+template <int N>
+__device__ __forceinline__ void g_setmaxnreg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void g_setmaxnreg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 
 template <int BN>
 struct GemmCfg {
@@ -43,6 +56,8 @@ struct GemmShape {
     int M, N, K;
     int num_m, num_n, num_k;
     int group_m;                                // tile raster: groups of group_m row tiles, see tile_coords
+    int group_n;                                // > 0: groups of group_n COLUMN tiles instead (W resident, A streams)
+    int l2_hints;                               // column groups only: A loads evict-first, W loads evict-last
     // Implicit-GEMM convolution over an NHWC activation (conv = 0: plain row-major A). The A tile of 128 output
     // pixels is one 4-D TMA box (64 channels x tw x th pixels) at a tap-dependent offset; image borders are the
     // TMA out-of-bounds zero fill. K runs over taps x channel blocks (weights [C_out][tap][C_in]).
@@ -56,6 +71,18 @@ struct GemmShape {
 // once. With the plain row-fastest order every column tile re-read ALL of A, which outgrows the 126 MB L2 as soon as
 // M x K x 2 B does (batched Flux steps, the K = 15360 projection): DRAM traffic of N/256 x |A| instead of |A|.
 __device__ __forceinline__ void tile_coords(const GemmShape& sh, int t, int& m_blk, int& n_blk) {
+    if (sh.group_n > 0) {
+        // column groups: the group's W rows (group_n x BN x K) stay in L2, the column tile runs fastest so that the CTAs
+        // working at the same time share each A row tile, and A streams through once per group. Cheaper than row groups
+        // when N is small and K large (the N = 3072 projections: |W| + |A| x groups_n  <  |A| + |W| x groups_m).
+        const int per_group = sh.group_n * sh.num_m;
+        const int g = t / per_group, r = t - g * per_group;
+        const int n0 = g * sh.group_n;
+        const int gn = min(sh.group_n, sh.num_n - n0);
+        m_blk = r / gn;
+        n_blk = n0 + (r - m_blk * gn);
+        return;
+    }
     const int per_group = sh.group_m * sh.num_n;
     const int g = t / per_group, r = t - g * per_group;
     const int m0 = g * sh.group_m;
@@ -220,43 +247,68 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, const GemmShap
         const int which = col_h / (epi.heads * hd);          // 0 q, 1 k, 2 v
         const int head = (col_h - which * epi.heads * hd) / hd;
         __nv_bfloat16* dst_base = (which == 0 ? epi.q_out : (which == 1 ? epi.k_out : epi.v_out));
+        // RoPE tables of this row: 2 x 64 fp32 = 32 x 16 B that no other row shares. Loading them where they are used made
+        // the epilogue a chain of 16 dependent L2 round trips per tile (tensor pipe 84 % busy on the QKV GEMM vs 98 % on
+        // the others), so they are software-pipelined PF iterations ahead, the first PF before the TMEM read.
+        constexpr int PF = 6;
+        const bool rope = which < 2;
+        const float* cs = epi.rope_cos + static_cast<size_t>(pos) * (hd / 2);
+        const float* sn = epi.rope_sin + static_cast<size_t>(pos) * (hd / 2);
+        float4 cbuf[PF], sbuf[PF];
+        if (rope && row_ok) {
+#pragma unroll
+            for (int p = 0; p < PF; ++p) {
+                cbuf[p] = __ldg(reinterpret_cast<const float4*>(cs) + p);
+                sbuf[p] = __ldg(reinterpret_cast<const float4*>(sn) + p);
+            }
+        }
         uint32_t r[hd];
 #pragma unroll
         for (int c = 0; c < hd; c += 32) tmem_ld_32x32_ptr(t_addr + h0 + c, &r[c]);
         tmem_ld_wait();
         float* x = reinterpret_cast<float*>(r);      // in place: x[j] = bf16(acc + bias)
         float ss = 0.f;
+        uint4 bnext = epi.bias ? __ldg(reinterpret_cast<const uint4*>(epi.bias + col_h)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int j = 0; j < hd; j += 8) {
-            float bb[8];
-            if (epi.bias) load_bf16x8(epi.bias + col_h + j, bb);
+            const uint4 bcur = bnext;
+            if (epi.bias && j + 8 < hd) bnext = __ldg(reinterpret_cast<const uint4*>(epi.bias + col_h + j + 8));
+            const __nv_bfloat162* bp = reinterpret_cast<const __nv_bfloat162*>(&bcur);
 #pragma unroll
-            for (int tt = 0; tt < 8; ++tt) {
-                const float xv = bf16_round(__uint_as_float(r[j + tt]) + (epi.bias ? bb[tt] : 0.f));
-                r[j + tt] = __float_as_uint(xv);
-                ss = fmaf(xv, xv, ss);
+            for (int tt = 0; tt < 4; ++tt) {
+                const float2 bf = __bfloat1622float2(bp[tt]);
+                const float x0 = bf16_round(__uint_as_float(r[j + 2 * tt]) + bf.x);
+                const float x1 = bf16_round(__uint_as_float(r[j + 2 * tt + 1]) + bf.y);
+                r[j + 2 * tt] = __float_as_uint(x0);
+                r[j + 2 * tt + 1] = __float_as_uint(x1);
+                ss = fmaf(x0, x0, ss);
+                ss = fmaf(x1, x1, ss);
             }
         }
         if (!row_ok) return;
         __nv_bfloat16* dst = dst_base + ((static_cast<size_t>(b) * epi.heads + head) * epi.s_total + pos) * hd;
-        if (which < 2) {
+        if (rope) {
             const float inv_rms = rsqrtf(ss * (1.f / hd) + epi.rms_eps);
             const __nv_bfloat16* nw = (which == 0) ? epi.q_norm_w : epi.k_norm_w;
-            const float* cs = epi.rope_cos + static_cast<size_t>(pos) * (hd / 2);
-            const float* sn = epi.rope_sin + static_cast<size_t>(pos) * (hd / 2);
+            uint4 wnext = __ldg(reinterpret_cast<const uint4*>(nw));
 #pragma unroll
             for (int j = 0; j < hd; j += 8) {
-                float w[8];
-                load_bf16x8(nw + j, w);
-                const float4 c4 = *reinterpret_cast<const float4*>(cs + j / 2);
-                const float4 s4 = *reinterpret_cast<const float4*>(sn + j / 2);
+                const uint4 wcur = wnext;
+                if (j + 8 < hd) wnext = __ldg(reinterpret_cast<const uint4*>(nw + j + 8));
+                const __nv_bfloat162* wp = reinterpret_cast<const __nv_bfloat162*>(&wcur);
+                const float4 c4 = cbuf[(j / 8) % PF], s4 = sbuf[(j / 8) % PF];
+                if (j / 8 + PF < hd / 8) {
+                    cbuf[(j / 8) % PF] = __ldg(reinterpret_cast<const float4*>(cs) + j / 8 + PF);
+                    sbuf[(j / 8) % PF] = __ldg(reinterpret_cast<const float4*>(sn) + j / 8 + PF);
+                }
                 const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
                 const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
                 float o[8];
 #pragma unroll
                 for (int tt = 0; tt < 4; ++tt) {
-                    const float x0 = bf16_round(bf16_round(x[j + 2 * tt] * inv_rms) * w[2 * tt]);
-                    const float x1 = bf16_round(bf16_round(x[j + 2 * tt + 1] * inv_rms) * w[2 * tt + 1]);
+                    const float2 w2 = __bfloat1622float2(wp[tt]);
+                    const float x0 = bf16_round(bf16_round(x[j + 2 * tt] * inv_rms) * w2.x);
+                    const float x1 = bf16_round(bf16_round(x[j + 2 * tt + 1] * inv_rms) * w2.y);
                     o[2 * tt] = x0 * cc[tt] - x1 * sv[tt];
                     o[2 * tt + 1] = x1 * cc[tt] + x0 * sv[tt];
                 }
@@ -334,6 +386,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // asynchronous instruction itself is predicated on one elected lane: addresses, descriptors and coordinates then
     // live in uniform registers (UTMALDG / UTCHMMA take UR operands) instead of costing an R2UR each, which is what
     // bounds a single-lane issuer at ~70 % tensor occupancy.
+    if (warp < G_EPI_WARP0) {
+    g_setmaxnreg_dec<G_REGS_MOVE>();
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         int stage = 0, phase = 0;
@@ -386,7 +440,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-    } else if (warp >= G_EPI_WARP0) {
+    }
+    } else {
+        g_setmaxnreg_inc<G_REGS_EPI>();
         // ------------------------------------------------------------------ epilogue
         const int quarter = warp & 3;              // TMEM lane quarter this warp may access
         int acc = 0, acc_phase = 0;
@@ -475,6 +531,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    if (warp < G_EPI_WARP0) {
+    g_setmaxnreg_dec<G_REGS_MOVE>();
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs; warp-uniform, see above)
         int stage = 0, phase = 0;
@@ -498,9 +556,14 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
                 }
                 if (elect_one()) {
                     if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
-                    if (!sh.conv) tma_load_2d_2cta(a_dst, &tmA, c0, c1, full_leader);
-                    else tma_load_4d_2cta(a_dst, &tmA, c0, c1, c2, c3, full_leader);
-                    tma_load_2d_2cta(b_dst, &tmB, kb * G_BK, b_row, full_leader);
+                    if (sh.l2_hints && !sh.conv) {
+                        tma_load_2d_2cta_hint(a_dst, &tmA, c0, c1, full_leader, L2_EVICT_FIRST);
+                        tma_load_2d_2cta_hint(b_dst, &tmB, kb * G_BK, b_row, full_leader, L2_EVICT_LAST);
+                    } else {
+                        if (!sh.conv) tma_load_2d_2cta(a_dst, &tmA, c0, c1, full_leader);
+                        else tma_load_4d_2cta(a_dst, &tmA, c0, c1, c2, c3, full_leader);
+                        tma_load_2d_2cta(b_dst, &tmB, kb * G_BK, b_row, full_leader);
+                    }
                 }
                 __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -535,7 +598,9 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-    } else if (warp >= G_EPI_WARP0) {
+    }
+    } else {
+        g_setmaxnreg_inc<G_REGS_EPI>();
         // ------------------------------------------------------------------ epilogue (both CTAs, own rows)
         const int quarter = warp & 3;
         int acc = 0, acc_phase = 0;
@@ -667,6 +732,8 @@ static int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 
 
 int g_gemm_force_1cta = 0;   // drag_debug_set key 3: 1 = always use the single-CTA kernel (A/B comparisons)
+int g_gemm_l2_hints = 0;     // drag_debug_set key 7: 1 = L2 eviction hints on the column-group raster
+int g_gemm_group_n = 0;      // drag_debug_set key 6: > 0 = column-group raster with this many column tiles per group
 int g_gemm_group_m = 0;      // drag_debug_set key 4: > 0 = force the raster group size (1 << 20 = plain row-fastest order)
 
 // Shared launch logic: builds the operand tensor maps (A from a row-major matrix unless a ready map is given) and
@@ -694,6 +761,8 @@ static int dispatch_gemm(const __nv_bfloat16* A, const CUtensorMap* tmA_ready, i
         gm = ceil_div(num_m_tiles, ceil_div(num_m_tiles, gmax));
     }
     if (g_gemm_group_m > 0) gm = g_gemm_group_m;
+    sh.group_n = g_gemm_group_n > 0 ? g_gemm_group_n : 0;
+    sh.l2_hints = (sh.group_n > 0 && g_gemm_l2_hints) ? 1 : 0;
     sh.group_m = gm;
     if (pair_ok) {
         sh.num_m = ceil_div(m_tiles, 2);

@@ -18,6 +18,10 @@ import numpy as np
 from .index import IndexFlatIP
 
 _INDEX_CACHE: dict = {}
+# path -> 128-d style vector of corpus images already seen: the reference recomputes the statistics of all
+# 100 candidates for every query (:468-470) although popular corpus images recur across queries.
+_STYLE_CACHE: Dict[str, np.ndarray] = {}
+_STYLE_CACHE_MAX = 200_000
 
 
 def clean_image_path(path):
@@ -134,11 +138,18 @@ def rerank_by_style(query_feat, cand_feats, first_stage_results):
 
 
 def resnet_second_stage_rerank(query_image_path, first_stage_results, resnet_model, device):
-    """Stage B: re-rank the CLIP candidates by L2 distance of stem style statistics."""
+    """Stage B: re-rank the CLIP candidates by L2 distance of stem style statistics. One batched launch for the query and
+    the candidates not yet in the style cache."""
     query_image_path = clean_image_path(query_image_path)
-    paths = [query_image_path] + [clean_image_path(r["image_path"]) for r in first_stage_results]
-    feats = compute_resnet_features_batch(paths, resnet_model, device)
+    cand_paths = [clean_image_path(r["image_path"]) for r in first_stage_results]
+    if len(_STYLE_CACHE) > _STYLE_CACHE_MAX:
+        _STYLE_CACHE.clear()
+    todo = [query_image_path] + [p for p in dict.fromkeys(cand_paths) if p not in _STYLE_CACHE]
+    feats = compute_resnet_features_batch(todo, resnet_model, device)
     if feats[0] is None:
         print(f"警告：无法计算查询图像的ResNet特征: {query_image_path}")
         return first_stage_results
-    return rerank_by_style(feats[0], feats[1:], first_stage_results)
+    for p, f in zip(todo[1:], feats[1:]):
+        if f is not None:
+            _STYLE_CACHE[p] = f
+    return rerank_by_style(feats[0], [_STYLE_CACHE.get(p) for p in cand_paths], first_stage_results)
