@@ -32,6 +32,15 @@ def flops_per_forward(s_img: int, s_txt: int = S_TXT, d: int = D, blocks: int = 
     return gemm, attn
 
 
+def gemm_traffic_from_profile():
+    """dram read+write bytes per launch of the dominant GEMM shape (MLP-up of a batch-4 step) from the committed
+    ncu --set full capture; None when the file is absent."""
+    try:
+        return json.loads((REPO / "profiles" / "r01_gemm_traffic.json").read_text())
+    except Exception:
+        return None
+
+
 def prof_collect():
     from domain_rag_b200 import _lib
     ms, work, cnt = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_int * 2)()
@@ -371,7 +380,9 @@ def run_full(args):
         "gpu_launches_note": "tcgen05 GEMM/conv + attention launches only (counted live); ~25 % more row kernels on top",
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": round(g_fl / (g_ms * 1e-3) / 1e12, 1), "peak": peak,
-                     "unit": "TFLOP/s", "frac": round(g_fl / (g_ms * 1e-3) / 1e12 / peak, 4), "traffic": None,
+                     "unit": "TFLOP/s", "frac": round(g_fl / (g_ms * 1e-3) / 1e12 / peak, 4),
+                     "traffic": (gemm_traffic_from_profile() or {}).get("traffic_bytes_per_launch"),
+                     "traffic_note": (gemm_traffic_from_profile() or {}).get("note"),
                      "kernel": "gemm_bf16_tcgen05_2cta_kernel (all GEMM/conv launches of one composition)",
                      "kernel_ms": round(g_ms / max(g_n, 1), 4), "launches": g_n,
                      "share_of_step": round(g_ms / (ms_per_step), 4), "peak_source": peaks["source"] + " (sustained)",

@@ -57,7 +57,6 @@ struct GemmShape {
     int num_m, num_n, num_k;
     int group_m;                                // tile raster: groups of group_m row tiles, see tile_coords
     int group_n;                                // > 0: groups of group_n COLUMN tiles instead (W resident, A streams)
-    int l2_hints;                               // column groups only: A loads evict-first, W loads evict-last
     // Implicit-GEMM convolution over an NHWC activation (conv = 0: plain row-major A). The A tile of 128 output
     // pixels is one 4-D TMA box (64 channels x tw x th pixels) at a tap-dependent offset; image borders are the
     // TMA out-of-bounds zero fill. K runs over taps x channel blocks (weights [C_out][tap][C_in]).
@@ -556,14 +555,9 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
                 }
                 if (elect_one()) {
                     if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
-                    if (sh.l2_hints && !sh.conv) {
-                        tma_load_2d_2cta_hint(a_dst, &tmA, c0, c1, full_leader, L2_EVICT_FIRST);
-                        tma_load_2d_2cta_hint(b_dst, &tmB, kb * G_BK, b_row, full_leader, L2_EVICT_LAST);
-                    } else {
-                        if (!sh.conv) tma_load_2d_2cta(a_dst, &tmA, c0, c1, full_leader);
-                        else tma_load_4d_2cta(a_dst, &tmA, c0, c1, c2, c3, full_leader);
-                        tma_load_2d_2cta(b_dst, &tmB, kb * G_BK, b_row, full_leader);
-                    }
+                    if (!sh.conv) tma_load_2d_2cta(a_dst, &tmA, c0, c1, full_leader);
+                    else tma_load_4d_2cta(a_dst, &tmA, c0, c1, c2, c3, full_leader);
+                    tma_load_2d_2cta(b_dst, &tmB, kb * G_BK, b_row, full_leader);
                 }
                 __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -732,7 +726,6 @@ static int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 
 
 int g_gemm_force_1cta = 0;   // drag_debug_set key 3: 1 = always use the single-CTA kernel (A/B comparisons)
-int g_gemm_l2_hints = 0;     // drag_debug_set key 7: 1 = L2 eviction hints on the column-group raster
 int g_gemm_group_n = 0;      // drag_debug_set key 6: > 0 = column-group raster with this many column tiles per group
 int g_gemm_group_m = 0;      // drag_debug_set key 4: > 0 = force the raster group size (1 << 20 = plain row-fastest order)
 
@@ -748,22 +741,27 @@ static int dispatch_gemm(const __nv_bfloat16* A, const CUtensorMap* tmA_ready, i
     if (tmA_ready) tmA = *tmA_ready;
     else if ((rc = make_tmap_bf16_2d(&tmA, A, M, K, lda, G_BM))) return rc;
     const int slot = prof_begin(PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
-    // Raster groups (tile_coords): when all of A fits comfortably in L2 (<= 48 MB) the plain row-fastest order is best
-    // (W streams once, A stays resident: measured 1345 vs 1299 TFLOP/s at M = 5337, K = 3072). Otherwise groups of row
-    // tiles whose A rows take ~32 MB (at most 16 tiles), balanced so that no group is a small remainder
-    // (M = 21348: 1083 -> 1318 TFLOP/s at N = 12288, K = 3072; 1080 -> 1255 at K = 15360).
+    // Tile raster (tile_coords). While all of A fits comfortably in L2 (<= 48 MB) the plain row-fastest order is best: W
+    // streams once, A stays resident (1345 vs 1299 TFLOP/s at M = 5337, K = 3072). Beyond that, COLUMN groups: up to 24
+    // column tiles whose W rows take <= ~96 MB stay L2-resident (they are re-touched by every wave), the column tile
+    // runs fastest so concurrent CTAs share each A row tile, and A streams through once per group. Measured at M = 21348
+    // (profiles/r01_gemm_raster*): row-fastest 1083, row groups 1318 / 1255 / 1271, column groups 1355 / 1323 / 1312
+    // TFLOP/s at (N, K) = (12288, 3072) / (3072, 15360) / (3072, 12288). L2 eviction hints (A evict-first, W evict-last)
+    // made every shape slower (1163-1264) and are not used.
     const long long tile_bytes = static_cast<long long>(pair_ok ? 2 * G_BM : G_BM) * K * 2;
     const int num_m_tiles = pair_ok ? ceil_div(m_tiles, 2) : m_tiles;
-    int gm = num_m_tiles;
+    const int num_n_tiles = pair_ok ? N / bn : ceil_div(N, bn);
+    int gm = num_m_tiles, gn = 0;
     if (tile_bytes * num_m_tiles > (48ll << 20)) {
-        int gmax = static_cast<int>((32ll << 20) / (tile_bytes > 0 ? tile_bytes : 1));
-        gmax = gmax < 1 ? 1 : (gmax > 16 ? 16 : gmax);
-        gm = ceil_div(num_m_tiles, ceil_div(num_m_tiles, gmax));
+        const long long col_bytes = static_cast<long long>(bn) * K * 2;
+        int gmax = static_cast<int>((96ll << 20) / (col_bytes > 0 ? col_bytes : 1));
+        gmax = gmax < 1 ? 1 : (gmax > 24 ? 24 : gmax);
+        gn = ceil_div(num_n_tiles, ceil_div(num_n_tiles, gmax));
     }
-    if (g_gemm_group_m > 0) gm = g_gemm_group_m;
-    sh.group_n = g_gemm_group_n > 0 ? g_gemm_group_n : 0;
-    sh.l2_hints = (sh.group_n > 0 && g_gemm_l2_hints) ? 1 : 0;
+    if (g_gemm_group_m > 0) { gm = g_gemm_group_m; gn = 0; }
+    if (g_gemm_group_n > 0) gn = g_gemm_group_n;
     sh.group_m = gm;
+    sh.group_n = gn;
     if (pair_ok) {
         sh.num_m = ceil_div(m_tiles, 2);
         sh.num_n = N / bn;

@@ -258,19 +258,6 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* dst_smem, const CUtensorM
         : "memory");
 }
 
-// Same with an L2 eviction-priority hint (createpolicy encodings as CUTLASS's TMA::CacheHintSm90 uses them).
-constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
-constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
-constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
-__device__ __forceinline__ void tma_load_2d_2cta_hint(void* dst_smem, const CUtensorMap* map, int c0, int c1,
-                                                      uint32_t bar_cluster_addr, uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst_smem)),
-        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(policy)
-        : "memory");
-}
-
 __device__ __forceinline__ void tma_load_4d_2cta(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2,
                                                  int c3, uint32_t bar_cluster_addr) {
     asm volatile(
