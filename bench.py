@@ -86,11 +86,14 @@ def run_scan(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms = []
     barrier(world)
+    from domain_rag_b200 import _lib
+    _lib.launch_count(reset=True)
     e0.record()
     for _ in range(args.steps):
         step_device()
         scan_ms.append(None)
     e1.record()
+    n_launches = _lib.launch_count()
     barrier(world)
     total_ms = max_over_ranks(e0.elapsed_time(e1), world)
     # per-launch duration of the dominant kernel (event bracket inside the library, same stream)
@@ -136,7 +139,7 @@ def run_scan(args):
                        "grid": geo["grid"], "ring_stages": geo["stages"], "rows_per_stage": geo["rows_per_stage"]},
             "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": nq * d * 4,
                     "d2h_bytes_per_step": nq * k * 12},
-            "gpu_launches": args.steps * 2,
+            "gpu_launches": int(n_launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": round(alg / (kern_avg * 1e-3) / 1e9, 1),
                          "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -80,6 +80,7 @@ SIGNATURES = {
     "drag_prof_enable": (C.c_int, [C.c_int]),
     "drag_prof_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "drag_debug_set": (C.c_int, [C.c_int, C.c_int]),
+    "drag_launch_count": (C.c_int, [C.POINTER(C.c_int64), C.c_int]),
     "drag_stem_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_float, C.c_void_p, C.c_void_p]),
 }
@@ -128,6 +129,13 @@ def ptr(t) -> C.c_void_p:
 def current_stream_ptr(device=None) -> C.c_void_p:
     import torch
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def launch_count(reset: bool = False) -> int:
+    """Kernels launched by the library in this process since the last reset (drag_launch_count)."""
+    n = C.c_int64(0)
+    check(load().drag_launch_count(C.byref(n), int(reset)), "drag_launch_count")
+    return int(n.value)
 
 
 def device_count() -> int:

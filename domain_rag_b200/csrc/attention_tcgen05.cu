@@ -455,7 +455,7 @@ static int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, cons
     a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
     dim3 grid((S + Cfg::QT * AT_TILE - 1) / (Cfg::QT * AT_TILE), static_cast<unsigned>(bh));
     const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * H * static_cast<double>(S) * S * HD, st);
-    attention_tcgen05_kernel<HD, PP><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tq, tk, tv, a);
+    attention_tcgen05_kernel<HD, PP><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tq, tk, tv, a); count_launch();
     prof_end(slot, st);
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;

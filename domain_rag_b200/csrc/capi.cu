@@ -27,6 +27,7 @@ int device_sm_count() {
     return n;
 }
 
+long long g_launch_count = 0;
 extern uint32_t g_attn_v_lbo, g_attn_v_sbo;
 extern int g_gemm_force_1cta;
 extern int g_gemm_group_m;
@@ -422,6 +423,13 @@ int drag_image_preprocess_u8(const uint8_t* in, const uint8_t* mask, void* out, 
 int drag_axpby_bf16(const void* x, const void* y, float a, float b, void* out, int64_t n, void* stream) {
     return axpby_bf16(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(y), a, b,
                       static_cast<__nv_bfloat16*>(out), static_cast<size_t>(n), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int drag_launch_count(int64_t* count, int reset) {
+    if (!count) return fail(DRAG_ERR_INVALID, "drag_launch_count: null pointer");
+    *count = g_launch_count;
+    if (reset) g_launch_count = 0;
+    return DRAG_OK;
 }
 
 int drag_debug_set(int key, int value) {

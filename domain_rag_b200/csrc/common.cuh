@@ -31,4 +31,8 @@ static inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + 
 
 int device_sm_count();
 
+// Every kernel launch of the library bumps this counter (bench.py reports it as `gpu_launches`; drag_launch_count).
+extern long long g_launch_count;
+static inline void count_launch() { ++g_launch_count; }
+
 }  // namespace drag

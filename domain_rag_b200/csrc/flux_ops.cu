@@ -87,7 +87,7 @@ int layernorm_bf16(const __nv_bfloat16* x, int ldx, __nv_bfloat16* out, int ldo,
     DRAG_REQUIRE(x && out && M >= 1 && d >= 8 && d % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "layernorm: bad arguments");
     if (rows_per_batch <= 0) rows_per_batch = 1 << 30;
     layernorm_kernel<<<ceil_div(M, 8), 256, 0, st>>>(x, ldx, out, ldo, M, d, mul, mul_ld, add, add_ld, mul_add_one,
-                                                     rows_per_batch, eps);
+                                                     rows_per_batch, eps); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -106,7 +106,7 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t, __nv_bfloat16
 }
 int timestep_embed(const float* t_dev, __nv_bfloat16* out, int B, cudaStream_t st) {
     DRAG_REQUIRE(t_dev && out && B >= 1, "timestep_embed: bad arguments");
-    timestep_embed_kernel<<<ceil_div(B * 128, 128), 128, 0, st>>>(t_dev, out, B);
+    timestep_embed_kernel<<<ceil_div(B * 128, 128), 128, 0, st>>>(t_dev, out, B); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -126,7 +126,7 @@ __global__ void sum_silu_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, 
 int sum_silu(const __nv_bfloat16* a, const __nv_bfloat16* b, const __nv_bfloat16* c, __nv_bfloat16* out, int n,
              int apply_silu, cudaStream_t st) {
     DRAG_REQUIRE(a && out && n >= 1, "sum_silu: bad arguments");
-    sum_silu_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a, b, c, out, n, apply_silu);
+    sum_silu_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a, b, c, out, n, apply_silu); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -149,7 +149,7 @@ int euler_step(__nv_bfloat16* x, int ldx, const __nv_bfloat16* v, int ldv, int r
                cudaStream_t st) {
     DRAG_REQUIRE(x && v && rows >= 1 && cols % 8 == 0 && ldx % 8 == 0 && ldv % 8 == 0, "euler_step: bad arguments");
     const int64_t n = static_cast<int64_t>(rows) * (cols / 8);
-    euler_step_kernel<<<ceil_div(n, 256), 256, 0, st>>>(x, ldx, v, ldv, rows, cols, dsigma);
+    euler_step_kernel<<<ceil_div(n, 256), 256, 0, st>>>(x, ldx, v, ldv, rows, cols, dsigma); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -189,7 +189,7 @@ int redux_blend(const __nv_bfloat16* txt, const __nv_bfloat16* img, const __nv_b
     DRAG_REQUIRE(txt && img && pooled && s_embed && s_pool && out_embeds && out_pooled && B >= 1, "redux_blend: bad arguments");
     const int64_t n = static_cast<int64_t>(n_txt + n_img) * dim + pooled_dim;
     redux_blend_kernel<<<ceil_div(n, 256), 256, 0, st>>>(txt, img, pooled, s_embed, s_pool, out_embeds, out_pooled, B,
-                                                         n_txt, n_img, dim, pooled_dim);
+                                                         n_txt, n_img, dim, pooled_dim); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -208,7 +208,7 @@ __global__ void l2_normalize_kernel(const float* x, float* out, int rows, int d)
 }
 int l2_normalize(const float* x, float* out, int rows, int d, cudaStream_t st) {
     DRAG_REQUIRE(x && out && rows >= 1 && d >= 1, "l2_normalize: bad arguments");
-    l2_normalize_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(x, out, rows, d);
+    l2_normalize_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(x, out, rows, d); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -238,7 +238,7 @@ int vit_patchify(const float* img, __nv_bfloat16* out, int B, int R, int p, int 
     // stride == kernel, no padding: floor(R / p) patches per side, trailing pixels unused (SigLIP 384 / 14 = 27)
     const int g = R / p;
     const int64_t total = static_cast<int64_t>(B) * g * g * kpad;
-    vit_patchify_kernel<<<ceil_div(total, 256), 256, 0, st>>>(img, out, B, R, p, g, kpad);
+    vit_patchify_kernel<<<ceil_div(total, 256), 256, 0, st>>>(img, out, B, R, p, g, kpad); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -264,7 +264,7 @@ int vit_assemble(const __nv_bfloat16* patch_emb, const __nv_bfloat16* cls, const
                  int B, int n_patch, int w, cudaStream_t st) {
     DRAG_REQUIRE(patch_emb && cls && pos && x && B >= 1 && w % 8 == 0, "vit_assemble: bad arguments");
     const int64_t total = static_cast<int64_t>(B) * (n_patch + 1) * (w / 8);
-    vit_assemble_kernel<<<ceil_div(total, 256), 256, 0, st>>>(patch_emb, cls, pos, x, B, n_patch, w);
+    vit_assemble_kernel<<<ceil_div(total, 256), 256, 0, st>>>(patch_emb, cls, pos, x, B, n_patch, w); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }

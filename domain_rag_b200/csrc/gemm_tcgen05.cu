@@ -698,7 +698,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     if (sms <= 0) sms = 148;
     int tiles = sh.num_m * sh.num_n;
     int grid = tiles < sms ? tiles : sms;
-    gemm_bf16_tcgen05_kernel<BN><<<grid, G_THREADS, Cfg::SMEM, st>>>(tmA, tmB, sh, epi);
+    gemm_bf16_tcgen05_kernel<BN><<<grid, G_THREADS, Cfg::SMEM, st>>>(tmA, tmB, sh, epi); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -719,7 +719,7 @@ static int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     const int pairs_max = sms / 2;
     const int tiles = sh.num_m * sh.num_n;
     const int pairs = tiles < pairs_max ? tiles : pairs_max;
-    gemm_bf16_tcgen05_2cta_kernel<BN><<<2 * pairs, G_THREADS, Cfg::SMEM, st>>>(tmA, tmB, sh, epi);
+    gemm_bf16_tcgen05_2cta_kernel<BN><<<2 * pairs, G_THREADS, Cfg::SMEM, st>>>(tmA, tmB, sh, epi); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }

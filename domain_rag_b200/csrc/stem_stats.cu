@@ -146,7 +146,7 @@ int stem_stats_device(const float* img, int B, int H, int W, const float* w_fold
     if (B == 0) return DRAG_OK;
     DRAG_CUDA(cudaFuncSetAttribute(stem_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    ST_SMEM));
-    stem_stats_kernel<<<B, ST_THREADS, ST_SMEM, st>>>(img, w_fold, b_fold, eps, out);
+    stem_stats_kernel<<<B, ST_THREADS, ST_SMEM, st>>>(img, w_fold, b_fold, eps, out); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }

@@ -638,7 +638,7 @@ static cudaError_t launch_scan(const ScanArgs& a, int grid, size_t smem, cudaStr
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    ip_scan_topk_kernel<NV><<<grid, SCAN_THREADS, smem, st>>>(a);
+    ip_scan_topk_kernel<NV><<<grid, SCAN_THREADS, smem, st>>>(a); count_launch();
     return cudaGetLastError();
 }
 
@@ -728,7 +728,7 @@ int index_search_device(Index* ix, const float* q, int nq, int k, float* D, int6
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  static_cast<int>(plan.smem));
                         if (e == cudaSuccess) {
-                            ip_scan_topk_direct_kernel<<<grids[i], SCAN_CW * 32, plan.smem, st>>>(a);
+                            ip_scan_topk_direct_kernel<<<grids[i], SCAN_CW * 32, plan.smem, st>>>(a); count_launch();
                             e = cudaGetLastError();
                         }
                     } else {
@@ -760,7 +760,7 @@ int index_search_device(Index* ix, const float* q, int nq, int k, float* D, int6
     m.partial = ix->partial; m.lists = lists_total; m.k = k; m.kpad = next_pow2(k);
     m.seg_start = ix->seg_start; m.seg_base = ix->seg_base; m.nseg = nseg > 0 ? nseg : 1;
     m.D = D; m.I = I;
-    topk_merge_keys_kernel<<<nq, MERGE_THREADS, 0, st>>>(m);
+    topk_merge_keys_kernel<<<nq, MERGE_THREADS, 0, st>>>(m); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -795,7 +795,7 @@ int merge_pairs_device(const float* scores, const int64_t* ids, int nq, int list
     DRAG_CUDA(cudaFuncSetAttribute(topk_merge_pairs_kernel,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(smem)));
-    topk_merge_pairs_kernel<<<nq, 1024, smem, st>>>(scores, ids, lists, k_in, k_out, npad, D, I);
+    topk_merge_pairs_kernel<<<nq, 1024, smem, st>>>(scores, ids, lists, k_in, k_out, npad, D, I); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }

@@ -135,11 +135,11 @@ int groupnorm_nhwc(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int 
     DRAG_REQUIRE(workspace_floats >= need, "groupnorm: workspace too small");
     float* part = workspace;
     float* stats = workspace + static_cast<size_t>(B) * chunks * 2 * C;
-    gn_partial_kernel<<<dim3(chunks, B), GN_THREADS, GN_THREADS * 16 * sizeof(float), st>>>(x, part, HW, C, chunk_px);
-    gn_finalize_kernel<<<dim3(groups, B), 32, 0, st>>>(part, stats, chunks, C, groups, HW, eps);
+    gn_partial_kernel<<<dim3(chunks, B), GN_THREADS, GN_THREADS * 16 * sizeof(float), st>>>(x, part, HW, C, chunk_px); count_launch();
+    gn_finalize_kernel<<<dim3(groups, B), 32, 0, st>>>(part, stats, chunks, C, groups, HW, eps); count_launch();
     const size_t total_oct = static_cast<size_t>(B) * HW * (C / 8);
     gn_apply_kernel<<<static_cast<unsigned>((total_oct + 255) / 256), 256, 0, st>>>(x, y, stats, gamma, beta, HW, C, groups,
-                                                                                   silu, total_oct);
+                                                                                   silu, total_oct); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
 int upsample2x_nhwc(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int H, int W, int C, cudaStream_t st) {
     DRAG_REQUIRE(x && y && C % 8 == 0, "upsample2x: bad arguments");
     const size_t total_oct = static_cast<size_t>(B) * 4 * H * W * (C / 8);
-    upsample2x_kernel<<<static_cast<unsigned>((total_oct + 255) / 256), 256, 0, st>>>(x, y, H, W, C, total_oct);
+    upsample2x_kernel<<<static_cast<unsigned>((total_oct + 255) / 256), 256, 0, st>>>(x, y, H, W, C, total_oct); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 
 int softmax_rows(const float* s, size_t ld_s, __nv_bfloat16* p, size_t ld_p, int rows, int cols, cudaStream_t st) {
     DRAG_REQUIRE(s && p && rows >= 1 && cols >= 4 && cols % 4 == 0 && ld_s % 4 == 0 && ld_p % 4 == 0, "softmax_rows: bad arguments");
-    softmax_rows_kernel<<<rows, 256, 0, st>>>(s, ld_s, p, ld_p, cols);
+    softmax_rows_kernel<<<rows, 256, 0, st>>>(s, ld_s, p, ld_p, cols); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -253,6 +253,7 @@ int nchw_to_nhwc_pad(const void* in, int in_is_f32, __nv_bfloat16* out, int B, i
     else
         nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), out, C, H * W, C_pad,
                                                                  scale, shift, total);
+    count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -279,6 +280,7 @@ int nhwc_to_nchw_f32(const void* in, int in_is_f32, int ld, float* out, int B, i
     else
         nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), ld, out, C, H * W, scale,
                                                                  shift, total);
+    count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(256) image_postprocess_kernel(const float* __r
 
 int image_postprocess_u8(const float* in, int ld, uint8_t* out, size_t pixels, cudaStream_t st) {
     DRAG_REQUIRE(in && out && ld >= 3, "image_postprocess: bad arguments");
-    image_postprocess_kernel<<<static_cast<unsigned>((pixels + 255) / 256), 256, 0, st>>>(in, ld, out, pixels);
+    image_postprocess_kernel<<<static_cast<unsigned>((pixels + 255) / 256), 256, 0, st>>>(in, ld, out, pixels); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(256) image_preprocess_kernel(const uint8_t* __
 int image_preprocess_u8(const uint8_t* in, const uint8_t* mask, __nv_bfloat16* out, size_t pixels, int C_pad, cudaStream_t st) {
     DRAG_REQUIRE(in && out && C_pad >= 3, "image_preprocess: bad arguments");
     const size_t total = pixels * C_pad;
-    image_preprocess_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, mask, out, C_pad, total);
+    image_preprocess_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, mask, out, C_pad, total); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(256) axpby_kernel(const __nv_bfloat16* __restr
 
 int axpby_bf16(const __nv_bfloat16* x, const __nv_bfloat16* y, float a, float b, __nv_bfloat16* out, size_t n, cudaStream_t st) {
     DRAG_REQUIRE(x && y && out, "axpby: null pointer");
-    axpby_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, y, a, b, out, n);
+    axpby_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, y, a, b, out, n); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }

@@ -31,6 +31,43 @@ DATASET_GROUPS = {"dataset1": ["UODD", "ArTaxOr", "FISH", "coco"], "dataset2": [
 ALL_DATASETS = ["FISH", "DIOR", "ArTaxOr", "UODD", "NEU-DET", "clipart1k", "coco"]
 
 
+def _redux_prior(pipe_prior_redux, coco_image, target_image):
+    """The two-image Redux call of reference :459-465 (scaled rows summed; pooled = 2 x CLIP(""))."""
+    return pipe_prior_redux([coco_image, target_image], prompt=["", PROMPT_RETRIEVAL], prompt_2=["", PROMPT_RETRIEVAL],
+                            prompt_embeds_scale=[COCO_IMAGE_SCALE, TARGET_IMAGE_SCALE],
+                            pooled_prompt_embeds_scale=[COCO_TEXT_SCALE, TARGET_TEXT_SCALE])
+
+
+def _write_outputs(image, coco_image_path, target_image_path, target_image, output_path, rank, similarity, database_type,
+                   num_inference_steps) -> None:
+    """Files of reference :476-519 for one generated image."""
+    width, height = target_image.size
+    height, width = max((height // 16) * 16, 64), max((width // 16) * 16, 64)     # derived but unused (Appendix B)
+    out_dir = os.path.dirname(output_path)
+    os.makedirs(out_dir, exist_ok=True)
+    image.save(output_path)
+    params_file = os.path.join(out_dir, "params.txt")
+    if not os.path.exists(params_file):
+        with open(params_file, "w") as f:
+            f.write(f"数据库类型: {database_type}\n参考图像权重: {COCO_IMAGE_SCALE}\n目标图像权重: {TARGET_IMAGE_SCALE}\n"
+                    f"参考文本权重: {COCO_TEXT_SCALE}\n目标文本权重: {TARGET_TEXT_SCALE}\n提示词: {PROMPT_RETRIEVAL}\n"
+                    f"指导比例: 2.5\n推理步数: {num_inference_steps}\n生成图像尺寸: {width}x{height}\n"
+                    f"原始图像尺寸: {target_image.size[0]}x{target_image.size[1]}\n")
+    rank_str = f"rank{rank}" if rank is not None else ""
+    sim_str = f"_sim{similarity:.4f}" if similarity is not None else ""
+    with open(os.path.join(out_dir, f"ref_info{rank_str}{sim_str}.txt"), "w") as f:
+        f.write(f"数据库类型: {database_type}\n参考图像: {coco_image_path}\n目标图像: {target_image_path}\n"
+                f"生成图像尺寸: {width}x{height}\n原始图像尺寸: {target_image.size[0]}x{target_image.size[1]}\n")
+        if rank is not None:
+            f.write(f"排名: {rank}\n")
+        if similarity is not None:
+            f.write(f"相似度: {similarity}\n")
+    target_out = os.path.join(out_dir, "target_input.png")
+    if not os.path.exists(target_out):
+        shutil.copy(target_image_path, target_out)
+    shutil.copy(coco_image_path, os.path.join(out_dir, f"ref_input{rank_str}.jpg"))
+
+
 def generate_image(pipe_prior_redux, pipe, coco_image_path, target_image_path, output_path, rank=None, similarity=None,
                    database_type="coco", num_inference_steps=50, size=1024) -> bool:
     """Reference :439-524. Returns False (after printing) on any failure, like the reference."""
@@ -39,40 +76,41 @@ def generate_image(pipe_prior_redux, pipe, coco_image_path, target_image_path, o
     try:
         coco_image = Image.open(coco_image_path).convert("RGB")
         target_image = Image.open(target_image_path).convert("RGB")
-        width, height = target_image.size
-        height, width = max((height // 16) * 16, 64), max((width // 16) * 16, 64)     # derived but unused (Appendix B)
-        prior = pipe_prior_redux([coco_image, target_image], prompt=["", PROMPT_RETRIEVAL], prompt_2=["", PROMPT_RETRIEVAL],
-                                 prompt_embeds_scale=[COCO_IMAGE_SCALE, TARGET_IMAGE_SCALE],
-                                 pooled_prompt_embeds_scale=[COCO_TEXT_SCALE, TARGET_TEXT_SCALE])
+        prior = _redux_prior(pipe_prior_redux, coco_image, target_image)
         images = pipe(guidance_scale=2.5, num_inference_steps=num_inference_steps, height=size, width=size,
                       generator=torch.Generator("cpu").manual_seed(0), **prior).images
-        out_dir = os.path.dirname(output_path)
-        os.makedirs(out_dir, exist_ok=True)
-        images[0].save(output_path)
-        params_file = os.path.join(out_dir, "params.txt")
-        if not os.path.exists(params_file):
-            with open(params_file, "w") as f:
-                f.write(f"数据库类型: {database_type}\n参考图像权重: {COCO_IMAGE_SCALE}\n目标图像权重: {TARGET_IMAGE_SCALE}\n"
-                        f"参考文本权重: {COCO_TEXT_SCALE}\n目标文本权重: {TARGET_TEXT_SCALE}\n提示词: {PROMPT_RETRIEVAL}\n"
-                        f"指导比例: 2.5\n推理步数: {num_inference_steps}\n生成图像尺寸: {width}x{height}\n"
-                        f"原始图像尺寸: {target_image.size[0]}x{target_image.size[1]}\n")
-        rank_str = f"rank{rank}" if rank is not None else ""
-        sim_str = f"_sim{similarity:.4f}" if similarity is not None else ""
-        with open(os.path.join(out_dir, f"ref_info{rank_str}{sim_str}.txt"), "w") as f:
-            f.write(f"数据库类型: {database_type}\n参考图像: {coco_image_path}\n目标图像: {target_image_path}\n"
-                    f"生成图像尺寸: {width}x{height}\n原始图像尺寸: {target_image.size[0]}x{target_image.size[1]}\n")
-            if rank is not None:
-                f.write(f"排名: {rank}\n")
-            if similarity is not None:
-                f.write(f"相似度: {similarity}\n")
-        target_out = os.path.join(out_dir, "target_input.png")
-        if not os.path.exists(target_out):
-            shutil.copy(target_image_path, target_out)
-        shutil.copy(coco_image_path, os.path.join(out_dir, f"ref_input{rank_str}.jpg"))
+        _write_outputs(images[0], coco_image_path, target_image_path, target_image, output_path, rank, similarity,
+                       database_type, num_inference_steps)
         return True
     except Exception as e:
         print(f"生成图像时出错: {e}")
         return False
+
+
+def generate_images_batch(pipe_prior_redux, pipe, jobs, database_type="coco", num_inference_steps=50, size=1024) -> List[bool]:
+    """Several (reference image, target image) generations of the same 1024^2 shape as ONE FluxPipeline call. `jobs` =
+    [(coco_image_path, target_image_path, output_path, rank, similarity)]. Every generation keeps the reference's fixed
+    seed 0 through its own CPU generator (reference :472), so the images equal the one-at-a-time loop's. A failing batch
+    falls back to generate_image per job, which keeps the reference's print-and-continue behaviour."""
+    from PIL import Image
+    import torch
+    if len(jobs) == 1:
+        c, t, o, r, sm = jobs[0]
+        return [generate_image(pipe_prior_redux, pipe, c, t, o, r, sm, database_type, num_inference_steps, size)]
+    try:
+        loaded = [(Image.open(c).convert("RGB"), Image.open(t).convert("RGB")) for c, t, _, _, _ in jobs]
+        priors = [_redux_prior(pipe_prior_redux, ci, ti) for ci, ti in loaded]
+        images = pipe(guidance_scale=2.5, num_inference_steps=num_inference_steps, height=size, width=size,
+                      generator=[torch.Generator("cpu").manual_seed(0) for _ in jobs],
+                      prompt_embeds=torch.cat([p_["prompt_embeds"] for p_ in priors]),
+                      pooled_prompt_embeds=torch.cat([p_["pooled_prompt_embeds"] for p_ in priors])).images
+        for (c, t, o, r, sm), (_, ti), im in zip(jobs, loaded, images):
+            _write_outputs(im, c, t, ti, o, r, sm, database_type, num_inference_steps)
+        return [True] * len(jobs)
+    except Exception as e:
+        print(f"批量生成图像时出错 ({e})，改为逐张生成")
+        return [generate_image(pipe_prior_redux, pipe, c, t, o, r, sm, database_type, num_inference_steps, size)
+                for c, t, o, r, sm in jobs]
 
 
 def load_retrieval_results(retrieval_results_dir: str, dataset_name: str, shot_number: int) -> Optional[dict]:
@@ -104,7 +142,7 @@ def top_similar_images(results: dict, sample_name: str, limit: int = 5) -> List[
 
 def process_kshot_dataset_with_retrieval(dataset_name, pipe_prior_redux, pipe, results, shot_number, output_dir,
                                          lamainpaint_dir=LAMAINPAINT_DIR, database_type="coco", num_inference_steps=50,
-                                         size=1024, sample_filter=None) -> Optional[str]:
+                                         size=1024, sample_filter=None, gen_batch: int = 1) -> Optional[str]:
     shot_dir = os.path.join(lamainpaint_dir, dataset_name, f"{shot_number}_shot")
     if not os.path.isdir(shot_dir):
         print(f"错误：找不到k-shot目录 {shot_dir}")
@@ -138,15 +176,19 @@ def process_kshot_dataset_with_retrieval(dataset_name, pipe_prior_redux, pipe, r
             bad += 1
             continue
         any_ok = False
-        for sim, ref, rank in tops:
-            out = os.path.join(sdir, f"generated_image_rank{rank}.png")
-            if generate_image(pipe_prior_redux, pipe, ref, target, out, rank=rank, similarity=sim,
-                              database_type=database_type, num_inference_steps=num_inference_steps, size=size):
-                print(f"成功生成样本 {name} 的图像 (rank {rank})")
-                total += 1
-                any_ok = True
-            else:
-                print(f"生成样本 {name} 的图像失败 (rank {rank})")
+        jobs = [(ref, target, os.path.join(sdir, f"generated_image_rank{rank}.png"), rank, sim) for sim, ref, rank in tops]
+        step = max(1, int(gen_batch))
+        for c0 in range(0, len(jobs), step):
+            chunk = jobs[c0:c0 + step]
+            done = generate_images_batch(pipe_prior_redux, pipe, chunk, database_type=database_type,
+                                         num_inference_steps=num_inference_steps, size=size)
+            for (_, _, _, rank, _), good in zip(chunk, done):
+                if good:
+                    print(f"成功生成样本 {name} 的图像 (rank {rank})")
+                    total += 1
+                    any_ok = True
+                else:
+                    print(f"生成样本 {name} 的图像失败 (rank {rank})")
         if any_ok:
             ok += 1
         else:
@@ -174,6 +216,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--model_size", type=str, default="full", choices=["full", "tiny"])
     p.add_argument("--num_inference_steps", type=int, default=50)
     p.add_argument("--image_size", type=int, default=1024)
+    p.add_argument("--gen_batch", type=int, default=4,
+                   help="generations of one sample (its top-ranked reference images) per FluxPipeline call; 1 = the "
+                        "reference's one-at-a-time loop (every generation keeps seed 0 either way)")
     p.add_argument("--rank", type=int, default=None, help="data-parallel rank (default: RANK env or 0)")
     p.add_argument("--world_size", type=int, default=None, help="data-parallel world size (default: WORLD_SIZE env or 1)")
     return p
@@ -194,7 +239,7 @@ def main(argv=None) -> int:
     world = args.world_size if args.world_size is not None else int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
     pipes = load_model(device=f"cuda:{local}", want=("dev",), weights_dir=args.weights_dir, size=args.model_size,
-                       max_side=args.image_size)
+                       max_side=args.image_size, max_batch=max(1, args.gen_batch))
     for ds in datasets:
         for k in shots:
             results = load_retrieval_results(args.retrieval_results_dir, ds, k)
@@ -206,5 +251,5 @@ def main(argv=None) -> int:
             mine = set(H.split_samples_for_gpus(names, world)[rank]) if world > 1 else None
             process_kshot_dataset_with_retrieval(ds, pipes.prior_redux, pipes.pipe, results, k, args.output_dir,
                                                  args.lamainpaint_dir, args.database, args.num_inference_steps,
-                                                 args.image_size, sample_filter=mine)
+                                                 args.image_size, sample_filter=mine, gen_batch=max(1, args.gen_batch))
     return 0

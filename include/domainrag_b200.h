@@ -181,6 +181,10 @@ int drag_axpby_bf16(const void* x, const void* y, float a, float b, void* out, i
 int drag_prof_enable(int on);
 int drag_prof_collect(double* ms, double* work, int* count, int n_classes);
 
+/* Number of CUDA kernels this library has launched in the calling process since the last reset (host-side counter bumped at
+ * every launch site; single-threaded use as everywhere in this ABI). bench.py reports it as `gpu_launches`. */
+int drag_launch_count(int64_t* count, int reset);
+
 /* Debug knobs for bring-up and A/B comparisons (key 1/2: unused; key 3: 1 = force the single-CTA GEMM kernel
  * instead of the CTA-pair cta_group::2 kernel; key 4: > 0 = force the GEMM tile-raster group size, 1 << 20 = plain
  * row-fastest order; key 5: 1 = head-dim-64 attention always on the two-tile ping-pong kernel; key 6: > 0 = force the

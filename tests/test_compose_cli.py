@@ -35,6 +35,8 @@ class StubPipe:
         self.calls.append(kw)
         w, h = kw.get("width", 64), kw.get("height", 64)
         n = len(kw["image"]) if isinstance(kw.get("image"), list) else 1
+        if "image" not in kw and isinstance(kw.get("generator"), list):
+            n = len(kw["generator"])
         return _Out(images=[Image.new("RGB", (16 * (w // 16), 16 * (h // 16)), (10, 200, 30)) for _ in range(n)])
 
 
@@ -79,6 +81,17 @@ def test_generate_cli_file_surface(tmp_path):
     assert (k["guidance_scale"], k["num_inference_steps"], k["height"], k["width"]) == (2.5, 50, 1024, 1024)
     assert k["generator"].initial_seed() == 0 and tuple(k["prompt_embeds"].shape) == (1, 3, 4)
     assert "生成图像尺寸: 96x64" in open(os.path.join(base, "airport_1", "params.txt")).read()
+    assert len(pipes.pipe.calls) == 5
+    # the same job with the ranks of a sample generated in batches of 4: same files, 2 pipeline calls, seed 0 per image
+    pipes_b = Pipes()
+    base_b = GC.process_kshot_dataset_with_retrieval("DIOR", pipes_b.prior_redux, pipes_b.pipe, results, 5,
+                                                     str(tmp_path / "result_b"), str(tmp_path / "lamainpaint"), gen_batch=4)
+    files_b = set(os.listdir(os.path.join(base_b, "airport_1")))
+    assert files_b == files
+    assert [len(c["generator"]) if isinstance(c["generator"], list) else 1 for c in pipes_b.pipe.calls] == [4, 1]
+    kb = pipes_b.pipe.calls[0]
+    assert all(g.initial_seed() == 0 for g in kb["generator"]) and tuple(kb["prompt_embeds"].shape) == (4, 3, 4)
+    assert len(pipes_b.prior_redux.calls) == 5 and GC.build_parser().parse_args([]).gen_batch == 4
 
 
 def test_compose_cli_file_surface(tmp_path):

@@ -155,3 +155,26 @@ def test_fill_batch_with_generator_list_equals_sequential_calls(lib):
     with pytest.raises(ValueError):
         fill(prompt_embeds=ctx, pooled_prompt_embeds=pooled, image=[image] * 3, mask_image=[mask] * 3,
              generator=[torch.Generator("cpu").manual_seed(1)], **kw)
+
+
+def test_generate_batch_with_generator_list_equals_sequential_calls(lib):
+    """batch_generate_flux_kshot's ranks of one sample as one FluxPipeline call: every image keeps seed 0 (reference :472)."""
+    from domain_rag_b200 import flux as F
+    from domain_rag_b200.vae import FluxVAE
+    vae = FluxVAE(bf(OV.init_params(seed=5000, ch=64)))
+    g = torch.Generator().manual_seed(9)
+    ctx, pooled = torch.randn(2, 24, 64, generator=g).bfloat16(), torch.randn(2, 32, generator=g).bfloat16()
+    H, W, T = 64, 96, 3
+    cfg = F.FluxConfig(in_channels=64, **FLUX_SMALL)
+    p = bf(OF.init_params(OF.FluxConfig(in_channels=64, **FLUX_SMALL), seed=3001))
+    pipe = F.FluxPipeline(F.FluxTransformer(cfg, p, max_batch=2, max_img_tokens=(H // 16) * (W // 16), txt_tokens=24), vae)
+    kw = dict(guidance_scale=2.5, num_inference_steps=T, height=H, width=W)
+    batch = pipe(prompt_embeds=ctx, pooled_prompt_embeds=pooled,
+                 generator=[torch.Generator("cpu").manual_seed(0) for _ in range(2)], **kw)
+    assert len(batch.images) == 2
+    for i in range(2):
+        one = pipe(prompt_embeds=ctx[i:i + 1], pooled_prompt_embeds=pooled[i:i + 1],
+                   generator=torch.Generator("cpu").manual_seed(0), **kw)
+        assert rel_l2(batch.latents[i:i + 1], one.latents) < 2e-3
+        d = np.abs(np.asarray(batch.images[i]).astype(np.int32) - np.asarray(one.images[0]).astype(np.int32))
+        assert d.max() <= 2, d.max()
