@@ -183,7 +183,7 @@ def run(args):
                      "share_of_step": round(g_ms / (g_ms + a_ms), 4), "peak_source": peaks["source"] + " (sustained)",
                      "attention": {"achieved": round(a_fl / (a_ms * 1e-3) / 1e12, 1), "kernel_ms": round(a_ms / max(a_n, 1), 4),
                                    "launches": a_n, "share_of_step": round(a_ms / (g_ms + a_ms), 4)}},
-        "cpu_baseline": cpu_baseline(),
+        **({"cpu_baseline": cpu_baseline()} if world == 1 else {}),   # rank 0 at N = 1 only
     }
     return out
 
@@ -393,5 +393,5 @@ def run_full(args):
                      "frac_of_same_box_cublas": round(g_fl / (g_ms * 1e-3) / 1e12 / max(cublas_here, 1e-9), 4),
                      "attention": {"achieved": round(a_fl / (a_ms * 1e-3) / 1e12, 1), "kernel_ms": round(a_ms / max(a_n, 1), 4),
                                    "launches": a_n, "share_of_step": round(a_ms / ms_per_step, 4)}},
-        "cpu_baseline": cpu_baseline(),
+        **({"cpu_baseline": cpu_baseline()} if world == 1 else {}),   # rank 0 at N = 1 only
     }

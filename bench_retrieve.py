@@ -169,7 +169,7 @@ def run(args):
                      "peak_source": peaks["source"] + " (sustained)",
                      "attention": {"achieved": round(a_fl / (a_ms * 1e-3) / 1e12, 1), "kernel_ms": round(a_ms / max(a_n, 1), 4),
                                    "launches": a_n, "share_of_step": round(a_ms / ms_per_step, 4)}},
-        "cpu_baseline": cpu_baseline(),
+        **({"cpu_baseline": cpu_baseline()} if world == 1 else {}),   # rank 0 at N = 1 only
     }
 
 
