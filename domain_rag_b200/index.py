@@ -196,13 +196,18 @@ class ShardedIndexFlatIP:
             D, I = self._local_search(self._rows, q, k, self.lo)
         if self.world == 1:
             return D, I
-        gather = self._all_gather
-        if gather is None:
-            def gather(t):
-                outs = [torch.empty_like(t) for _ in range(self.world)]
-                dist.all_gather(outs, t.contiguous())
-                return torch.stack(outs, dim=1)  # [nq, world, k]
-        Dg, Ig = gather(D), gather(I)
+        if self._all_gather is not None:
+            Dg, Ig = self._all_gather(D), self._all_gather(I)
+        else:
+            # ONE collective per search: scores bit-cast to int32, widened to int64 and sent as the second column of
+            # the [nq, k, 2] int64 (id, score) pairs (two separate all-gathers cost two NCCL latencies; at nq = 1 the
+            # exchange is pure latency: nq * k * 16 B per rank)
+            pairs = torch.stack([I, D.contiguous().view(torch.int32).to(torch.int64)], dim=-1).contiguous()
+            out = torch.empty((self.world,) + tuple(pairs.shape), dtype=torch.int64, device=pairs.device)
+            dist.all_gather(list(out.unbind(0)), pairs)          # contiguous views of one buffer: one collective
+            out = out.permute(1, 0, 2, 3)                                   # [nq, world, k, 2]
+            Ig = out[..., 0].contiguous()
+            Dg = out[..., 1].to(torch.int32).contiguous().view(torch.float32)
         if self._merge is not None:
             return self._merge(Dg, Ig, k)
         return merge_topk_device(Dg, Ig, k)
