@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
 import torch

@@ -14,7 +14,7 @@ Everything executes in libdomainrag_b200.so; there is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Callable, Optional, Sequence
+from typing import Callable, Optional
 
 import numpy as np
 

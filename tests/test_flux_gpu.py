@@ -1,8 +1,6 @@
 """GPU parity: attention / row kernels vs PyTorch fp32 references of the same op, and the Flux MMDiT
 engine (forward + sampling loop) vs the CPU fp32 oracle at reduced size (full width is infeasible on
 the CPU: 88.85 TFLOP per forward)."""
-import math
-
 import pytest
 import torch
 

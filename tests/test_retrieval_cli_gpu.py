@@ -6,7 +6,6 @@ import os
 import numpy as np
 import pytest
 import torch
-from PIL import Image
 
 from oracle import ip_topk as OT
 from oracle import stem as OS

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import ip_topk as O
-from tests.synth import corpus, well_separated
+from tests.synth import well_separated
 
 pytestmark = pytest.mark.gpu
 
