@@ -57,6 +57,7 @@ def run(args):
     rank, world, local = B.dist_setup(args.gpus)
     dev = torch.device("cuda", local)
     lib = _lib.load()
+    MODEL = getattr(args, "clip_model", None) or globals()["MODEL"]     # ViT-L/14 (BASELINE) or ViT-B/32 (reference default)
     model, _ = clip.load(MODEL, device=dev, seed=2000)
     cfg = clip.CONFIGS[MODEL]
     stem = ResNetEncoder(seed=2000).to(dev).eval()
@@ -145,7 +146,7 @@ def run(args):
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     h2d = (corpus_h.numel() + queries_h.numel() + style_h.numel()) * 4
     return {
-        "metric": "C2 retrieval: corpus images embedded + indexed + queried per second (ViT-L/14, top-100, style re-rank)",
+        "metric": f"C2 retrieval: corpus images embedded + indexed + queried per second ({MODEL}, top-100, style re-rank)",
         "value": round(n_img * world / (ms_per_step * 1e-3), 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -169,11 +170,11 @@ def run(args):
                      "peak_source": peaks["source"] + " (sustained)",
                      "attention": {"achieved": round(a_fl / (a_ms * 1e-3) / 1e12, 1), "kernel_ms": round(a_ms / max(a_n, 1), 4),
                                    "launches": a_n, "share_of_step": round(a_ms / ms_per_step, 4)}},
-        **({"cpu_baseline": cpu_baseline()} if world == 1 else {}),   # rank 0 at N = 1 only
+        **({"cpu_baseline": cpu_baseline(model=MODEL)} if world == 1 else {}),   # rank 0 at N = 1 only
     }
 
 
-def cpu_baseline(n_sample: int = 16):
+def cpu_baseline(n_sample: int = 16, model: str = MODEL):
     """Oracle on the host cores: ViT-L/14 fp32 embed of a bounded sample, scaled linearly to the corpus (the scan and
     the stem statistics are < 1 % of the CPU time at C2 sizes and are timed on their full sizes)."""
     import numpy as np
@@ -183,6 +184,7 @@ def cpu_baseline(n_sample: int = 16):
     from oracle import stem as OS
     from oracle import vit as OV
     torch.set_num_threads(os.cpu_count())
+    MODEL = model
     cfg = OV.CONFIGS[MODEL]
     state = OV.init_state(cfg, 2000)
     x = torch.randn(n_sample, 3, cfg.image, cfg.image, generator=torch.Generator().manual_seed(1))
@@ -214,16 +216,17 @@ def run_reference(args):
     if rank != 0:
         return None
     vals, cb = [], None
+    m = getattr(args, "clip_model", None) or MODEL
     for _ in range(max(1, min(args.steps, 2))):
-        cb = cpu_baseline()
+        cb = cpu_baseline(model=m)
         vals.append(cb["value"])
     val = sum(vals) / len(vals)
     cb["value"] = val
     return {"impl": "reference",
-            "metric": "C2 retrieval: corpus images embedded + indexed + queried per second (ViT-L/14, top-100, style re-rank)",
+            "metric": f"C2 retrieval: corpus images embedded + indexed + queried per second ({m}, top-100, style re-rank)",
             "value": val, "unit": "images/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round((N_CORPUS + N_QUERY) / val * 1e3, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C2 per GPU: {N_CORPUS} images, CLIP {MODEL}, top-{TOP_K}, style re-rank (CPU oracle, bounded "
+            "config": {"workload": f"C2 per GPU: {N_CORPUS} images, CLIP {m}, top-{TOP_K}, style re-rank (CPU oracle, bounded "
                                    "sample scaled linearly)"},
             "cpu_baseline": cb, "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
