@@ -217,6 +217,7 @@ def main():
                     help="compose: compositions per GPU and step, run as one batch (C4: 32 compositions / 8 GPUs = 4)")
     ap.add_argument("--clip-model", dest="clip_model", default=None, choices=["ViT-L/14", "ViT-B/32", "ViT-B/16"],
                     help="retrieve: image tower (default ViT-L/14 = BASELINE config C2; ViT-B/32 = the reference script's default)")
+    ap.add_argument("--embed-batch", dest="embed_batch", type=int, default=None, help="retrieve: images per encode_image call (default 500)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     workload = args.workload or default_workload()

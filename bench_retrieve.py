@@ -19,7 +19,7 @@ from pathlib import Path
 
 REPO = Path(__file__).resolve().parent
 
-N_CORPUS, N_QUERY, TOP_K, EMBED_BATCH = 10_000, 7, 100, 250
+N_CORPUS, N_QUERY, TOP_K, EMBED_BATCH = 10_000, 7, 100, 500      # 500 vs 250 per encode call: 5308 vs 5188 img/s (run 30)
 MODEL = "ViT-L/14"
 
 
@@ -58,6 +58,7 @@ def run(args):
     dev = torch.device("cuda", local)
     lib = _lib.load()
     MODEL = getattr(args, "clip_model", None) or globals()["MODEL"]     # ViT-L/14 (BASELINE) or ViT-B/32 (reference default)
+    EMBED_BATCH = int(getattr(args, "embed_batch", None) or globals()["EMBED_BATCH"])
     model, _ = clip.load(MODEL, device=dev, seed=2000)
     cfg = clip.CONFIGS[MODEL]
     stem = ResNetEncoder(seed=2000).to(dev).eval()
