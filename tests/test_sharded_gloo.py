@@ -48,14 +48,13 @@ def _worker(rank, world, port, n, d, nq, k, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,k", [(1001, 10), (37, 100)])
-def test_sharded_search_equals_single_index_under_gloo(n, k):
-    world = 2
+@pytest.mark.parametrize("n,k,world", [(1001, 10, 2), (37, 100, 2), (501, 16, 3)])
+def test_sharded_search_equals_single_index_under_gloo(n, k, world):
     port = _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, n, 32, 3, k, ret), nprocs=world, join=True)
-    assert dict(ret) == {0: True, 1: True}
+    assert dict(ret) == {r: True for r in range(world)}
 
 
 def test_shard_bounds_matches_reference_split_rule():
