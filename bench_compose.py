@@ -32,6 +32,16 @@ def flops_per_forward(s_img: int, s_txt: int = S_TXT, d: int = D, blocks: int = 
     return gemm, attn
 
 
+def full_workload(Bc: int) -> str:
+    """config.workload of the compose line - shared by the b200 arm and the reference arm."""
+    return (f"C4 per-GPU slice (32 compositions / 8 GPUs): {Bc} full Flux-Redux compositions at 1024^2 per "
+            "step and GPU, run as one batch: Redux prior per composition (SigLIP so400m + Redux embedder + "
+            "blend) -> Flux-Fill (VAE encode of images and masked images, mask packing, 50 MMDiT steps, "
+            "C_in=384, 19+38 blocks, S=1241+4096, guidance 30, strength 1.0) -> VAE decode -> uint8 pixels; "
+            "random-init weights, synthetic images; text tokens are per-prompt constants (T5/CLIP-text not "
+            "on the path); LaMa out of scope")
+
+
 def gemm_traffic_from_profile():
     """dram read+write bytes per launch of the dominant GEMM shape (MLP-up of a batch-4 step) from the committed
     ncu --set full capture; None when the file is absent."""
@@ -237,8 +247,11 @@ def run_reference(args):
             "value": val, "unit": "images/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(1e3 / val, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C4 per-GPU slice: Flux-Redux composition 1024^2, 50 steps, batch 1 "
-                                   "(CPU oracle, extrapolated from one double + one single block per step sample)"},
+            "config": {"workload": full_workload(max(1, int(getattr(args, "batch", 4)))),
+                       "batch_per_gpu": max(1, int(getattr(args, "batch", 4))),
+                       "sample": "CPU oracle (fp32, all host cores): one double + one single MMDiT block timed at full width and "
+                                 "sequence per step, extrapolated x19 / x38 x 50 steps; images/s does not depend on the batch on "
+                                 "the CPU; SigLIP / VAE (< 0.2 % of the FLOPs) not timed"},
             "cpu_baseline": cb,
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
@@ -365,12 +378,7 @@ def run_full(args):
         "value": round(Bc * world / (ms_per_step * 1e-3), 5), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"C4 per-GPU slice (32 compositions / 8 GPUs): {Bc} full Flux-Redux compositions at 1024^2 per "
-                               "step and GPU, run as one batch: Redux prior per composition (SigLIP so400m + Redux embedder + "
-                               "blend) -> Flux-Fill (VAE encode of images and masked images, mask packing, 50 MMDiT steps, "
-                               "C_in=384, 19+38 blocks, S=1241+4096, guidance 30, strength 1.0) -> VAE decode -> uint8 pixels; "
-                               "random-init weights, synthetic images; text tokens are per-prompt constants (T5/CLIP-text not "
-                               "on the path); LaMa out of scope",
+        "config": {"workload": full_workload(Bc),
                    "batch_per_gpu": Bc,
                    "l2_policy": "23.8 GB of weights + 0.4 GB of activations stream per denoising step (>> 126 MB L2)",
                    "flops_per_image": STEPS * (gemm_fl + attn_fl),
