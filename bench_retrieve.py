@@ -30,6 +30,14 @@ def vit_flops_per_image(cfg) -> float:
     return cfg.layers * layer + 2.0 * g * g * (3 * cfg.patch ** 2) * d + 2.0 * d * cfg.out_dim
 
 
+def c2_workload(model: str, embed_batch: int) -> str:
+    """config.workload of the retrieve line - shared by the b200 arm and the reference arm."""
+    return (f"C2 per GPU: {N_CORPUS} synthetic 224^2 images -> CLIP {model} embed (batches of {embed_batch}) + "
+            f"L2 normalise -> resident fp32 index shard; {N_QUERY} queries -> exact top-{TOP_K} "
+            f"(sharded: all-gather of per-shard top-k) -> ResNet-50-stem style statistics of "
+            f"{N_QUERY}x(1+{TOP_K}) 256^2 images; random-init weights")
+
+
 def synth_images(n, res, seed, device, chunk=500):
     """Preprocessed image tensors fp32 [n,3,res,res] (what `preprocess(PIL)` stacks to), generated on the device:
     low-frequency structure + noise so embeddings are spread out."""
@@ -151,10 +159,7 @@ def run(args):
         "value": round(n_img * world / (ms_per_step * 1e-3), 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"C2 per GPU: {N_CORPUS} synthetic 224^2 images -> CLIP {MODEL} embed (batches of {EMBED_BATCH}) + "
-                               f"L2 normalise -> resident fp32 index shard; {N_QUERY} queries -> exact top-{TOP_K} "
-                               f"(sharded: all-gather of per-shard top-k) -> ResNet-50-stem style statistics of "
-                               f"{N_QUERY}x(1+{TOP_K}) 256^2 images; random-init weights",
+        "config": {"workload": c2_workload(MODEL, EMBED_BATCH),
                    "l2_policy": "6 GB of images stream through per step (>> 126 MB L2)",
                    "flops_per_image": vit_flops_per_image(cfg),
                    "achieved_tflops": round(flops / (ms_per_step * 1e-3) / 1e12, 1)},
@@ -228,6 +233,6 @@ def run_reference(args):
             "value": val, "unit": "images/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round((N_CORPUS + N_QUERY) / val * 1e3, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C2 per GPU: {N_CORPUS} images, CLIP {m}, top-{TOP_K}, style re-rank (CPU oracle, bounded "
-                                   "sample scaled linearly)"},
+            "config": {"workload": c2_workload(m, int(getattr(args, "embed_batch", None) or EMBED_BATCH)),
+                       "sample": cb["sample"]},
             "cpu_baseline": cb, "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
