@@ -231,8 +231,10 @@ def axpby_(x: torch.Tensor, y: torch.Tensor, a: float, b: float) -> torch.Tensor
 
 
 def executed_range(num_inference_steps: int, strength: float) -> int:
-    """First executed step index of an img2img-style call: T - min(int(T * strength), T) (diffusers get_timesteps)."""
-    return num_inference_steps - int(min(num_inference_steps * strength, num_inference_steps))
+    """First executed step index of an img2img-style call, as diffusers' Flux get_timesteps computes it:
+    t_start = int(max(T - min(T * strength, T), 0)) - the truncation happens AFTER the subtraction, so a fractional
+    T * strength rounds the start DOWN (T = 50, strength 0.75 -> start 12, 38 executed steps)."""
+    return int(max(num_inference_steps - min(num_inference_steps * strength, num_inference_steps), 0))
 
 
 class FluxPipeline:

@@ -51,8 +51,9 @@ def dataset_params(dataset_name: str) -> DatasetParams:
 
 
 def executed_steps(num_inference_steps: int, strength: float) -> int:
-    """Steps an img2img-style Flux pipeline actually runs: min(int(T * s), T) (diffusers get_timesteps)."""
-    return int(min(num_inference_steps * strength, num_inference_steps))
+    """Steps an img2img-style Flux pipeline actually runs: T - t_start with
+    t_start = int(max(T - min(T * s, T), 0)) (diffusers get_timesteps; T = 50, s = 0.75 -> 38 steps)."""
+    return num_inference_steps - int(max(num_inference_steps - min(num_inference_steps * strength, num_inference_steps), 0))
 
 
 def split_samples_for_gpus(sample_list: Sequence, num_gpus: int) -> List[list]:

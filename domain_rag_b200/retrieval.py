@@ -25,9 +25,14 @@ _STYLE_CACHE_MAX = 200_000
 
 
 def clean_image_path(path):
-    """reference :77-86 - strip the stray "pipeline/" prefix some caches carry."""
-    if isinstance(path, str):
-        return path.replace("../../pipeline/datasets", "../../datasets")
+    """reference :77-86 - two rewrites, the second only when the first did not apply: the stray "pipeline/" prefix some
+    caches carry is stripped; otherwise corpus paths cached as ../../datasets/coco/... are redirected to ./coco/...
+    (the default --pretrained-coco-features path lists rely on it)."""
+    if not isinstance(path, str):
+        return path
+    for stale, current in (("../../pipeline/datasets", "../../datasets"), ("../../datasets/coco", "./coco")):
+        if stale in path:
+            return path.replace(stale, current)
     return path
 
 

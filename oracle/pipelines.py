@@ -27,7 +27,8 @@ def redux_prior(siglip_state, siglip_cfg, redux_state, images, txt_tokens, poole
 
 
 def executed_start(num_steps: int, strength: float) -> int:
-    return num_steps - int(min(num_steps * strength, num_steps))
+    """diffusers 0.33.1 FluxFillPipeline.get_timesteps: init = min(T * s, T); t_start = int(max(T - init, 0))."""
+    return int(max(num_steps - min(num_steps * strength, num_steps), 0))
 
 
 def pack_mask(mask: torch.Tensor) -> torch.Tensor:

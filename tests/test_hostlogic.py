@@ -40,4 +40,14 @@ def test_tables_and_steps():
     assert H.dataset_params("FISH").redux_prompt.startswith("wihout fish") and H.dataset_params("FISH").image_prompt_scale == 1.2
     assert H.dataset_params("unknown") == H.DatasetParams(0.75, 30.0, 1.0, 1024, "")
     assert [H.executed_steps(50, s) for s in (0.3, 0.4, 0.8, 0.9, 1.0, 1.5)] == [15, 20, 40, 45, 50, 50]
+    # fractional T * s: diffusers truncates the START index (int(max(T - min(T*s, T), 0))), so the step count rounds UP;
+    # the reference's default strength 0.75 (every dataset outside the table) runs 38 of 50 steps, not 37
+    assert [H.executed_steps(50, s) for s in (0.75, 0.35, 0.6, 0.01)] == [38, 18, 30, 1]
+    assert [H.executed_steps(28, s) for s in (0.75, 0.5, 0.33)] == [21, 14, 10]
+    from domain_rag_b200.flux import executed_range
+    from oracle.pipelines import executed_start
+    for T in (4, 20, 28, 50):
+        for s in (0.0, 0.01, 0.3, 0.33, 0.35, 0.5, 0.6, 0.75, 0.8, 0.9, 0.99, 1.0, 1.5):
+            assert executed_range(T, s) == executed_start(T, s) == T - H.executed_steps(T, s)
+            assert executed_range(T, s) == int(max(T - min(T * s, T), 0))
     assert H.scale_bbox((10.6, 3.2, 7.9, 5.5), 1.7) == (18, 5, 13, 9)

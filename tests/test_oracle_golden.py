@@ -94,3 +94,39 @@ def test_ip_topk_oracle_properties():
     Ds, Is = ip_topk.sharded_ip_topk(x, q, 10, shard_bounds(500, 3))
     np.testing.assert_array_equal(Is, I)
     np.testing.assert_array_equal(Ds, D)
+
+
+# ------------------------------------------------------------------ second batch of reference-generated vectors
+@pytest.fixture(scope="module")
+def ref_extra(golden_dir):
+    return json.load(open(golden_dir / "ref_extra.json")), np.load(golden_dir / "ref_extra_arrays.npz")
+
+
+def test_clean_image_path_matches_reference_golden(ref_extra):
+    """Both rewrites of retrieval/clip100_resnet_style_all_shots.py:77-86 (pipeline/ prefix, ../../datasets/coco -> ./coco)."""
+    from domain_rag_b200.retrieval import clean_image_path
+    for c in ref_extra[0]["clean_paths"]:
+        assert clean_image_path(c["in"]) == c["out"], c
+
+
+def test_dataset_tables_match_reference_golden(ref_extra):
+    from domain_rag_b200 import hostlogic as H
+    for name, want in ref_extra[0]["dataset_params"].items():
+        p = H.dataset_params(name)
+        assert dict(strength=p.strength, guidance_scale=p.guidance_scale, image_prompt_scale=p.image_prompt_scale,
+                    upscale_dimension=p.upscale_dimension, redux_prompt=p.redux_prompt) == want, name
+
+
+def test_first_stage_oracle_matches_reference_call_site(ref_extra):
+    """oracle.ip_topk over the vstack of the non-empty sources (dict order, float32 cast) reproduces the records the
+    reference's clip_first_stage_retrieval emitted (ids, order, scores, k clamp, duplicate across sources)."""
+    g, arrs = ref_extra
+    x = np.vstack([arrs["coco"].astype(np.float32), arrs["mini_imagenet"].astype(np.float32)])
+    for case in g["first_stage"]:
+        if case.get("only_empty"):
+            assert case["records"] == []
+            continue
+        q = arrs["queries"][case["query"]][None].astype(np.float32)
+        D, I = ip_topk.ip_topk(x, q, min(case["top_k"], len(x)))
+        assert [r["index"] for r in case["records"]] == I[0].tolist()
+        np.testing.assert_allclose([r["similarity"] for r in case["records"]], D[0], rtol=0, atol=1e-6)

@@ -141,3 +141,29 @@ def test_full_size_properties(IndexFlatIP):
     s = (x.double() @ q[1].double())
     kth = torch.topk(s, k).values[-1]
     assert abs(float(D[1, -1]) - float(kth)) <= 1e-6
+
+
+def test_first_stage_retrieval_matches_reference_call_site_golden(lib, golden_dir):
+    """domain_rag_b200.retrieval.clip_first_stage_retrieval (the drop-in for :396-451) on the GPU reproduces, record for
+    record, what the reference's own function emitted for a seeded multi-source corpus (tests/golden/ref_extra.json,
+    oracle/make_golden_extra.py): source order, ids, duplicate across sources, k clamp, empty and None sources."""
+    import json
+
+    from domain_rag_b200 import retrieval as R
+    g = json.load(open(golden_dir / "ref_extra.json"))
+    arrs = np.load(golden_dir / "ref_extra_arrays.npz")
+    feats = {"coco": arrs["coco"], "empty": np.zeros((0, 64), np.float32), "none": None,
+             "mini_imagenet": arrs["mini_imagenet"]}
+    paths = {"coco": [f"../../datasets/coco/train2017/{i:012d}.jpg" for i in range(300)], "empty": [], "none": [],
+             "mini_imagenet": [f"./mini/n{i:05d}.JPEG" for i in range(150)]}
+    for case in g["first_stage"]:
+        q = arrs["queries"][case["query"]]
+        if case.get("only_empty"):
+            assert R.clip_first_stage_retrieval(q, {"empty": feats["empty"], "none": None}, {"empty": [], "none": []},
+                                                top_k=case["top_k"]) == []
+            continue
+        got = R.clip_first_stage_retrieval(q, feats, paths, top_k=case["top_k"])
+        want = case["records"]
+        assert [(r["index"], r["image_path"], r["source_dataset"]) for r in got] == \
+               [(r["index"], r["image_path"], r["source_dataset"]) for r in want]
+        np.testing.assert_allclose([r["similarity"] for r in got], [r["similarity"] for r in want], rtol=0, atol=1e-6)
