@@ -278,7 +278,8 @@ def run_full(args):
     dev = torch.device("cuda", local)
     lib = _lib.load()
     Bc = max(1, int(getattr(args, "batch", 4)))
-    pipes = load_model(device=dev, want=("fill",), weights_dir=None, size="full", max_side=HEIGHT, seed=3000, max_batch=Bc)
+    pipes = load_model(device=dev, want=("fill",), weights_dir=None, size="full", max_side=HEIGHT, seed=3000, max_batch=Bc,
+                       allow_random_init=True)
     prior, fill = pipes.prior_redux, pipes.pipe_fill
     vae = fill.vae
     rng = np.random.default_rng(1000 + rank)

@@ -112,7 +112,7 @@ def find_backgrounds(sample_dir: str) -> List[str]:
 def process_sample_hires(dataset_name, sample_id, pipes, process_id, category_name=None, sample_dir=None, shot_number=1,
                          datasets_dir=DATASETS_DIR, result_dir=RESULT_DIR, outpaint_base="./outpaint_hires",
                          upscale_override: Optional[Dict[str, int]] = None, seed_fn: Optional[Callable[[], int]] = None,
-                         num_inference_steps: int = 50, compose_batch: int = 1) -> dict:
+                         num_inference_steps: int = 50, compose_batch: int = 1, seed: Optional[int] = None) -> dict:
     """One sample end to end; returns the reference's log record (status completed / error)."""
     from PIL import Image
     import torch
@@ -193,9 +193,11 @@ def process_sample_hires(dataset_name, sample_id, pipes, process_id, category_na
                 continue
             bg_saved = os.path.join(out_dir, f"{prefix}_bg{suffix}_original.png")
             shutil.copy(bg_path, bg_saved)
-            seed = seed_fn() if seed_fn else random.randint(0, 2 ** 32 - 1)
+            # `seed` (--seed, an int: crosses the spawn boundary of --multi_gpu) > seed_fn > a fresh random seed per
+            # composition like the reference (:1230-1231)
+            job_seed = seed if seed is not None else (seed_fn() if seed_fn else random.randint(0, 2 ** 32 - 1))
             jobs.append(dict(bg_idx=bg_idx, bg_path=bg_path, bg_name=bg_name, suffix=suffix, mask_path=mask_path,
-                             bg_image=bg_image, bg_saved=bg_saved, seed=seed))
+                             bg_image=bg_image, bg_saved=bg_saved, seed=job_seed))
         step = max(1, int(compose_batch))
         for c0 in range(0, len(jobs), step):
             chunk = jobs[c0:c0 + step]
@@ -218,7 +220,7 @@ def process_sample_hires(dataset_name, sample_id, pipes, process_id, category_na
                                           generator=gens, strength=prm.strength).images
             for j, result in zip(chunk, results):
                 bg_idx, bg_path, bg_name, suffix = j["bg_idx"], j["bg_path"], j["bg_name"], j["suffix"]
-                mask_path, bg_saved, seed = j["mask_path"], j["bg_saved"], j["seed"]
+                mask_path, bg_saved, job_seed = j["mask_path"], j["bg_saved"], j["seed"]
                 hires_path = os.path.join(out_dir, f"{prefix}_hires_result{suffix}.png")
                 result.save(hires_path)
                 final = result
@@ -231,7 +233,7 @@ def process_sample_hires(dataset_name, sample_id, pipes, process_id, category_na
                 params = {"categories": categories, "image_scale": 1.0, "prompt_scale": 1.0,
                           "image_prompt_scale": prm.image_prompt_scale, "guidance_scale": prm.guidance_scale,
                           "num_inference_steps": num_inference_steps, "strength": prm.strength,
-                          "redux_prompt": prm.redux_prompt, "seed": seed, "process_id": process_id,
+                          "redux_prompt": prm.redux_prompt, "seed": job_seed, "process_id": process_id,
                           "shot_number": shot_number, "bg_index": bg_idx, "bg_filename": bg_name,
                           "original_bg_path": bg_path, "copied_bg_path": bg_saved,
                           "original_resolution": {"width": original.width, "height": original.height},
@@ -349,6 +351,48 @@ def _worker(rank, gpu_lists, dataset_name, shot_number, process_id, kwargs, load
     out_queue.put((rank, res))
 
 
+def _dead_rank_result(dataset_name, sample_ids, shot_number, process_id, rank, exitcode) -> dict:
+    """Result JSON of a worker that died before reporting (OOM, load_model error ...): every one of its samples is an
+    error record, so the merged JSON and --failed_only still account for them."""
+    msg = f"GPU {rank} 工作进程异常退出 (exit code {exitcode})"
+    logs = [{"dataset": dataset_name, "sample_id": sid, "sample_prefix": f"{dataset_name}_{sid}_{shot_number}shot",
+             "category": None, "shot_number": shot_number, "status": "error", "error": msg, "outpainted_images": [],
+             "process_time_seconds": 0} for sid in sample_ids]
+    res = formatted_result_json(dataset_name, logs, shot_number, process_id)
+    res["gpu_process_id"] = f"{process_id}_gpu{rank}"
+    return res
+
+
+def collect_worker_results(procs: Dict[int, object], q, poll_seconds: float = 1.0) -> Dict[int, Optional[dict]]:
+    """Drain one (rank, result) per worker from `q` while watching the workers: a rank whose process has exited without
+    reporting maps to None instead of blocking the parent forever. `procs`: rank -> object with is_alive() / exitcode."""
+    import queue as _queue
+    results: Dict[int, Optional[dict]] = {}
+    pending = set(procs)
+    while pending:
+        try:
+            rank, res = q.get(timeout=poll_seconds)
+            results[rank] = res
+            pending.discard(rank)
+            continue
+        except _queue.Empty:
+            pass
+        for r in list(pending):
+            if not procs[r].is_alive():
+                try:                                   # its result may have landed between the timeout and this check
+                    while True:
+                        rank, res = q.get(timeout=0.2)
+                        results[rank] = res
+                        pending.discard(rank)
+                except _queue.Empty:
+                    pass
+                if r in pending:
+                    print(f"错误：GPU {r} 的工作进程已退出 (exit code {procs[r].exitcode})，未返回结果")
+                    results[r] = None
+                    pending.discard(r)
+    return results
+
+
 def process_dataset_samples_multi_gpu(dataset_name, sample_ids, shot_number, num_gpus, process_id, kwargs, load_kwargs):
     import torch.multiprocessing as mp
     lists = H.split_samples_for_gpus(sample_ids, num_gpus)
@@ -356,14 +400,16 @@ def process_dataset_samples_multi_gpu(dataset_name, sample_ids, shot_number, num
         print(f"GPU {i}: {len(s)} 个样本")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, lists, dataset_name, shot_number, process_id, kwargs, load_kwargs, q))
-             for r in range(num_gpus) if lists[r]]
-    for p in procs:
+    procs = {r: ctx.Process(target=_worker, args=(r, lists, dataset_name, shot_number, process_id, kwargs, load_kwargs, q))
+             for r in range(num_gpus) if lists[r]}
+    for p in procs.values():
         p.start()
-    results = dict(q.get() for _ in procs)
-    for p in procs:
+    results = collect_worker_results(procs, q)
+    for p in procs.values():
         p.join()
-    return merge_gpu_results(dataset_name, [results[r] for r in sorted(results)], shot_number, process_id)
+    jsons = [results[r] if results[r] is not None else
+             _dead_rank_result(dataset_name, lists[r], shot_number, process_id, r, procs[r].exitcode) for r in sorted(results)]
+    return merge_gpu_results(dataset_name, jsons, shot_number, process_id)
 
 
 def build_parser() -> argparse.ArgumentParser:
@@ -387,6 +433,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--model_size", type=str, default="full", choices=["full", "tiny"])
     p.add_argument("--num_inference_steps", type=int, default=50)
     p.add_argument("--seed", type=int, default=None, help="fixed seed instead of a random one per composition")
+    p.add_argument("--allow_random_init", action="store_true",
+                   help="dry run without checkpoints: seeded random-init models and synthetic text tokens (noise images); "
+                        "without it a missing weight file is an error")
     p.add_argument("--compose_batch", type=int, default=4,
                    help="backgrounds of one sample composed per FluxFillPipeline call (same image and mask; 1 = the "
                         "reference's one-at-a-time loop; seeds stay per composition either way)")
@@ -415,9 +464,13 @@ def main(argv=None) -> int:
         done, failed = parse_resume_log(args.log_file)
     n_gpus = args.num_gpus or (torch.cuda.device_count() if args.multi_gpu else 1)
     load_kwargs = dict(weights_dir=args.weights_dir, size=args.model_size, max_side=H.MAX_DIMENSION,
-                       max_batch=max(1, args.compose_batch))
-    seed_fn = (lambda: args.seed) if args.seed is not None else None
-    kwargs = dict(upscale_override=upscale_override, num_inference_steps=args.num_inference_steps, seed_fn=seed_fn,
+                       max_batch=max(1, args.compose_batch), allow_random_init=args.allow_random_init)
+    from .models import missing_files
+    lacking = missing_files(args.weights_dir, ("fill",))
+    if lacking and not args.allow_random_init:
+        print(f"错误：权重目录 {args.weights_dir} 缺少 {lacking}；如只做流程测试请显式传入 --allow_random_init")
+        return 2
+    kwargs = dict(upscale_override=upscale_override, num_inference_steps=args.num_inference_steps, seed=args.seed,
                   compose_batch=max(1, args.compose_batch))
     pipes = None
     for ds in datasets:
@@ -430,9 +483,7 @@ def main(argv=None) -> int:
             print(f"警告：数据集 {ds} 没有找到任何样本")
             continue
         if args.multi_gpu and n_gpus > 1:
-            kw = dict(kwargs)
-            kw.pop("seed_fn")                # lambdas do not cross the spawn boundary; workers draw their own seeds
-            res = process_dataset_samples_multi_gpu(ds, ids, args.shot, n_gpus, process_id, kw, load_kwargs)
+            res = process_dataset_samples_multi_gpu(ds, ids, args.shot, n_gpus, process_id, kwargs, load_kwargs)
         else:
             if pipes is None:
                 from .models import load_model

@@ -219,6 +219,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--gen_batch", type=int, default=4,
                    help="generations of one sample (its top-ranked reference images) per FluxPipeline call; 1 = the "
                         "reference's one-at-a-time loop (every generation keeps seed 0 either way)")
+    p.add_argument("--allow_random_init", action="store_true",
+                   help="dry run without checkpoints: seeded random-init models and synthetic text tokens (noise images); "
+                        "without it a missing weight file is an error")
     p.add_argument("--rank", type=int, default=None, help="data-parallel rank (default: RANK env or 0)")
     p.add_argument("--world_size", type=int, default=None, help="data-parallel world size (default: WORLD_SIZE env or 1)")
     return p
@@ -238,8 +241,13 @@ def main(argv=None) -> int:
     rank = args.rank if args.rank is not None else int(os.environ.get("RANK", "0"))
     world = args.world_size if args.world_size is not None else int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
-    pipes = load_model(device=f"cuda:{local}", want=("dev",), weights_dir=args.weights_dir, size=args.model_size,
-                       max_side=args.image_size, max_batch=max(1, args.gen_batch))
+    try:
+        pipes = load_model(device=f"cuda:{local}", want=("dev",), weights_dir=args.weights_dir, size=args.model_size,
+                           max_side=args.image_size, max_batch=max(1, args.gen_batch),
+                           allow_random_init=args.allow_random_init)
+    except FileNotFoundError as e:
+        print(f"错误：{e}")
+        return 2
     for ds in datasets:
         for k in shots:
             results = load_retrieval_results(args.retrieval_results_dir, ds, k)

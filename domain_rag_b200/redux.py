@@ -12,9 +12,11 @@ the two-image generation call is 2 x CLIP("")). The output object works as `**kw
 
 The image half runs on the sm_100a kernels (siglip.py). The text half is a per-prompt CONSTANT (the reference only
 ever passes "" or one fixed sentence per dataset): it is looked up in a `TextEmbeddingTable` that is filled once per
-process - from a file of precomputed T5 / CLIP-text outputs, from caller-provided encoder callables (e.g.
-transformers T5EncoderModel / CLIPTextModel, library code off the hot path), or, with no checkpoints offline, from a
-seeded synthetic generator. SURVEY 8f N2: "T5("")/CLIP("") computed once per process".
+process - from a file of precomputed T5 / CLIP-text outputs (scripts/make_text_embeds.py writes it from the real
+encoders when their checkpoints are present), or from caller-provided encoder callables (e.g. transformers
+T5EncoderModel / CLIPTextModel, library code off the hot path). A prompt that is in neither raises KeyError; only a table
+built with allow_synthetic=True (tests, benches, --allow_random_init dry runs) substitutes seeded synthetic tokens.
+SURVEY 8f N2: "T5("")/CLIP("") computed once per process".
 """
 from __future__ import annotations
 
@@ -44,8 +46,9 @@ class TextEmbeddingTable:
 
     def __init__(self, device="cuda", t5_encode: Optional[Callable[[str], torch.Tensor]] = None,
                  clip_encode: Optional[Callable[[str], torch.Tensor]] = None, txt_dim: int = T5_DIM,
-                 pooled_dim: int = POOLED_DIM, tokens: int = T5_TOKENS):
+                 pooled_dim: int = POOLED_DIM, tokens: int = T5_TOKENS, allow_synthetic: bool = False):
         self.device = torch.device(device)
+        self.allow_synthetic = allow_synthetic
         self.t5_encode, self.clip_encode = t5_encode, clip_encode
         self.txt_dim, self.pooled_dim, self.tokens = txt_dim, pooled_dim, tokens
         self._table: Dict[Tuple[str, str], Tuple[torch.Tensor, torch.Tensor]] = {}
@@ -71,8 +74,12 @@ class TextEmbeddingTable:
                 t5 = self.t5_encode(key[1]).to(self.device, torch.bfloat16).reshape(self.tokens, self.txt_dim)
                 pooled = self.clip_encode(key[0]).to(self.device, torch.bfloat16).reshape(self.pooled_dim)
                 self._table[key] = (t5, pooled)
-            else:
+            elif self.allow_synthetic:
                 self._table[key] = self._synthetic(key)
+            else:
+                raise KeyError(f"no text embeddings for prompt pair {key!r}: the table holds {sorted(self._table)} and no "
+                               "T5 / CLIP-text encoders were supplied. Precompute them with scripts/make_text_embeds.py "
+                               "(-> <weights_dir>/text_embeds.pt) or run with --allow_random_init for a synthetic dry run")
         return self._table[key]
 
 

@@ -20,8 +20,21 @@ from .index import IndexFlatIP
 _INDEX_CACHE: dict = {}
 # path -> 128-d style vector of corpus images already seen: the reference recomputes the statistics of all
 # 100 candidates for every query (:468-470) although popular corpus images recur across queries.
-_STYLE_CACHE: Dict[str, np.ndarray] = {}
+# The cache lives on the encoder object (a style vector is only valid for the stem weights that produced it).
 _STYLE_CACHE_MAX = 200_000
+
+
+def _style_cache(resnet_model) -> Dict[str, np.ndarray]:
+    cache = getattr(resnet_model, "_style_cache", None)
+    if cache is None:
+        cache = {}
+        try:
+            resnet_model._style_cache = cache
+        except AttributeError:      # foreign encoder objects without a __dict__: no caching
+            pass
+    if len(cache) > _STYLE_CACHE_MAX:
+        cache.clear()
+    return cache
 
 
 def clean_image_path(path):
@@ -38,7 +51,13 @@ def clean_image_path(path):
 
 def _cached_index(dataset_features: Dict[str, np.ndarray], d: int, device: int) -> IndexFlatIP:
     """One resident index per (set of feature arrays); the reference re-adds N*d floats per query."""
-    key = (device, d) + tuple((name, id(f), len(f)) for name, f in dataset_features.items()
+    # content fingerprint (17 sampled rows), not id(): a recomputed feature array may reuse a freed array's address
+    def fingerprint(f):
+        a = np.asarray(f)
+        rows = a[:: max(1, len(a) // 16)][:17]
+        return hash((a.shape, str(a.dtype), np.ascontiguousarray(rows).tobytes()))
+
+    key = (device, d) + tuple((name, fingerprint(f)) for name, f in dataset_features.items()
                               if f is not None and len(f) > 0)
     ix = _INDEX_CACHE.get(key)
     if ix is None:
@@ -147,14 +166,13 @@ def resnet_second_stage_rerank(query_image_path, first_stage_results, resnet_mod
     the candidates not yet in the style cache."""
     query_image_path = clean_image_path(query_image_path)
     cand_paths = [clean_image_path(r["image_path"]) for r in first_stage_results]
-    if len(_STYLE_CACHE) > _STYLE_CACHE_MAX:
-        _STYLE_CACHE.clear()
-    todo = [query_image_path] + [p for p in dict.fromkeys(cand_paths) if p not in _STYLE_CACHE]
+    cache = _style_cache(resnet_model)
+    todo = [query_image_path] + [p for p in dict.fromkeys(cand_paths) if p not in cache]
     feats = compute_resnet_features_batch(todo, resnet_model, device)
     if feats[0] is None:
         print(f"警告：无法计算查询图像的ResNet特征: {query_image_path}")
         return first_stage_results
     for p, f in zip(todo[1:], feats[1:]):
         if f is not None:
-            _STYLE_CACHE[p] = f
-    return rerank_by_style(feats[0], [_STYLE_CACHE.get(p) for p in cand_paths], first_stage_results)
+            cache[p] = f
+    return rerank_by_style(feats[0], [cache.get(p) for p in cand_paths], first_stage_results)

@@ -31,6 +31,41 @@ from . import retrieval as R
 RESULTS_DIR = "./retrieval_results"
 LAMAINPAINT_DIR = "../lamainpaint"
 
+# Tag of the encoder weights the feature caches of this run are computed with ("<model>:<sha1 of the weights file>" or
+# "<model>:random-init"). Written next to every cache this driver creates (<cache>.meta.json); a cache whose tag differs is
+# recomputed instead of reused, so features from a random-init dry run can never leak into a run with real weights.
+# Caches without a sidecar (written by the reference itself) are trusted as they are.
+_WEIGHTS_TAG = {"clip": None}
+
+
+def _file_sha1(path: str) -> str:
+    import hashlib
+    h = hashlib.sha1()
+    with open(path, "rb") as f:
+        for chunk in iter(lambda: f.read(1 << 22), b""):
+            h.update(chunk)
+    return h.hexdigest()[:16]
+
+
+def _write_cache_tag(cache_file: str) -> None:
+    with open(cache_file + ".meta.json", "w") as f:
+        json.dump({"clip_weights": _WEIGHTS_TAG["clip"]}, f)
+
+
+def _cache_tag_ok(cache_file: str) -> bool:
+    meta = cache_file + ".meta.json"
+    if not os.path.exists(meta):
+        return True
+    try:
+        with open(meta, "r") as f:
+            tag = json.load(f).get("clip_weights")
+    except Exception:
+        return False
+    if tag != _WEIGHTS_TAG["clip"]:
+        print(f"缓存 {cache_file} 由不同的CLIP权重生成 ({tag} != {_WEIGHTS_TAG['clip']})，将重新计算")
+        return False
+    return True
+
 
 # ------------------------------------------------------------------------------------ query side
 def get_inpainted_images(dataset_name: str, shot_count: int, lamainpaint_dir: Optional[str] = None):
@@ -171,7 +206,7 @@ def load_or_compute_corpus_features(kind: str, args, device, model, preprocess, 
             except Exception as e:
                 print(f"加载预提取特征时出错: {e}")
                 feats, paths = None, None
-        if feats is None and os.path.exists(feat_file) and os.path.exists(path_file):
+        if feats is None and os.path.exists(feat_file) and os.path.exists(path_file) and _cache_tag_ok(feat_file):
             try:
                 feats = np.load(feat_file)
                 with open(path_file, "r") as f:
@@ -193,6 +228,7 @@ def load_or_compute_corpus_features(kind: str, args, device, model, preprocess, 
             np.save(feat_file, feats)           # fp32 (the reference saves fp16 when computed on CUDA, then casts)
             with open(path_file, "w") as f:
                 json.dump(paths, f)
+            _write_cache_tag(feat_file)
     if feats is None or len(feats) == 0:
         print(f"警告：没有{kind}特征")
         return None, None
@@ -241,7 +277,7 @@ def retrieve_by_category_multi_source(dataset_name, shot_count, clip_model, clip
     feat_file = os.path.join(results_dir, f"{dataset_name}_{shot_count}_shot_inpainted_clip_features.npy")
     path_file = os.path.join(results_dir, f"{dataset_name}_{shot_count}_shot_inpainted_image_paths.json")
     q_feats, q_paths = None, None
-    if not force_recompute_inpainted and os.path.exists(feat_file) and os.path.exists(path_file):
+    if not force_recompute_inpainted and os.path.exists(feat_file) and os.path.exists(path_file) and _cache_tag_ok(feat_file):
         try:
             q_feats = np.load(feat_file)
             with open(path_file, "r") as f:
@@ -256,6 +292,7 @@ def retrieve_by_category_multi_source(dataset_name, shot_count, clip_model, clip
             np.save(feat_file, q_feats)
             with open(path_file, "w") as f:
                 json.dump(q_paths, f)
+            _write_cache_tag(feat_file)
     q_by_path = {p: q_feats[i] for i, p in enumerate(q_paths)}
 
     all_results: Dict[str, list] = {}
@@ -322,7 +359,15 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--force-recompute-inpainted", action="store_true")
     # additions (absent from the reference; defaults keep its behaviour)
     p.add_argument("--clip-model", type=str, default="ViT-B/32", help="ViT-B/32 (reference) or ViT-L/14")
-    p.add_argument("--clip-weights", type=str, default=None, help="OpenAI-format state dict (.pt, weights_only)")
+    p.add_argument("--clip-weights", type=str, default=None,
+                   help="OpenAI-format CLIP state dict (.pt, read with weights_only=True; `visual.*` keys) - what clip.load "
+                        "downloads in the reference (:209). Required unless --allow-random-init")
+    p.add_argument("--resnet-weights", type=str, default=None,
+                   help="torchvision ResNet-50 state dict (.pt, weights_only=True; only conv1.weight and bn1.* are read) - "
+                        "what resnet50(pretrained=True) downloads in the reference (:54). Required unless --allow-random-init")
+    p.add_argument("--allow-random-init", action="store_true",
+                   help="dry runs / CI without checkpoints: seeded random-init encoders. The feature caches written by such "
+                        "a run are tagged and never reused by a run with real weights")
     p.add_argument("--no-visual", action="store_true", help="skip the *_visual.jpg contact sheets")
     return p
 
@@ -342,13 +387,33 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     device = torch.device(f"cuda:{args.gpu_id}")
     torch.cuda.set_device(device)
     print(f"使用设备: {device}")
+    missing = [flag for flag, v in (("--clip-weights", args.clip_weights), ("--resnet-weights", args.resnet_weights)) if not v]
+    if missing and not args.allow_random_init:
+        print(f"错误：缺少权重文件参数 {' '.join(missing)}；参考实现在此处下载预训练的CLIP / ResNet-50权重。"
+              "如只需用随机初始化的编码器做流程测试，请显式传入 --allow-random-init")
+        return 2
     state = None
     if args.clip_weights:
         state = torch.load(args.clip_weights, map_location="cpu", weights_only=True)
+        _WEIGHTS_TAG["clip"] = f"{args.clip_model}:{_file_sha1(args.clip_weights)}"
+        print(f"成功加载CLIP模型 {args.clip_model}")
+    else:
+        _WEIGHTS_TAG["clip"] = f"{args.clip_model}:random-init"
+        print(f"警告：CLIP模型 {args.clip_model} 使用随机初始化权重 (--allow-random-init)，检索结果没有语义意义")
     clip_model, clip_preprocess = clip.load(args.clip_model, device=device, state_dict=state)
-    print(f"成功加载CLIP模型 {args.clip_model}")
-    resnet_model = ResNetEncoder().to(device).eval()
-    print("成功加载ResNet特征提取器")
+    stem_state = None
+    if args.resnet_weights:
+        sd = torch.load(args.resnet_weights, map_location="cpu", weights_only=True)
+        need = ("conv1.weight", "bn1.weight", "bn1.bias", "bn1.running_mean", "bn1.running_var")
+        lacking = [k for k in need if k not in sd]
+        if lacking:
+            print(f"错误：{args.resnet_weights} 缺少ResNet-50 stem参数: {lacking}")
+            return 2
+        stem_state = {k: sd[k].float() for k in need}
+        print("成功加载ResNet特征提取器")
+    else:
+        print("警告：ResNet特征提取器使用随机初始化权重 (--allow-random-init)，风格重排序没有语义意义")
+    resnet_model = ResNetEncoder(stem_state).to(device).eval()
 
     dataset_features, dataset_paths = {}, {}
     for kind in ("coco", "mini-imagenet"):

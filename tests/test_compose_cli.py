@@ -170,3 +170,94 @@ def test_compose_cli_file_surface(tmp_path):
     bad = CC.process_sample_hires("DIOR", "nope", pipes, "PID", shot_number=5, datasets_dir=str(tmp_path / "datasets"),
                                   result_dir=str(tmp_path / "result"), outpaint_base=str(tmp_path / "outpaint_hires"))
     assert bad["status"] == "error" and bad["error"]
+
+
+# ------------------------------------------------------------------ round-2 host logic: loud failures, seeds, dead workers
+def test_load_model_refuses_missing_weights(tmp_path):
+    """A missing weight file is an error naming the files (no silent noise models); the CLIs return 2 before touching a GPU."""
+    from domain_rag_b200 import models as M
+    assert M.missing_files(str(tmp_path), ("fill",)) == ["siglip.pt", "redux.pt", "text_embeds.pt", "vae.pt", "flux_fill.pt"]
+    (tmp_path / "vae.safetensors").write_bytes(b"")
+    (tmp_path / "siglip.pt").write_bytes(b"")
+    assert M.missing_files(str(tmp_path), ("dev", "fill")) == ["redux.pt", "text_embeds.pt", "flux_dev.pt", "flux_fill.pt"]
+    with pytest.raises(FileNotFoundError, match="flux_fill.pt"):
+        M.load_model(device="cpu", want=("fill",), weights_dir=str(tmp_path))
+    assert CC.main(["--dataset", "DIOR", "--shot", "5", "--weights_dir", str(tmp_path)]) == 2
+    assert GC.main(["--dataset", "DIOR", "--shots", "5", "--weights_dir", str(tmp_path)]) == 2
+
+
+def test_text_table_is_strict_unless_synthetic_is_allowed():
+    import torch
+    from domain_rag_b200 import redux as R
+    t = R.TextEmbeddingTable("cpu", txt_dim=8, pooled_dim=4, tokens=3)
+    with pytest.raises(KeyError, match="make_text_embeds"):
+        t.lookup("", "")
+    t2 = R.TextEmbeddingTable("cpu", txt_dim=8, pooled_dim=4, tokens=3, allow_synthetic=True)
+    a, b = t2.lookup("", ""), t2.lookup("", None)
+    assert a[0].shape == (3, 8) and a[1].shape == (4,) and torch.equal(a[0], b[0])
+    t3 = R.TextEmbeddingTable("cpu", txt_dim=8, pooled_dim=4, tokens=3, t5_encode=lambda s: torch.full((3, 8), float(len(s))),
+                              clip_encode=lambda s: torch.full((4,), float(len(s))))
+    e = t3.lookup("ab", "abcd")      # diffusers: prompt -> CLIP (pooled), prompt_2 -> T5
+    assert float(e[0][0, 0]) == 4.0 and float(e[1][0]) == 2.0
+
+
+def test_multi_gpu_seed_crosses_the_spawn_boundary(tmp_path, monkeypatch):
+    """--seed reaches the per-GPU workers as a plain int (it used to be dropped with the lambda)."""
+    seen = {}
+
+    def fake_multi(ds, ids, shot, n_gpus, process_id, kwargs, load_kwargs):
+        import pickle
+        pickle.dumps(kwargs)                      # must survive mp spawn
+        seen.update(kwargs=kwargs, load_kwargs=load_kwargs, n=n_gpus)
+        return CC.formatted_result_json(ds, [], shot, process_id)
+
+    monkeypatch.setattr(CC, "process_dataset_samples_multi_gpu", fake_multi)
+    monkeypatch.chdir(tmp_path)
+    assert CC.main(["--dataset", "DIOR", "--shot", "5", "--sample_id", "s1", "--multi_gpu", "--num_gpus", "2", "--seed", "77",
+                    "--allow_random_init", "--model_size", "tiny"]) == 0
+    assert seen["kwargs"]["seed"] == 77 and seen["n"] == 2 and seen["load_kwargs"]["allow_random_init"] is True
+
+
+def test_dead_worker_does_not_block_the_parent():
+    import multiprocessing as mp
+    import time
+
+    class P:
+        def __init__(self, alive, code=None):
+            self.alive, self.exitcode = alive, code
+
+        def is_alive(self):
+            return self.alive
+
+    q = mp.Queue()
+    q.put((0, {"samples": [{"status": "completed"}], "gpu_process_id": "p_gpu0"}))
+    procs = {0: P(True), 1: P(False, -9)}
+    t0 = time.time()
+    res = CC.collect_worker_results(procs, q, poll_seconds=0.1)
+    assert time.time() - t0 < 5 and res[0]["gpu_process_id"] == "p_gpu0" and res[1] is None
+    dead = CC._dead_rank_result("DIOR", ["a", "b"], 5, "p", 1, -9)
+    merged = CC.merge_gpu_results("DIOR", [res[0], dead], 5, "p")
+    assert merged["total_samples"] == 3 and merged["failed_samples"] == 2 and merged["num_gpus"] == 2
+    assert all("exit code -9" in s["error"] for s in merged["samples"] if s["status"] == "error")
+
+
+def test_text_embeds_script_prompts_and_table_roundtrip(tmp_path):
+    """scripts/make_text_embeds.py encodes exactly the prompt pairs the two scripts ever pass; its file layout is what
+    TextEmbeddingTable.load_file reads; without encoder checkpoints it refuses (no synthetic fallback)."""
+    import importlib.util
+    import torch
+    from domain_rag_b200 import redux as R
+    spec = importlib.util.spec_from_file_location("mte", str(CC.__file__).replace("domain_rag_b200/compose_cli.py",
+                                                                                 "scripts/make_text_embeds.py"))
+    mte = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mte)
+    pairs = mte.prompt_pairs(["x"])
+    assert pairs == [("", ""), (H.FISH_PROMPT, ""), ("x", "x")]
+    assert mte.main(["--flux_dir", str(tmp_path / "nope"), "--out", str(tmp_path / "t.pt")]) == 2
+    torch.save({"prompts": [list(p) for p in pairs], "t5": torch.randn(3, 5, 8).bfloat16(),
+                "pooled": torch.randn(3, 4).bfloat16()}, tmp_path / "t.pt")
+    t = R.TextEmbeddingTable("cpu", txt_dim=8, pooled_dim=4, tokens=5)
+    t.load_file(str(tmp_path / "t.pt"))
+    assert t.lookup(H.FISH_PROMPT, "")[0].shape == (5, 8) and t.lookup("", None)[1].shape == (4,)
+    with pytest.raises(KeyError):
+        t.lookup("something else", "")

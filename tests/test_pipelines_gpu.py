@@ -38,7 +38,7 @@ def test_redux_prior_matches_oracle(lib):
     cfgd = dict(hidden=160, layers=2, heads=2, mlp=272, patch=14, image=60)
     st = bf(OS.init_state(OS.SiglipConfig(**cfgd), seed=6000))
     rd = bf(OS.init_redux(seed=6100, d_in=160, d_hidden=192, d_out=64))
-    table = R.TextEmbeddingTable(txt_dim=64, pooled_dim=32, tokens=24)
+    table = R.TextEmbeddingTable(txt_dim=64, pooled_dim=32, tokens=24, allow_synthetic=True)
     pipe = R.FluxPriorReduxPipeline(S.SiglipVisionTower(S.SiglipConfig(**cfgd), st), S.ReduxImageEncoder(rd), table)
     imgs = [synth_image(1, 80, 120), synth_image(2, 64, 64)]
     out = pipe(imgs, prompt=["", "a b"], prompt_2=["", "a b"], prompt_embeds_scale=[0.8, 1.0], pooled_prompt_embeds_scale=[1.0, 1.0])

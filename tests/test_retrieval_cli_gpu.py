@@ -20,10 +20,14 @@ def test_end_to_end_tree(lib, tmp_path):
     shot = make_tree(tmp_path, n_coco=40)
     json.dump({"a1": "beetle"}, open(shot / "category_mapping.json", "w"))
     out = tmp_path / "res"
-    rc = RC.main(["--datasets", "DS", "MISSING", "--shots", "1", "5", "--coco-dir", str(tmp_path / "coco"),
-                  "--lamainpaint-dir", str(tmp_path / "lamainpaint"), "--output-dir", str(out),
-                  "--pretrained-coco-features", str(tmp_path / "none.pt"), "--clip-top-k", "10"])
+    base = ["--coco-dir", str(tmp_path / "coco"), "--lamainpaint-dir", str(tmp_path / "lamainpaint"), "--output-dir", str(out),
+            "--pretrained-coco-features", str(tmp_path / "none.pt"), "--clip-top-k", "10"]
+    # no checkpoints and no explicit opt-in: refuse (the reference downloads pretrained CLIP / ResNet-50 here)
+    assert RC.main(["--datasets", "DS", "--shots", "1", *base]) == 2
+    assert not (out / "coco_clip_features.npy").exists()
+    rc = RC.main(["--datasets", "DS", "MISSING", "--shots", "1", "5", *base, "--allow-random-init"])
     assert rc == 0
+    assert json.load(open(out / "coco_clip_features.npy.meta.json")) == {"clip_weights": "ViT-B/32:random-init"}
     # file surface
     names = set(os.listdir(out))
     assert {"coco_clip_features.npy", "coco_image_paths.json", "DS_1_shot_inpainted_clip_features.npy",
@@ -64,7 +68,21 @@ def test_end_to_end_tree(lib, tmp_path):
 
     # second run is served from the caches and reproduces the same results bit for bit
     before = open(out / "DS_1_shot_retrieval_results.json").read()
-    assert RC.main(["--datasets", "DS", "--shots", "1", "--coco-dir", str(tmp_path / "coco"), "--lamainpaint-dir",
-                    str(tmp_path / "lamainpaint"), "--output-dir", str(out), "--pretrained-coco-features",
-                    str(tmp_path / "none.pt"), "--clip-top-k", "10", "--no-visual"]) == 0
+    assert RC.main(["--datasets", "DS", "--shots", "1", *base, "--no-visual", "--allow-random-init"]) == 0
     assert open(out / "DS_1_shot_retrieval_results.json").read() == before
+
+    # a run with weight FILES (here: differently seeded stand-ins in the OpenAI / torchvision key layouts) must not reuse
+    # the random-init caches: tags differ -> features recomputed, stem weights taken from the file
+    from domain_rag_b200 import clip
+    torch.save(clip.random_state(clip.CONFIGS["ViT-B/32"], seed=7), tmp_path / "clip.pt")
+    torch.save({**random_stem_state(9), "fc.weight": torch.zeros(3, 3)}, tmp_path / "resnet50.pt")
+    assert RC.main(["--datasets", "DS", "--shots", "1", *base, "--no-visual", "--clip-weights", str(tmp_path / "clip.pt"),
+                    "--resnet-weights", str(tmp_path / "resnet50.pt")]) == 0
+    tag = json.load(open(out / "coco_clip_features.npy.meta.json"))["clip_weights"]
+    assert tag.startswith("ViT-B/32:") and not tag.endswith("random-init")
+    X2 = np.load(out / "coco_clip_features.npy")
+    assert X2.shape == X.shape and np.abs(X2 - X).max() > 1e-2
+    assert open(out / "DS_1_shot_retrieval_results.json").read() != before
+    torch.save({"conv1.weight": torch.zeros(64, 3, 7, 7)}, tmp_path / "bad.pt")
+    assert RC.main(["--datasets", "DS", "--shots", "1", *base, "--clip-weights", str(tmp_path / "clip.pt"),
+                    "--resnet-weights", str(tmp_path / "bad.pt")]) == 2
