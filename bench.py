@@ -1,235 +1,64 @@
 #!/usr/bin/env python
 """bench.py - the driver's measurement contract for the Domain-RAG retrieve-then-compose hot path.
 
-    python bench.py --gpus N --steps K --warmup W [--workload compose|scan] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload compose|c3|scan|retrieve] [--impl reference]
 
-Prints ONE JSON line on rank 0. Workloads:
-  compose  (default once built) composed 1024^2 images/sec, 50 Flux-Redux steps per image.
-  scan     corpus cosine-top-k: 1M x 512 fp32 embeddings per GPU, top-100, achieved HBM GB/s.
-  retrieve BASELINE config C2: 10k-image corpus -> CLIP ViT-L/14 embed -> resident index -> top-100 -> style re-rank.
-`--impl reference` times the CPU oracle (the reference's algorithm; its own third-party packages are
-not installable offline) on the host cores for the same metric/config.
+Prints ONE JSON line on rank 0. Workloads (each module's docstring has the details):
+  compose  (default) BASELINE metric: composed 1024^2 images/sec, 50 Flux-Redux steps per image (C4 per-GPU slice, batch 4).
+           The line also carries `gpu_baseline` (the oracle modules in bf16 torch-eager on the same B200 = the reference's
+           torch path), `cpu_baseline` (N = 1) and `secondary` = the second half of the metric and the other configs measured
+           in the same run: C5 scan GB/s vs HBM peak, C2 retrieve images/s, C3 seconds per batch.  [bench_compose.py]
+  c3       BASELINE config C3: Flux-Redux outpainting 512^2, 20 steps, batch 8.                      [bench_compose.py]
+  scan     C5: corpus cosine-top-k, 1M x 512 fp32 rows per GPU, top-100, achieved HBM GB/s; `--sweep` = the whole
+           N x D x nq grid. At N > 1 every search is verified against a replicated single index.     [bench_scan.py]
+  retrieve C2: 10k-image corpus -> CLIP ViT-L/14 embed -> resident index -> top-100 -> style re-rank. [bench_retrieve.py]
+`--impl reference` times the CPU oracle (the reference's algorithm; its own third-party packages are not installable
+offline) on the host cores for the same metric/config.
 """
 from __future__ import annotations
 
 import argparse
 import json
-import os
 import sys
-import time
 from pathlib import Path
 
 REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
 
-
-from domain_rag_b200.benchutil import (ClockSampler, barrier, dist_setup, max_over_ranks,  # noqa: E402
-                                       measured_peaks)
+DEFAULT_STEPS = {"scan": 20, "retrieve": 3, "c3": 3, "compose": 4}
 
 
-# ------------------------------------------------------------------------------------ scan workload
-SCAN_N, SCAN_D, SCAN_K, SCAN_NQ = 1_000_000, 512, 100, 1
-
-
-def scan_algorithmic_bytes(n, d, nq, k):
-    return n * d * 4 + nq * d * 4 + nq * k * 12
-
-
-def scan_traffic_from_profile():
-    """dram read+write bytes per launch of the scan kernel from the committed ncu --set full capture."""
-    p = REPO / "profiles" / "r01_scan_traffic.json"
-    try:
-        return json.loads(p.read_text())["traffic_bytes_per_launch"]
-    except Exception:
-        return None
-
-
-def make_corpus_device(n, d, seed, device):
-    import torch
-    g = torch.Generator(device=device).manual_seed(seed)
-    x = torch.randn(n, d, generator=g, device=device)
-    x /= x.norm(dim=1, keepdim=True)
-    return x
-
-
-def run_scan(args):
-    import numpy as np
-    import torch
-
-    from domain_rag_b200.index import ShardedIndexFlatIP
-
-    rank, world, local = dist_setup(args.gpus)
-    dev = torch.device("cuda", local)
-    n, d, k, nq = SCAN_N, SCAN_D, SCAN_K, SCAN_NQ
-    # weak scaling: every rank owns n rows of an (n * world)-row corpus; ids offset by rank * n
-    x = make_corpus_device(n, d, 4006 + rank, dev)
-    six = ShardedIndexFlatIP(d, rank, world, device=local)
-    six.add_local(x, lo=rank * n, ntotal_global=n * world)
-    ix = six._index
-    ix.set_timing(True)
-    gq = torch.Generator().manual_seed(4999)
-    q_host = torch.randn(nq, d, generator=gq)
-    q_host = (q_host / q_host.norm(dim=1, keepdim=True)).pin_memory()
-    q_dev = q_host.to(dev)
-
-    def step_device():
-        return six.search(q_dev, k)
-
-    for _ in range(args.warmup):
-        step_device()
-    barrier(world)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    scan_ms = []
-    barrier(world)
-    from domain_rag_b200 import _lib
-    _lib.launch_count(reset=True)
-    e0.record()
-    for _ in range(args.steps):
-        step_device()
-        scan_ms.append(None)
-    e1.record()
-    n_launches = _lib.launch_count()
-    barrier(world)
-    total_ms = max_over_ranks(e0.elapsed_time(e1), world)
-    # per-launch duration of the dominant kernel (event bracket inside the library, same stream)
-    kern_ms = []
-    for _ in range(args.steps):
-        step_device()
-        kern_ms.append(ix.last_scan_ms())
-    barrier(world)
-    clocks = sampler.stop() if rank == 0 else {}
-    kern_avg = sum(kern_ms) / len(kern_ms)
-
-    # end to end through the public host-buffer API: H2D of the query, D2H of (D, I) every step
-    def step_e2e():
-        qd = q_host.to(dev, non_blocking=True)
-        D, I = six.search(qd, k)
-        return D.cpu(), I.cpu()
-
-    for _ in range(args.warmup):
-        step_e2e()
-    barrier(world)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        Dh, Ih = step_e2e()
-    barrier(world)
-    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
-
-    ms_per_step = total_ms / args.steps
-    alg = scan_algorithmic_bytes(n, d, nq, k)
-    value = alg * world / (ms_per_step * 1e-3) / 1e9
-    e2e_value = alg * world / (e2e_s / args.steps) / 1e9
-    peaks = measured_peaks()
-    out = None
-    if rank == 0:
-        geo = ix.last_launch()
-        out = {
-            "metric": "corpus cosine-top-k scan throughput (algorithmic bytes / device time)",
-            "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C5 scan: {n} x {d} fp32 embeddings per GPU, nq={nq}, top-{k}; "
-                                   f"index row-sharded, all-gather of per-shard top-k",
-                       "l2_policy": "inputs larger than L2 (2.05 GB per GPU vs 126 MB)",
-                       "grid": geo["grid"], "ring_stages": geo["stages"], "rows_per_stage": geo["rows_per_stage"]},
-            "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": nq * d * 4,
-                    "d2h_bytes_per_step": nq * k * 12},
-            "gpu_launches": int(n_launches),
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": round(alg / (kern_avg * 1e-3) / 1e9, 1),
-                         "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": round(alg / (kern_avg * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
-                         "traffic": scan_traffic_from_profile(), "kernel": "ip_scan_topk_kernel<4>", "kernel_ms": round(kern_avg, 4),
-                         "peak_source": peaks["source"]},
-        }
-        if world == 1:
-            out["cpu_baseline"] = scan_cpu_baseline(d, nq, k)
-    return out
-
-
-def scan_cpu_baseline(d, nq, k, n_sample=200_000, min_seconds=2.0):
-    """The oracle (numpy fp64-accumulate scan + top-k) on a bounded sample of the same workload."""
-    import numpy as np
-
-    from oracle import ip_topk as O
-    g = np.random.default_rng(1)
-    x = g.standard_normal((n_sample, d), dtype=np.float32)
-    x /= np.linalg.norm(x, axis=1, keepdims=True)
-    q = g.standard_normal((nq, d), dtype=np.float32)
-    O.ip_topk(x[:1000], q, k)
-    t0 = time.perf_counter()
-    reps = 0
-    while True:
-        O.ip_topk(x, q, k)
-        reps += 1
-        if time.perf_counter() - t0 > min_seconds:
-            break
-    dt = (time.perf_counter() - t0) / reps
-    return {"value": round(scan_algorithmic_bytes(n_sample, d, nq, k) / dt / 1e9, 3), "unit": "GB/s",
-            "cores": os.cpu_count(), "kind": "port",
-            "sample": f"oracle.ip_topk over {n_sample} x {d} rows ({reps} reps), BLAS threads = all cores"}
-
-
-def run_scan_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return None
-    n, d, k, nq = SCAN_N, SCAN_D, SCAN_K, SCAN_NQ
-    import numpy as np
-
-    from oracle import ip_topk as O
-    n_sample = 200_000
-    g = np.random.default_rng(1)
-    x = g.standard_normal((n_sample, d), dtype=np.float32)
-    x /= np.linalg.norm(x, axis=1, keepdims=True)
-    q = g.standard_normal((nq, d), dtype=np.float32)
-    for _ in range(args.warmup):
-        O.ip_topk(x, q, k)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        O.ip_topk(x, q, k)
-    dt = (time.perf_counter() - t0) / args.steps
-    val = round(scan_algorithmic_bytes(n_sample, d, nq, k) / dt / 1e9, 3)
-    sample = f"each step = oracle.ip_topk over a {n_sample}-row sample of the {n}-row corpus"
-    return {"impl": "reference", "metric": "corpus cosine-top-k scan throughput (algorithmic bytes / device time)",
-            "value": val, "unit": "GB/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C5 scan: {n} x {d} fp32 embeddings per GPU, nq={nq}, top-{k}", "sample": sample},
-            "cpu_baseline": {"value": val, "unit": "GB/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-
-
-# --------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=None, help="default: 4 (compose: 4 x --batch images), 20 (scan)")
+    ap.add_argument("--steps", type=int, default=None, help="default: 4 (compose: 4 x --batch images), 3 (c3, retrieve), 20 (scan)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=["compose", "scan", "retrieve"])
-    ap.add_argument("--scope", default="full", choices=["full", "loop"],
-                    help="compose: full = prior + Fill pipeline + VAE per image; loop = blend + 50 denoising steps only")
-    ap.add_argument("--batch", type=int, default=4,
-                    help="compose: compositions per GPU and step, run as one batch (C4: 32 compositions / 8 GPUs = 4)")
+    ap.add_argument("--workload", default="compose", choices=["compose", "c3", "scan", "retrieve"])
+    ap.add_argument("--batch", type=int, default=None,
+                    help="compose / c3: compositions per GPU and step, run as one batch (default 4 = C4: 32 compositions / "
+                         "8 GPUs; c3: 8)")
+    ap.add_argument("--sweep", action="store_true", help="scan: the whole C5 grid N x D x nq in one line (`sweep` list)")
+    ap.add_argument("--no-secondary", dest="no_secondary", action="store_true",
+                    help="compose: skip the secondary block (scan / C2 / C3 records)")
+    ap.add_argument("--no-gpu-baseline", dest="no_gpu_baseline", action="store_true",
+                    help="compose / c3: skip the torch-eager GPU baseline leg")
     ap.add_argument("--clip-model", dest="clip_model", default=None, choices=["ViT-L/14", "ViT-B/32", "ViT-B/16"],
                     help="retrieve: image tower (default ViT-L/14 = BASELINE config C2; ViT-B/32 = the reference script's default)")
     ap.add_argument("--embed-batch", dest="embed_batch", type=int, default=None, help="retrieve: images per encode_image call (default 500)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    workload = args.workload or default_workload()
     if args.steps is None:
-        args.steps = {"scan": 20, "retrieve": 3}.get(workload, 4)
-    if workload == "retrieve":
-        import bench_retrieve
-        out = bench_retrieve.run_reference(args) if args.impl == "reference" else bench_retrieve.run(args)
-    elif args.impl == "reference":
-        out = run_scan_reference(args) if workload == "scan" else run_compose_reference(args)
+        args.steps = DEFAULT_STEPS[args.workload]
+    if args.workload == "retrieve":
+        import bench_retrieve as W
+        out = W.run_reference(args) if args.impl == "reference" else W.run(args)
+    elif args.workload == "scan":
+        import bench_scan as W
+        out = W.run_reference(args) if args.impl == "reference" else W.run(args)
     else:
-        out = run_scan(args) if workload == "scan" else run_compose(args)
+        import bench_compose as W
+        out = W.run_reference(args, args.workload) if args.impl == "reference" else W.run(args, args.workload)
     if out is not None:
         print(json.dumps(out), flush=True)
     try:
@@ -238,24 +67,6 @@ def main():
             dist.destroy_process_group()
     except Exception:
         pass
-
-
-def default_workload() -> str:
-    try:
-        import domain_rag_b200.flux  # noqa: F401  (compose path present?)
-        return "compose"
-    except ImportError:
-        return "scan"
-
-
-def run_compose(args):
-    from bench_compose import run
-    return run(args)
-
-
-def run_compose_reference(args):
-    from bench_compose import run_reference
-    return run_reference(args)
 
 
 if __name__ == "__main__":

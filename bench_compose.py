@@ -1,11 +1,25 @@
-"""Compose workload of bench.py: composed 1024^2 images/sec at 50 Flux-Redux steps (BASELINE.json metric).
+"""Compose workloads of bench.py.
 
-One "step" of the bench = one composed image on each GPU: Redux prompt blend (512 T5 + 729 Redux
-tokens, reference batch_generate_flux_kshot.py:459-465 / outpainting_updown_sampling_redux.py:1237-1243)
-followed by 50 denoising steps of the FLUX.1-Fill-dev-shaped MMDiT (19 double + 38 single blocks,
-d = 3072, 24 heads, C_in = 384, S = 1241 + 4096 tokens) with the flow-match Euler update, batch 1 per
-GPU like the reference. Random-init weights and synthetic tokens (no checkpoints / encoders offline);
-VAE decode and the SigLIP/T5 encoders are outside the timed region (not built yet).
+  compose (default)  BASELINE metric: composed 1024^2 images/sec at 50 Flux-Redux steps - the C4 per-GPU slice (4 full
+                     compositions per step and GPU as one batch).
+  c3                 BASELINE config C3: Flux-Redux outpainting at 512^2, 20 steps, batch 8 on one GPU.
+
+One bench "step" = `batch` COMPLETE compositions on each GPU through the pipeline mirrors: Redux prior per composition
+(SigLIP so400m tower + Redux embedder + blend with the constant text tokens; reference batch_generate_flux_kshot.py:459-465 /
+outpainting_updown_sampling_redux.py:1237-1243) -> FluxFillPipeline (VAE encode of the image and of the masked image, 8x8
+mask packing, T MMDiT steps of the FLUX.1-Fill-dev-shaped transformer: 19 double + 38 single blocks, d = 3072, 24 heads,
+C_in = 384, S = 1241 + (side/16)^2 tokens, flow-match Euler; outpainting...:1246-1257) -> VAE decode -> uint8 pixels.
+`value`: inputs resident in HBM (FluxFillPipeline.run_resident - the same code path __call__ uses after its host work);
+`e2e`: the public calls with PIL inputs (host preprocessing, pinned H2D, D2H of the images). Random-init weights and
+synthetic images (no checkpoints offline).
+
+Beside it, in the same run on the same box:
+  gpu_baseline  the oracle modules in bf16 torch-eager on the B200 (oracle/torchref.py: cuBLAS GEMMs, SDPA, unfused row ops) =
+                "the reference's torch/diffusers path" (diffusers itself is not installable offline), batch 1 as the reference
+                runs it and at this line's batch;
+  cpu_baseline  the oracle in fp32 on the host cores (bounded sample, extrapolated - stated);
+  secondary     (default line only) the other half of BASELINE.json's metric and the remaining configs: C5 scan GB/s vs HBM
+                peak, C2 retrieve images/s, C3 seconds per batch.
 """
 from __future__ import annotations
 
@@ -17,38 +31,40 @@ from pathlib import Path
 
 REPO = Path(__file__).resolve().parent
 
-HEIGHT = WIDTH = 1024
-STEPS = 50
 S_TXT, N_T5, N_REDUX = 1241, 512, 729
 GUIDANCE = 30.0                      # outpainting_updown_sampling_redux.py:45-56 default_guidance_scale
 D, HEADS, N_DOUBLE, N_SINGLE = 3072, 24, 19, 38
+METRIC = "composed images/sec (1024^2, 50-step Flux-Redux, device-timed)"
+C3_METRIC = "C3: composed images/sec (Flux-Redux outpainting 512^2, 20 steps, batch 8, device-timed)"
+WORKLOADS = {"compose": dict(side=1024, T=50, batch=4), "c3": dict(side=512, T=20, batch=8)}
 
 
 def flops_per_forward(s_img: int, s_txt: int = S_TXT, d: int = D, blocks: int = N_DOUBLE + N_SINGLE):
     """per block 24 d^2 S (GEMMs) + 4 S^2 d (attention), S = s_txt + s_img."""
     s = s_img + s_txt
-    gemm = blocks * 24.0 * d * d * s
-    attn = blocks * 4.0 * s * s * d
-    return gemm, attn
+    return blocks * 24.0 * d * d * s, blocks * 4.0 * s * s * d
 
 
-def full_workload(Bc: int) -> str:
-    """config.workload of the compose line - shared by the b200 arm and the reference arm."""
-    return (f"C4 per-GPU slice (32 compositions / 8 GPUs): {Bc} full Flux-Redux compositions at 1024^2 per "
-            "step and GPU, run as one batch: Redux prior per composition (SigLIP so400m + Redux embedder + "
-            "blend) -> Flux-Fill (VAE encode of images and masked images, mask packing, 50 MMDiT steps, "
-            "C_in=384, 19+38 blocks, S=1241+4096, guidance 30, strength 1.0) -> VAE decode -> uint8 pixels; "
-            "random-init weights, synthetic images; text tokens are per-prompt constants (T5/CLIP-text not "
-            "on the path); LaMa out of scope")
+def full_workload(Bc: int, side: int = 1024, T: int = 50) -> str:
+    """config.workload of a compose line - shared by the b200 arm and the reference arm."""
+    head = ("C4 per-GPU slice (32 compositions / 8 GPUs)" if side == 1024 else
+            "C3 (Flux-Redux outpainting 512^2, 20 steps, batch 8, one centred 30 % box kept)")
+    return (f"{head}: {Bc} full Flux-Redux compositions at {side}^2 per step and GPU, run as one batch: Redux prior per "
+            f"composition (SigLIP so400m + Redux embedder + blend) -> Flux-Fill (VAE encode of images and masked images, mask "
+            f"packing, {T} MMDiT steps, C_in=384, 19+38 blocks, S=1241+{(side // 16) ** 2}, guidance 30, strength 1.0 = {T} "
+            "executed steps) -> VAE decode -> uint8 pixels; random-init weights, synthetic images; text tokens are per-prompt "
+            "constants (T5/CLIP-text not on the path); LaMa out of scope")
 
 
 def gemm_traffic_from_profile():
     """dram read+write bytes per launch of the dominant GEMM shape (MLP-up of a batch-4 step) from the committed
     ncu --set full capture; None when the file is absent."""
-    try:
-        return json.loads((REPO / "profiles" / "r01_gemm_traffic.json").read_text())
-    except Exception:
-        return None
+    for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+        try:
+            return json.loads((REPO / "profiles" / name).read_text())
+        except Exception:
+            continue
+    return None
 
 
 def prof_collect():
@@ -58,68 +74,66 @@ def prof_collect():
     return [(ms[i], work[i], cnt[i]) for i in range(2)]
 
 
-def build_model(device, seed=3000, in_channels=384, max_batch=1):
-    import torch
+def synth_scene(rank: int, Bc: int, side: int):
+    """Synthetic targets (smooth structure + noise), backgrounds (Redux image prompts) and outpaint masks (one box of
+    30 % x 30 % kept, like the reference's default box, outpainting...:943-947)."""
+    import numpy as np
+    from PIL import Image
 
-    from domain_rag_b200.flux import FluxConfig, FluxPipeline, FluxTransformer, init_params_device
-    cfg = FluxConfig(in_channels=in_channels, d=D, heads=HEADS, n_double=N_DOUBLE, n_single=N_SINGLE)
-    params = init_params_device(cfg, seed=seed, device=device)
-    tr = FluxTransformer(cfg, params, max_batch=max_batch, max_img_tokens=(HEIGHT // 16) * (WIDTH // 16), txt_tokens=S_TXT,
-                         device=device)
-    return cfg, tr, FluxPipeline(tr)
-
-
-def synth_inputs(seed: int, batch: int = 1):
-    """Host-side (pinned) synthetic stand-ins for what the encoders / VAE would hand to the pipeline."""
-    import torch
-    g = torch.Generator().manual_seed(seed)
-    s_img = (HEIGHT // 16) * (WIDTH // 16)
-    t5 = torch.randn(batch, N_T5, 4096, generator=g).bfloat16().pin_memory()
-    redux = torch.randn(batch, N_REDUX, 4096, generator=g).bfloat16().pin_memory()
-    pooled = torch.randn(batch, 768, generator=g).bfloat16().pin_memory()
-    cond = torch.randn(batch, s_img, 320, generator=g).bfloat16().pin_memory()   # masked-image latents (64) + mask (256)
-    return t5, redux, pooled, cond
+    from domain_rag_b200 import hostlogic as H
+    rng = np.random.default_rng(1000 + rank)
+    yy, xx = np.mgrid[0:side, 0:side].astype(np.float32)
+    base = np.stack([np.sin(xx / (40 + 7 * c)) * np.cos(yy / (55 - 6 * c)) for c in range(3)], -1) * 0.35 + 0.5
+    targets = [Image.fromarray(((base + rng.normal(0, 0.04, base.shape)).clip(0, 1) * 255).astype(np.uint8)) for _ in range(Bc)]
+    backgrounds = [Image.fromarray((rng.random((640, 640, 3)) * 255).astype(np.uint8)) for _ in range(Bc)]
+    masks = [H.generate_outpaint_mask(targets[i], [(int(side * (0.30 + 0.02 * (i % 4))), int(side * 0.35), int(side * 0.3),
+                                                     int(side * 0.3))])[0] for i in range(Bc)]
+    return targets, backgrounds, masks
 
 
-def blend_rows(redux_blend, t5, redux, pooled):
-    """One Redux blend per composition (each has its own background image) -> prompt tensors [B,1241,4096], [B,768]."""
-    import torch
-    outs = [redux_blend(t5[i:i + 1], redux[i:i + 1], pooled[i:i + 1], [1.0], [1.0]) for i in range(t5.shape[0])]
-    if len(outs) == 1:
-        return outs[0]
-    return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
-
-
-def run(args):
-    if getattr(args, "scope", "full") == "full":
-        return run_full(args)
+def measure_compose(pipes, rank, world, local, Bc, side, T, steps, warmup, launch_list_only=False):
+    """Timed legs of one compose workload on built pipelines. Returns a dict of raw measurements (every rank)."""
+    import numpy as np
     import torch
 
     from domain_rag_b200 import _lib
     from domain_rag_b200 import benchutil as B
-    from domain_rag_b200.flux import redux_blend
+    from domain_rag_b200 import flux as F
+    from domain_rag_b200 import siglip as S
 
-    rank, world, local = B.dist_setup(args.gpus)
     dev = torch.device("cuda", local)
     lib = _lib.load()
-    Bc = max(1, int(getattr(args, "batch", 1)))
-    cfg, tr, pipe = build_model(dev, max_batch=Bc)
-    t5_h, redux_h, pooled_h, cond_h = synth_inputs(3000 + rank, Bc)
-    t5, redux, pooled, cond = (t.to(dev) for t in (t5_h, redux_h, pooled_h, cond_h))
-    s_img = (HEIGHT // 16) * (WIDTH // 16)
+    prior, fill = pipes.prior_redux, pipes.pipe_fill
+    targets, backgrounds, masks = synth_scene(rank, Bc, side)
     gen = torch.Generator("cpu")
 
-    def compose_device(seed):
-        """Inputs already resident in HBM: blend -> 50 steps -> final latents (stay on the device)."""
-        pe, pp = blend_rows(redux_blend, t5, redux, pooled)
-        lat, _, _ = latents_cache[seed % len(latents_cache)]
-        return pipe(prompt_embeds=pe, pooled_prompt_embeds=pp, guidance_scale=GUIDANCE, num_inference_steps=STEPS,
-                    height=HEIGHT, width=WIDTH, latents=lat.clone(), extra_cond=cond)
-
-    latents_cache = [pipe.prepare_latents(Bc, HEIGHT, WIDTH, gen.manual_seed(s), dev) for s in range(2)]
+    # device-resident inputs of the `value` leg
+    px_dev = S.preprocess(backgrounds, prior.image_size).to(dev)
+    img_u8 = torch.from_numpy(np.stack([np.asarray(t) for t in targets])).to(dev)
+    mask_u8 = torch.from_numpy(np.stack([(np.asarray(m) >= 128).astype(np.uint8) for m in masks])).to(dev)
+    txt_row = prior.text_table.lookup("", "")
+    txt, pooled = txt_row[0][None].contiguous(), txt_row[1][None].contiguous()
+    noise_cache = [fill.prepare_latents(Bc, side, side, gen.manual_seed(s), dev)[0] for s in range(2)]
+    vgen = torch.Generator(device=dev)
     torch.cuda.synchronize()
 
-    for i in range(args.warmup):
+    def compose_device(seed):
+        img_tokens = prior.image_embedder(prior.image_encoder.last_hidden_state(px_dev)).contiguous()
+        rows = [F.redux_blend(txt, img_tokens[i:i + 1], pooled, [1.0], [1.0]) for i in range(Bc)]
+        pe, pp = torch.cat([r[0] for r in rows]), torch.cat([r[1] for r in rows])
+        vgen.manual_seed(seed)
+        return fill.run_resident(img_u8, mask_u8, pe, pp, GUIDANCE, T, 1.0, vgen, output_type="u8",
+                                 noise=noise_cache[seed % 2]).images
+
+    def compose_e2e(seed):
+        outs = [prior([bg], prompt="", prompt_2="", prompt_embeds_scale=[1.0], pooled_prompt_embeds_scale=[1.0])
+                for bg in backgrounds]
+        return fill(image=targets, mask_image=masks, height=side, width=side, guidance_scale=GUIDANCE,
+                    num_inference_steps=T, generator=gen.manual_seed(seed), strength=1.0,
+                    prompt_embeds=torch.cat([o.prompt_embeds for o in outs]),
+                    pooled_prompt_embeds=torch.cat([o.pooled_prompt_embeds for o in outs])).images
+
+    for i in range(warmup):
         compose_device(i)
     B.barrier(world)
     sampler = B.ClockSampler(local)
@@ -128,76 +142,135 @@ def run(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     B.barrier(world)
     torch.cuda.cudart().cudaProfilerStart()   # no-op unless run under `ncu --profile-from-start off`
+    _lib.launch_count(reset=True)
     e0.record()
-    for i in range(args.steps):
-        out = compose_device(i)
+    for i in range(steps):
+        compose_device(i)
     e1.record()
+    n_launches = _lib.launch_count()
     torch.cuda.cudart().cudaProfilerStop()
     B.barrier(world)
     total_ms = B.max_over_ranks(e0.elapsed_time(e1), world)
     clocks = sampler.stop() if rank == 0 else {}
+    m = {"ms_per_step": total_ms / steps, "clocks": clocks, "gpu_launches": int(n_launches)}
+    if launch_list_only:
+        return m
 
-    # dominant-kernel timing: CUDA-event bracket around every GEMM / attention launch of ONE more image
+    # dominant kernels: CUDA-event bracket around every GEMM / attention launch of ONE more step (same stream)
     lib.drag_prof_enable(1)
     compose_device(0)
     torch.cuda.synchronize()
-    (g_ms, g_fl, g_n), (a_ms, a_fl, a_n) = prof_collect()
+    (m["g_ms"], m["g_fl"], m["g_n"]), (m["a_ms"], m["a_fl"], m["a_n"]) = prof_collect()
     lib.drag_prof_enable(0)
+    m["cublas_here"] = B.same_box_cublas_tflops() if rank == 0 else 0.0   # hot chip, same power state as the timed region
 
-    # end to end through the pipeline call with HOST buffers: H2D of tokens / conditioning / latents drawn
-    # with the CPU generator, D2H of the final latents, every image
-    def compose_e2e(seed):
-        t5d, rd, pd, cd = (t.to(dev, non_blocking=True) for t in (t5_h, redux_h, pooled_h, cond_h))
-        pe, pp = blend_rows(redux_blend, t5d, rd, pd)
-        o = pipe(prompt_embeds=pe, pooled_prompt_embeds=pp, guidance_scale=GUIDANCE, num_inference_steps=STEPS,
-                 height=HEIGHT, width=WIDTH, generator=gen.manual_seed(seed), extra_cond=cd)
-        return o.latents.cpu()
-
-    n_e2e = max(1, min(args.steps, 2))
+    n_e2e = max(1, min(steps, 2))
     compose_e2e(0)
     B.barrier(world)
     t0 = time.perf_counter()
     for i in range(n_e2e):
-        lat_h = compose_e2e(i)
+        imgs = compose_e2e(i)
     B.barrier(world)
-    e2e_s = B.max_over_ranks(time.perf_counter() - t0, world) / n_e2e
+    m["e2e_s"] = B.max_over_ranks(time.perf_counter() - t0, world) / n_e2e
+    assert len(imgs) == Bc and imgs[0].size == (side, side)
+    m["h2d"] = Bc * (side * side * 3 + side * side + 3 * prior.image_size ** 2 * 4 + (side // 16) ** 2 * 64 * 2)
+    m["d2h"] = Bc * side * side * 3
+    return m
 
-    if rank != 0:
-        return None
-    ms_per_step = total_ms / args.steps
+
+def compose_line(m, metric, world, steps, warmup, Bc, side, T, peaks):
+    s_img = (side // 16) ** 2
     gemm_fl, attn_fl = flops_per_forward(s_img)
-    peaks = B.measured_peaks()
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-    kernels_per_forward = 12 + N_DOUBLE * 13 + N_SINGLE * 5 + 2   # see flux_engine.cu
-    out = {
-        "metric": "composed images/sec (1024^2, 50-step Flux-Redux, device-timed)",
-        "value": round(Bc * world / (ms_per_step * 1e-3), 5), "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
+    ms = m["ms_per_step"]
+    tr = gemm_traffic_from_profile() or {}
+    g_tf = m["g_fl"] / (m["g_ms"] * 1e-3) / 1e12
+    return {
+        "metric": metric, "value": round(Bc * world / (ms * 1e-3), 5), "unit": "images/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"C4 per-GPU slice, denoising loop only: {Bc} Flux-Redux compositions per step and GPU as one "
-                               "batch, 1024^2, 50 steps (Fill-shaped MMDiT C_in=384, 19+38 blocks, S=1241+4096, guidance "
-                               "30), random-init weights, synthetic T5/Redux tokens; VAE + encoders outside the timed region",
-                   "batch_per_gpu": Bc,
-                   "l2_policy": "23.8 GB of weights + 0.4 GB of activations stream per denoising step (>> 126 MB L2)",
-                   "flops_per_image": STEPS * (gemm_fl + attn_fl),
-                   "achieved_tflops": round(Bc * STEPS * (gemm_fl + attn_fl) / (ms_per_step * 1e-3) / 1e12, 1)},
-        "e2e": {"value": round(Bc * world / e2e_s, 5), "unit": "images/s",
-                "h2d_bytes_per_step": int(sum(t.numel() * 2 for t in (t5_h, redux_h, pooled_h, cond_h)) + Bc * s_img * 64 * 2),
-                "d2h_bytes_per_step": int(lat_h.numel() * 2)},
-        "gpu_launches": args.steps * (STEPS * (kernels_per_forward + 1) + Bc),
-        "clocks": clocks,
-        "roofline": {"bound": "tensor", "achieved": round(g_fl / (g_ms * 1e-3) / 1e12, 1), "peak": peak,
-                     "unit": "TFLOP/s", "frac": round(g_fl / (g_ms * 1e-3) / 1e12 / peak, 4), "traffic": None,
-                     "kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of one image)",
-                     "kernel_ms": round(g_ms / max(g_n, 1), 4), "launches": g_n,
-                     "share_of_step": round(g_ms / (g_ms + a_ms), 4), "peak_source": peaks["source"] + " (sustained)",
-                     "attention": {"achieved": round(a_fl / (a_ms * 1e-3) / 1e12, 1), "kernel_ms": round(a_ms / max(a_n, 1), 4),
-                                   "launches": a_n, "share_of_step": round(a_ms / (g_ms + a_ms), 4)}},
-        **({"cpu_baseline": cpu_baseline()} if world == 1 else {}),   # rank 0 at N = 1 only
+        "config": {"workload": full_workload(Bc, side, T), "batch_per_gpu": Bc, "executed_steps": T,
+                   "l2_policy": "23.8 GB of weights + activations stream per denoising step (>> 126 MB L2)",
+                   "flops_per_image": T * (gemm_fl + attn_fl),
+                   "flops_note": "denoising loop only; SigLIP/Redux/VAE are timed but not counted",
+                   "achieved_tflops": round(Bc * T * (gemm_fl + attn_fl) / (ms * 1e-3) / 1e12, 1),
+                   "ideal_seconds_per_step_at_peak": round(Bc * T * (gemm_fl + attn_fl) / (peak * 1e12), 3)},
+        "e2e": {"value": round(Bc * world / m["e2e_s"], 5), "unit": "images/s", "h2d_bytes_per_step": int(m["h2d"]),
+                "d2h_bytes_per_step": int(m["d2h"])},
+        "gpu_launches": m["gpu_launches"],
+        "gpu_launches_note": f"every kernel of libdomainrag_b200.so launched inside the timed region (host-side counter at the "
+                             f"launch sites); {int(m['g_n'] + m['a_n'])} per step are tcgen05 GEMM/conv + attention",
+        "clocks": m["clocks"],
+        "roofline": {"bound": "tensor", "achieved": round(g_tf, 1), "peak": peak, "unit": "TFLOP/s",
+                     "frac": round(g_tf / peak, 4), "traffic": tr.get("traffic_bytes_per_launch"),
+                     "traffic_note": tr.get("note"),
+                     "kernel": "gemm_bf16_tcgen05_2cta_kernel (all GEMM/conv launches of one step)",
+                     "kernel_ms": round(m["g_ms"] / max(m["g_n"], 1), 4), "launches": m["g_n"],
+                     "share_of_step": round(m["g_ms"] / ms, 4), "peak_source": peaks["source"] + " (sustained)",
+                     "same_box_cublas_sustained_tflops": round(m["cublas_here"], 1),
+                     "frac_of_same_box_cublas": round(g_tf / max(m["cublas_here"], 1e-9), 4),
+                     "attention": {"achieved": round(m["a_fl"] / (m["a_ms"] * 1e-3) / 1e12, 1),
+                                   "frac": round(m["a_fl"] / (m["a_ms"] * 1e-3) / 1e12 / peak, 4),
+                                   "kernel_ms": round(m["a_ms"] / max(m["a_n"], 1), 4), "launches": m["a_n"],
+                                   "share_of_step": round(m["a_ms"] / ms, 4)},
+                     "whole_step_frac": round(Bc * T * (gemm_fl + attn_fl) / (ms * 1e-3) / 1e12 / peak, 4)},
     }
+
+
+def build_pipes(local, max_batch, max_side):
+    import torch
+
+    from domain_rag_b200.models import load_model
+    return load_model(device=torch.device("cuda", local), want=("fill",), weights_dir=None, size="full", max_side=max_side,
+                      seed=3000, max_batch=max_batch, allow_random_init=True)
+
+
+# ------------------------------------------------------------------------------------------ torch-eager GPU baseline
+def gpu_baseline(pipes, local, side, T, batches, seed=0):
+    """The oracle modules in bf16 torch-eager on this GPU (oracle/torchref.py; test infrastructure used as the yardstick the
+    metric asks for): full Flux-Fill sampling loop of T steps + VAE encode x2 + decode at each batch size, timed with CUDA
+    events after one warm-up forward. Weights are the product path's own device tensors (shared, not copied). SigLIP / Redux
+    prior (< 0.2 % of the FLOPs) not included - stated."""
+    import torch
+
+    from oracle import flux as OF
+    from oracle import torchref as TR
+    from oracle import vae as OV
+    dev = torch.device("cuda", local)
+    tr = pipes.pipe_fill.transformer
+    ocfg = OF.FluxConfig(in_channels=384)
+    p_vae = {k: v.to(dev) for k, v in OV.init_params(seed=5000).items()}
+    h2 = side // 16
+    out = {"kind": "torch-eager bf16 (oracle modules on the B200: cuBLAS GEMM + SDPA + unfused row ops)", "unit": "images/s",
+           "by_batch": {}}
+    g = torch.Generator(device=dev).manual_seed(seed)
+    for Bc in batches:
+        lat = torch.randn(Bc, h2 * h2, 64, generator=g, device=dev).bfloat16()
+        cond = torch.randn(Bc, h2 * h2, 320, generator=g, device=dev).bfloat16()
+        ctx = (0.3 * torch.randn(Bc, S_TXT, 4096, generator=g, device=dev)).bfloat16()
+        pooled = torch.randn(Bc, 768, generator=g, device=dev).bfloat16()
+        img = torch.randint(0, 255, (Bc, side, side, 3), generator=g, device=dev, dtype=torch.uint8)
+        TR.sample(tr.params, ocfg, lat, ctx, pooled, GUIDANCE, 1, h2, h2, extra_cond=cond)      # warm-up: one step
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        TR.vae_encode(img, p_vae, dtype=torch.bfloat16)
+        TR.vae_encode(img, p_vae, dtype=torch.bfloat16)
+        x = TR.sample(tr.params, ocfg, lat, ctx, pooled, GUIDANCE, T, h2, h2, extra_cond=cond)
+        TR.vae_decode_u8(OF.unpack_latents(x, 2 * h2, 2 * h2), p_vae, dtype=torch.bfloat16)
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3
+        out["by_batch"][str(Bc)] = {"images_per_s": round(Bc / sec, 5), "seconds": round(sec, 3)}
+        del lat, cond, ctx, pooled, img, x
+        torch.cuda.empty_cache()
+    out["value"] = out["by_batch"][str(batches[-1])]["images_per_s"]
+    out["sample"] = (f"one full composition per batch size: VAE encode x2 + {T} sampling steps at {side}^2 + VAE decode, device-"
+                     "timed; batch 1 = how the reference calls it (outpainting...:1246-1257)")
     return out
 
 
+# ------------------------------------------------------------------------------------------ CPU oracle baseline
 def _time_oracle_block(n_double: int, n_single: int, s_img: int, seed: int):
     """Seconds for one oracle forward with the given block counts at full width / sequence (fp32 CPU)."""
     import torch
@@ -217,190 +290,124 @@ def _time_oracle_block(n_double: int, n_single: int, s_img: int, seed: int):
         return time.perf_counter() - t0
 
 
-def cpu_baseline():
+def cpu_baseline(side: int = 1024, T: int = 50):
     """Oracle on the host cores, bounded sample: ONE double block and ONE single block at full width and
-    full sequence (d=3072, S=5337), extrapolated to 19 + 38 blocks x 50 steps (embedders < 0.1 %)."""
+    full sequence, extrapolated to 19 + 38 blocks x T steps (embedders < 0.1 %)."""
     import torch
     torch.set_num_threads(os.cpu_count())
-    s_img = (HEIGHT // 16) * (WIDTH // 16)
+    s_img = (side // 16) ** 2
     base = _time_oracle_block(0, 0, s_img, 1)
     t_d = max(_time_oracle_block(1, 0, s_img, 2) - base, 1e-6)
     t_s = max(_time_oracle_block(0, 1, s_img, 3) - base, 1e-6)
-    per_image = STEPS * (N_DOUBLE * t_d + N_SINGLE * t_s + base)
+    per_image = T * (N_DOUBLE * t_d + N_SINGLE * t_s + base)
     return {"value": round(1.0 / per_image, 8), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
             "sample": f"oracle.flux_forward fp32: 1 double block ({t_d:.2f} s) + 1 single block ({t_s:.2f} s) at "
-                      f"d=3072, S=5337, extrapolated x19/x38 x50 steps (a full image is ~{per_image / 3600:.1f} h)"}
+                      f"d=3072, S={S_TXT + s_img}, EXTRAPOLATED x19/x38 x{T} steps (a full image is ~{per_image / 3600:.2f} h); "
+                      "SigLIP / VAE not timed"}
 
 
-def run_reference(args):
+def run_reference(args, workload="compose"):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
+    w = WORKLOADS[workload]
+    Bc = max(1, int(args.batch or w["batch"]))
     cb = None
     vals = []
     for _ in range(max(1, min(args.steps, 2))):
-        cb = cpu_baseline()
+        cb = cpu_baseline(w["side"], w["T"])
         vals.append(cb["value"])
     val = sum(vals) / len(vals)
     cb["value"] = val
-    return {"impl": "reference", "metric": "composed images/sec (1024^2, 50-step Flux-Redux, device-timed)",
+    return {"impl": "reference", "metric": METRIC if workload == "compose" else C3_METRIC,
             "value": val, "unit": "images/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(1e3 / val, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": full_workload(max(1, int(getattr(args, "batch", 4)))),
-                       "batch_per_gpu": max(1, int(getattr(args, "batch", 4))),
+            "config": {"workload": full_workload(Bc, w["side"], w["T"]), "batch_per_gpu": Bc,
                        "sample": "CPU oracle (fp32, all host cores): one double + one single MMDiT block timed at full width and "
-                                 "sequence per step, extrapolated x19 / x38 x 50 steps; images/s does not depend on the batch on "
-                                 "the CPU; SigLIP / VAE (< 0.2 % of the FLOPs) not timed"},
+                                 "sequence per step, EXTRAPOLATED x19 / x38 x T steps; images/s does not depend on the batch on "
+                                 "the CPU; one host only - the number does not scale with --gpus; SigLIP / VAE (< 0.2 % of the "
+                                 "FLOPs) not timed"},
             "cpu_baseline": cb,
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
-# ------------------------------------------------------------------------------------------ full composition
-def run_full(args):
-    """One bench step = the C4 per-GPU slice (`--batch` COMPLETE compositions, default 4 = 32 compositions / 8 GPUs) run as
-    one batch through the pipeline mirrors: Redux prior per composition (SigLIP so400m tower + Redux embedder + blend with
-    the constant text tokens) -> FluxFillPipeline at 1024^2 (VAE encode of the images and of the masked images, 8x8 mask
-    packing, 50 MMDiT steps at strength 1.0, VAE decode, uint8 pixels). `value`: inputs resident in HBM; `e2e`: the public
-    calls with PIL inputs (host preprocessing, pinned H2D, D2H of the images) inside the timed region."""
-    import numpy as np
-    import torch
-    from PIL import Image
+# ------------------------------------------------------------------------------------------ entry points
+def run(args, workload="compose"):
+    """`compose`: the default BASELINE line (+ gpu_baseline, cpu_baseline, secondary). `c3`: config C3 as its own line."""
+    import torch  # noqa: F401
 
-    from domain_rag_b200 import _lib
     from domain_rag_b200 import benchutil as B
-    from domain_rag_b200 import flux as F
-    from domain_rag_b200 import hostlogic as H
-    from domain_rag_b200 import siglip as S
-    from domain_rag_b200.models import load_model
-
+    w = WORKLOADS[workload]
     rank, world, local = B.dist_setup(args.gpus)
-    dev = torch.device("cuda", local)
-    lib = _lib.load()
-    Bc = max(1, int(getattr(args, "batch", 4)))
-    pipes = load_model(device=dev, want=("fill",), weights_dir=None, size="full", max_side=HEIGHT, seed=3000, max_batch=Bc,
-                       allow_random_init=True)
-    prior, fill = pipes.prior_redux, pipes.pipe_fill
-    vae = fill.vae
-    rng = np.random.default_rng(1000 + rank)
-    yy, xx = np.mgrid[0:HEIGHT, 0:WIDTH].astype(np.float32)
-    base = np.stack([np.sin(xx / (40 + 7 * c)) * np.cos(yy / (55 - 6 * c)) for c in range(3)], -1) * 0.35 + 0.5
-    targets = [Image.fromarray(((base + rng.normal(0, 0.04, base.shape)).clip(0, 1) * 255).astype(np.uint8)) for _ in range(Bc)]
-    backgrounds = [Image.fromarray((rng.random((640, 640, 3)) * 255).astype(np.uint8)) for _ in range(Bc)]
-    masks = [H.generate_outpaint_mask(targets[i], [(int(WIDTH * (0.30 + 0.02 * i)), int(HEIGHT * 0.35), int(WIDTH * 0.3),
-                                                     int(HEIGHT * 0.3))])[0] for i in range(Bc)]
-    gen = torch.Generator("cpu")
-    s_img = (HEIGHT // 16) * (WIDTH // 16)
-
-    # device-resident inputs of the `value` leg
-    px_dev = S.preprocess(backgrounds, prior.image_size).to(dev)
-    img_u8 = torch.from_numpy(np.stack([np.asarray(t) for t in targets])).to(dev)
-    mask_u8 = torch.from_numpy(np.stack([(np.asarray(m) >= 128).astype(np.uint8) for m in masks])).to(dev)
-    txt_row = prior.text_table.lookup("", "")
-    txt, pooled = txt_row[0][None].contiguous(), txt_row[1][None].contiguous()
-    noise_cache = [fill.prepare_latents(Bc, HEIGHT, WIDTH, gen.manual_seed(s), dev)[0] for s in range(2)]
-    vgen = torch.Generator(device=dev)
-    torch.cuda.synchronize()
-
-    def compose_device(seed):
-        img_tokens = prior.image_embedder(prior.image_encoder.last_hidden_state(px_dev)).contiguous()
-        rows = [F.redux_blend(txt, img_tokens[i:i + 1], pooled, [1.0], [1.0]) for i in range(Bc)]
-        pe, pp = torch.cat([r[0] for r in rows]), torch.cat([r[1] for r in rows])
-        vgen.manual_seed(seed)
-        image_latents = F.pack_latents(vae.encode(img_u8, generator=vgen)).contiguous()
-        sig0 = F.flow_match_sigmas(STEPS, s_img)[0]
-        latents = F.axpby_(noise_cache[seed % 2], image_latents, sig0, 1.0 - sig0)
-        masked = F.pack_latents(vae.encode(img_u8, generator=vgen, mask=mask_u8))
-        cond = torch.cat([masked, F.pack_mask(mask_u8).to(torch.bfloat16)], dim=-1).contiguous()
-        packed, _ = fill._denoise(latents, HEIGHT // 8, WIDTH // 8, pe, pp, GUIDANCE, STEPS, 0, cond)
-        return vae.decode(F.unpack_latents(packed, HEIGHT // 8, WIDTH // 8), output_type="u8")
-
-    def compose_e2e(seed):
-        outs = [prior([bg], prompt="", prompt_2="", prompt_embeds_scale=[1.0], pooled_prompt_embeds_scale=[1.0])
-                for bg in backgrounds]
-        return fill(image=targets, mask_image=masks, height=HEIGHT, width=WIDTH, guidance_scale=GUIDANCE,
-                    num_inference_steps=STEPS, generator=gen.manual_seed(seed), strength=1.0,
-                    prompt_embeds=torch.cat([o.prompt_embeds for o in outs]),
-                    pooled_prompt_embeds=torch.cat([o.pooled_prompt_embeds for o in outs])).images
-
-    for i in range(args.warmup):
-        compose_device(i)
-    B.barrier(world)
-    sampler = B.ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    B.barrier(world)
-    torch.cuda.cudart().cudaProfilerStart()   # no-op unless run under `ncu --profile-from-start off`
-    _lib.launch_count(reset=True)
-    e0.record()
-    for i in range(args.steps):
-        compose_device(i)
-    e1.record()
-    n_launches = _lib.launch_count()
-    torch.cuda.cudart().cudaProfilerStop()
-    B.barrier(world)
-    total_ms = B.max_over_ranks(e0.elapsed_time(e1), world)
-    clocks = sampler.stop() if rank == 0 else {}
-
-    if os.environ.get("DRAG_BENCH_LAUNCH_LIST_ONLY") == "1":
+    Bc = max(1, int(args.batch or w["batch"]))
+    with_secondary = workload == "compose" and not getattr(args, "no_secondary", False)
+    max_batch = max(Bc, WORKLOADS["c3"]["batch"]) if with_secondary else Bc
+    pipes = build_pipes(local, max_batch, 1024 if with_secondary else w["side"])
+    launch_only = os.environ.get("DRAG_BENCH_LAUNCH_LIST_ONLY") == "1"
+    m = measure_compose(pipes, rank, world, local, Bc, w["side"], w["T"], args.steps, args.warmup, launch_only)
+    if launch_only:
         # profiler runs (ncu launch list of the timed region): the legs after the timed region add nothing to the capture
         if rank == 0:
-            print(json.dumps({"launch_list_only": True, "ms_per_step_under_profiler": total_ms / args.steps}), flush=True)
+            print(json.dumps({"launch_list_only": True, "ms_per_step_under_profiler": m["ms_per_step"]}), flush=True)
         return None
-
-    lib.drag_prof_enable(1)
-    compose_device(0)
-    torch.cuda.synchronize()
-    (g_ms, g_fl, g_n), (a_ms, a_fl, a_n) = prof_collect()
-    lib.drag_prof_enable(0)
-
-    cublas_here = B.same_box_cublas_tflops() if rank == 0 else 0.0     # hot chip, same power state as the timed region
-
-    n_e2e = max(1, min(args.steps, 2))
-    compose_e2e(0)
-    B.barrier(world)
-    t0 = time.perf_counter()
-    for i in range(n_e2e):
-        imgs = compose_e2e(i)
-    B.barrier(world)
-    e2e_s = B.max_over_ranks(time.perf_counter() - t0, world) / n_e2e
-    assert len(imgs) == Bc and imgs[0].size == (WIDTH, HEIGHT)
-
-    if rank != 0:
-        return None
-    ms_per_step = total_ms / args.steps
-    gemm_fl, attn_fl = flops_per_forward(s_img)
     peaks = B.measured_peaks()
+    out = None
+    if rank == 0:
+        out = compose_line(m, METRIC if workload == "compose" else C3_METRIC, world, args.steps, args.warmup, Bc, w["side"],
+                           w["T"], peaks)
+        if workload == "c3":
+            out["config"]["seconds_per_batch"] = round(m["ms_per_step"] * 1e-3, 3)
+    if not getattr(args, "no_gpu_baseline", False):
+        gb = gpu_baseline(pipes, local, w["side"], w["T"], [1, Bc]) if rank == 0 else None
+        B.barrier(world)
+        if rank == 0:
+            out["gpu_baseline"] = gb
+            out["gpu_baseline"]["ours_over_torch_eager"] = round(out["value"] / world / max(gb["value"], 1e-12), 3)
+    if with_secondary:
+        sec = secondary(pipes, rank, world, local, args)
+        if rank == 0:
+            out["secondary"] = sec
+    if rank == 0 and world == 1:
+        out["cpu_baseline"] = cpu_baseline(w["side"], w["T"])      # rank 0 at N = 1 only
+    return out
+
+
+def secondary(pipes, rank, world, local, args):
+    """The second half of BASELINE.json's metric and the configs the headline does not exercise, measured in the same run
+    (compact records; each has its own full line under --workload scan / retrieve / c3)."""
+    import torch
+
+    import bench_retrieve
+    import bench_scan
+    from domain_rag_b200 import benchutil as B
+    peaks = B.measured_peaks()
+    sec = {}
+    # C3 first: it reuses the resident Fill pipeline
+    c3 = WORKLOADS["c3"]
+    m = measure_compose(pipes, rank, world, local, c3["batch"], c3["side"], c3["T"], 2, 1)
+    gemm_fl, attn_fl = flops_per_forward((c3["side"] // 16) ** 2)
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-    h2d = Bc * (HEIGHT * WIDTH * 3 + HEIGHT * WIDTH + 3 * prior.image_size ** 2 * 4 + s_img * 64 * 2)
-    return {
-        "metric": "composed images/sec (1024^2, 50-step Flux-Redux, device-timed)",
-        "value": round(Bc * world / (ms_per_step * 1e-3), 5), "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": full_workload(Bc),
-                   "batch_per_gpu": Bc,
-                   "l2_policy": "23.8 GB of weights + 0.4 GB of activations stream per denoising step (>> 126 MB L2)",
-                   "flops_per_image": STEPS * (gemm_fl + attn_fl),
-                   "flops_note": "denoising loop only; SigLIP/Redux/VAE (~8 TFLOP) are timed but not counted",
-                   "achieved_tflops": round(Bc * STEPS * (gemm_fl + attn_fl) / (ms_per_step * 1e-3) / 1e12, 1)},
-        "e2e": {"value": round(Bc * world / e2e_s, 5), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(Bc * HEIGHT * WIDTH * 3)},
-        "gpu_launches": int(n_launches),
-        "gpu_launches_note": f"every kernel of libdomainrag_b200.so launched inside the timed region (host-side counter at the "
-                             f"launch sites); of these {int(g_n + a_n)} per step are tcgen05 GEMM/conv + attention",
-        "clocks": clocks,
-        "roofline": {"bound": "tensor", "achieved": round(g_fl / (g_ms * 1e-3) / 1e12, 1), "peak": peak,
-                     "unit": "TFLOP/s", "frac": round(g_fl / (g_ms * 1e-3) / 1e12 / peak, 4),
-                     "traffic": (gemm_traffic_from_profile() or {}).get("traffic_bytes_per_launch"),
-                     "traffic_note": (gemm_traffic_from_profile() or {}).get("note"),
-                     "kernel": "gemm_bf16_tcgen05_2cta_kernel (all GEMM/conv launches of one composition)",
-                     "kernel_ms": round(g_ms / max(g_n, 1), 4), "launches": g_n,
-                     "share_of_step": round(g_ms / (ms_per_step), 4), "peak_source": peaks["source"] + " (sustained)",
-                     "same_box_cublas_sustained_tflops": round(cublas_here, 1),
-                     "frac_of_same_box_cublas": round(g_fl / (g_ms * 1e-3) / 1e12 / max(cublas_here, 1e-9), 4),
-                     "attention": {"achieved": round(a_fl / (a_ms * 1e-3) / 1e12, 1), "kernel_ms": round(a_ms / max(a_n, 1), 4),
-                                   "launches": a_n, "share_of_step": round(a_ms / ms_per_step, 4)}},
-        **({"cpu_baseline": cpu_baseline()} if world == 1 else {}),   # rank 0 at N = 1 only
-    }
+    total_fl = c3["batch"] * c3["T"] * (gemm_fl + attn_fl)
+    sec["c3"] = {"workload": "C3: 8 x 512^2 x 20-step Flux-Redux outpainting per GPU (full compositions)",
+                 "seconds_per_batch": round(m["ms_per_step"] * 1e-3, 3),
+                 "images_per_s": round(c3["batch"] * world / (m["ms_per_step"] * 1e-3), 4),
+                 "executed_steps": c3["T"], "flops_per_batch": total_fl,
+                 "ideal_seconds_at_peak": round(total_fl / (peak * 1e12), 3),
+                 "frac_of_tensor_peak": round(total_fl / (m["ms_per_step"] * 1e-3) / 1e12 / peak, 4),
+                 "e2e_images_per_s": round(c3["batch"] * world / m["e2e_s"], 4)}
+    del m
+    # the compose models are no longer needed: free their 24 GB before the retrieval workloads
+    pipes.pipe_fill = None
+    pipes.prior_redux = None
+    torch.cuda.empty_cache()
+    pt = bench_scan.measure(rank, world, local, bench_scan.SCAN_N, bench_scan.SCAN_D, bench_scan.SCAN_NQ, bench_scan.SCAN_K,
+                            20, 3)
+    sec["scan"] = {"workload": f"C5 point: {pt['n_per_gpu']} x {pt['d']} fp32 rows per GPU, nq={pt['nq']}, top-{pt['k']}",
+                   "gbs": pt["gbs"], "ms_per_search": pt["ms_per_search"], "e2e_gbs": pt["e2e_gbs"],
+                   "roofline": {"bound": "hbm", "achieved": pt["kernel_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                "frac": round(pt["kernel_gbs"] / peaks["hbm_gbs"], 4), "kernel": "ip_scan_topk_kernel",
+                                "kernel_ms": pt["kernel_ms"], "traffic": bench_scan.scan_traffic_from_profile()},
+                   "verified_sharded_equals_single": pt["verified_sharded_equals_single"]}
+    sec["c2"] = bench_retrieve.measure_compact(rank, world, local)
+    return sec

@@ -52,8 +52,10 @@ def synth_images(n, res, seed, device, chunk=500):
     return out
 
 
-def run(args):
-    import numpy as np
+def measure(rank, world, local, MODEL, EMBED_BATCH, steps, warmup, with_e2e=True, launch_list_only=False):
+    """The C2 job on an initialised process group; returns raw measurements (every rank)."""
+    import ctypes as C
+
     import torch
 
     from domain_rag_b200 import _lib, clip
@@ -62,11 +64,8 @@ def run(args):
     from domain_rag_b200.resnet import ResNetEncoder
     from domain_rag_b200.retrieval import rerank_by_style
 
-    rank, world, local = B.dist_setup(args.gpus)
     dev = torch.device("cuda", local)
     lib = _lib.load()
-    MODEL = getattr(args, "clip_model", None) or globals()["MODEL"]     # ViT-L/14 (BASELINE) or ViT-B/32 (reference default)
-    EMBED_BATCH = int(getattr(args, "embed_batch", None) or globals()["EMBED_BATCH"])
     model, _ = clip.load(MODEL, device=dev, seed=2000)
     cfg = clip.CONFIGS[MODEL]
     stem = ResNetEncoder(seed=2000).to(dev).eval()
@@ -97,7 +96,7 @@ def run(args):
             ranked.append(rerank_by_style(fh[base], list(fh[base + 1: base + 1 + TOP_K]), first))
         return Dh, Ih, ranked
 
-    for _ in range(max(1, min(args.warmup, 3))):
+    for _ in range(max(1, min(warmup, 3))):
         job(corpus, queries, style_imgs, False)
     B.barrier(world)
     sampler = B.ClockSampler(local)
@@ -108,52 +107,82 @@ def run(args):
     torch.cuda.cudart().cudaProfilerStart()
     _lib.launch_count(reset=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         job(corpus, queries, style_imgs, False)
     e1.record()
     n_launches = _lib.launch_count()
     torch.cuda.cudart().cudaProfilerStop()
     B.barrier(world)
     total_ms = B.max_over_ranks(e0.elapsed_time(e1), world)
-    clocks = sampler.stop() if rank == 0 else {}
-
-    if os.environ.get("DRAG_BENCH_LAUNCH_LIST_ONLY") == "1":     # profiler runs: nothing after the timed region matters
-        if rank == 0:
-            print('{"launch_list_only": true}', flush=True)
-        return None
+    m = {"ms_per_step": total_ms / steps, "clocks": sampler.stop() if rank == 0 else {}, "gpu_launches": int(n_launches),
+         "cfg": cfg}
+    if launch_list_only:
+        return m
 
     # dominant kernels: event bracket around every GEMM / attention launch of one more job (same stream)
-    import ctypes as C
     lib.drag_prof_enable(1)
     job(corpus, queries, style_imgs, False)
     torch.cuda.synchronize()
     ms, work, cnt = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_int * 2)()
     _lib.check(lib.drag_prof_collect(ms, work, cnt, 2), "drag_prof_collect")
     lib.drag_prof_enable(0)
-    (g_ms, g_fl, g_n), (a_ms, a_fl, a_n) = [(ms[i], work[i], cnt[i]) for i in range(2)]
+    (m["g_ms"], m["g_fl"], m["g_n"]), (m["a_ms"], m["a_fl"], m["a_n"]) = [(ms[i], work[i], cnt[i]) for i in range(2)]
 
-    # end to end: pinned host tensors in, ranked lists out
-    corpus_h = torch.empty(corpus.shape, dtype=torch.float32, pin_memory=True)
-    corpus_h.copy_(corpus)
-    queries_h, style_h = queries.cpu().pin_memory(), style_imgs.cpu().pin_memory()
-    job(corpus_h, queries_h, style_h, True)
-    B.barrier(world)
-    n_e2e = max(1, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for _ in range(n_e2e):
-        Dh, Ih, ranked = job(corpus_h, queries_h, style_h, True)
-    B.barrier(world)
-    e2e_s = B.max_over_ranks(time.perf_counter() - t0, world) / n_e2e
-    assert len(ranked) == N_QUERY and len(ranked[0]) == TOP_K and ranked[0][0]["rank"] == 1
+    # the stem-statistics kernel on its own (one launch over the 707 style images), CUDA events on the launching stream
+    for _ in range(2):
+        stem.style_features(style_imgs)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(10):
+        stem.style_features(style_imgs)
+    s1.record()
+    torch.cuda.synchronize()
+    m["stem_ms"] = s0.elapsed_time(s1) / 10
+    m["stem_bytes"] = style_imgs.shape[0] * (3 * 256 * 256 * 4 + 128 * 4)        # 786 432 B in + 512 B out per image
 
+    if with_e2e:            # end to end: pinned host tensors in, ranked lists out
+        corpus_h = torch.empty(corpus.shape, dtype=torch.float32, pin_memory=True)
+        corpus_h.copy_(corpus)
+        queries_h, style_h = queries.cpu().pin_memory(), style_imgs.cpu().pin_memory()
+        job(corpus_h, queries_h, style_h, True)
+        B.barrier(world)
+        n_e2e = max(1, min(steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            Dh, Ih, ranked = job(corpus_h, queries_h, style_h, True)
+        B.barrier(world)
+        m["e2e_s"] = B.max_over_ranks(time.perf_counter() - t0, world) / n_e2e
+        assert len(ranked) == N_QUERY and len(ranked[0]) == TOP_K and ranked[0][0]["rank"] == 1
+        m["h2d"] = (corpus_h.numel() + queries_h.numel() + style_h.numel()) * 4
+    return m
+
+
+def stem_roofline(m, peaks):
+    gbs = m["stem_bytes"] / (m["stem_ms"] * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": round(gbs / peaks["hbm_gbs"], 4), "kernel": "stem_stats_kernel (707 images of 256^2, one launch)",
+            "kernel_ms": round(m["stem_ms"], 4), "traffic": None}
+
+
+def run(args):
+    from domain_rag_b200 import benchutil as B
+    rank, world, local = B.dist_setup(args.gpus)
+    MODEL = getattr(args, "clip_model", None) or globals()["MODEL"]     # ViT-L/14 (BASELINE) or ViT-B/32 (reference default)
+    EMBED_BATCH = int(getattr(args, "embed_batch", None) or globals()["EMBED_BATCH"])
+    launch_only = os.environ.get("DRAG_BENCH_LAUNCH_LIST_ONLY") == "1"
+    m = measure(rank, world, local, MODEL, EMBED_BATCH, args.steps, args.warmup, launch_list_only=launch_only)
+    if launch_only:     # profiler runs: nothing after the timed region matters
+        if rank == 0:
+            print('{"launch_list_only": true}', flush=True)
+        return None
     if rank != 0:
         return None
-    ms_per_step = total_ms / args.steps
+    cfg, ms_per_step = m["cfg"], m["ms_per_step"]
+    g_ms, g_fl, g_n, a_ms, a_fl, a_n = m["g_ms"], m["g_fl"], m["g_n"], m["a_ms"], m["a_fl"], m["a_n"]
     n_img = N_CORPUS + N_QUERY
     flops = vit_flops_per_image(cfg) * n_img
     peaks = B.measured_peaks()
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-    h2d = (corpus_h.numel() + queries_h.numel() + style_h.numel()) * 4
     return {
         "metric": f"C2 retrieval: corpus images embedded + indexed + queried per second ({MODEL}, top-100, style re-rank)",
         "value": round(n_img * world / (ms_per_step * 1e-3), 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
@@ -162,22 +191,42 @@ def run(args):
         "config": {"workload": c2_workload(MODEL, EMBED_BATCH),
                    "l2_policy": "6 GB of images stream through per step (>> 126 MB L2)",
                    "flops_per_image": vit_flops_per_image(cfg),
-                   "achieved_tflops": round(flops / (ms_per_step * 1e-3) / 1e12, 1)},
-        "e2e": {"value": round(n_img * world / e2e_s, 1), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+                   "achieved_tflops": round(flops / (ms_per_step * 1e-3) / 1e12, 1),
+                   "whole_job_frac_of_tensor_peak": round(flops / (ms_per_step * 1e-3) / 1e12 / peak, 4)},
+        "e2e": {"value": round(n_img * world / m["e2e_s"], 1), "unit": "images/s", "h2d_bytes_per_step": int(m["h2d"]),
                 "d2h_bytes_per_step": int(N_QUERY * TOP_K * 12 + N_QUERY * (1 + TOP_K) * 128 * 4)},
-        "gpu_launches": int(n_launches),
+        "gpu_launches": m["gpu_launches"],
         "gpu_launches_note": f"every kernel of libdomainrag_b200.so launched inside the timed region; {int(g_n + a_n)} per step "
                              "are tcgen05 GEMM + attention",
-        "clocks": clocks,
+        "clocks": m["clocks"],
         "roofline": {"bound": "tensor", "achieved": round(g_fl / (g_ms * 1e-3) / 1e12, 1), "peak": peak, "unit": "TFLOP/s",
                      "frac": round(g_fl / (g_ms * 1e-3) / 1e12 / peak, 4), "traffic": None,
                      "kernel": "gemm_bf16_tcgen05_2cta_kernel (all GEMM launches of one C2 job)",
                      "kernel_ms": round(g_ms / max(g_n, 1), 4), "launches": g_n, "share_of_step": round(g_ms / ms_per_step, 4),
                      "peak_source": peaks["source"] + " (sustained)",
                      "attention": {"achieved": round(a_fl / (a_ms * 1e-3) / 1e12, 1), "kernel_ms": round(a_ms / max(a_n, 1), 4),
-                                   "launches": a_n, "share_of_step": round(a_ms / ms_per_step, 4)}},
+                                   "launches": a_n, "share_of_step": round(a_ms / ms_per_step, 4)},
+                     "stem_stats": stem_roofline(m, peaks)},
         **({"cpu_baseline": cpu_baseline(model=MODEL)} if world == 1 else {}),   # rank 0 at N = 1 only
     }
+
+
+def measure_compact(rank, world, local, model: str = MODEL):
+    """Compact C2 record for the default line's `secondary` block (2 timed jobs, no e2e leg)."""
+    from domain_rag_b200 import benchutil as B
+    m = measure(rank, world, local, model, EMBED_BATCH, 2, 1, with_e2e=False)
+    peaks = B.measured_peaks()
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    n_img = N_CORPUS + N_QUERY
+    flops = vit_flops_per_image(m["cfg"]) * n_img
+    ms = m["ms_per_step"]
+    return {"workload": f"C2 per GPU: {N_CORPUS} images -> CLIP {model} embed -> resident index -> {N_QUERY} queries top-{TOP_K} "
+                        "-> style re-rank statistics",
+            "images_per_s": round(n_img * world / (ms * 1e-3), 1), "ms_per_job": round(ms, 2),
+            "frac_of_tensor_peak": round(flops / (ms * 1e-3) / 1e12 / peak, 4),
+            "gemm_tflops": round(m["g_fl"] / (m["g_ms"] * 1e-3) / 1e12, 1),
+            "attention_tflops": round(m["a_fl"] / (m["a_ms"] * 1e-3) / 1e12, 1),
+            "stem_stats": stem_roofline(m, peaks)}
 
 
 def cpu_baseline(n_sample: int = 16, model: str = MODEL):

@@ -300,6 +300,8 @@ class FluxPipeline:
             return PipelineOutput(latents=lat, images=None, steps_run=steps_run)
         if self.vae is None:
             raise RuntimeError("this pipeline was built without a VAE: pass vae=FluxVAE(...) or output_type='latent'")
+        if output_type == "u8":          # uint8 [B,H,W,3] left on the device (bench.py's device-resident leg)
+            return PipelineOutput(latents=lat, images=self.vae.decode(lat, output_type="u8"), steps_run=steps_run)
         return PipelineOutput(latents=lat, images=self.vae.decode(lat, output_type="pil"), steps_run=steps_run)
 
     def __call__(self, prompt_embeds, pooled_prompt_embeds, guidance_scale=3.5, num_inference_steps=28, height=1024,
@@ -375,13 +377,25 @@ class FluxFillPipeline(FluxPipeline):
             msk_np.append((np.asarray(mk) >= 128).astype(np.uint8))
         img_u8 = torch.from_numpy(np.stack(img_np)).pin_memory().to(dev, non_blocking=True)
         mask_u8 = torch.from_numpy(np.stack(msk_np)).pin_memory().to(dev, non_blocking=True)
+        return self.run_resident(img_u8, mask_u8, prompt_embeds, pooled_prompt_embeds, guidance_scale, num_inference_steps,
+                                 strength, generator, output_type)
+
+    def run_resident(self, img_u8, mask_u8, prompt_embeds, pooled_prompt_embeds, guidance_scale, num_inference_steps,
+                     strength, generator, output_type="pil", noise=None):
+        """Everything of __call__ after the host-side PIL work, on device-resident inputs: img_u8 uint8 [B,H,W,3],
+        mask_u8 uint8 [B,H,W] (1 = repaint), H and W multiples of 16. `noise` (packed bf16 [B,S,64]) replaces the CPU
+        generator's initial-noise draw (bench.py's `value` leg keeps it resident; `generator` may then be a device
+        generator for the two VAE samples). __call__ and the bench share this one code path."""
+        dev = self.transformer.device
+        B, H, W = mask_u8.shape
         start = executed_range(num_inference_steps, strength)
         if start >= num_inference_steps:
             raise ValueError(f"After adjusting the num_inference_steps by strength parameter: {strength}, the number of "
                              "pipeline steps is 0 which is < 1")
         h, w = H // 8, W // 8
         image_latents = pack_latents(self.vae.encode(img_u8, generator=generator)).contiguous()
-        noise, _, _ = self.prepare_latents(B, H, W, generator, dev)
+        if noise is None:
+            noise, _, _ = self.prepare_latents(B, H, W, generator, dev)
         s0 = flow_match_sigmas(num_inference_steps, noise.shape[1])[start]
         latents = axpby_(noise.contiguous(), image_latents, s0, 1.0 - s0)
         masked = pack_latents(self.vae.encode(img_u8, generator=generator, mask=mask_u8))

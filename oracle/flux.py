@@ -109,7 +109,7 @@ def timestep_embedding(t: torch.Tensor, dim: int = 256) -> torch.Tensor:
     """[cos | sin] of 1000*t * exp(-ln(1e4) * i / half) (diffusers Timesteps with flip_sin_to_cos,
     downscale_freq_shift=0; same as torchtitan layers.py:35-59)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = (1000.0 * t.float())[:, None] * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
@@ -128,14 +128,18 @@ def rope_tables(ids: torch.Tensor, axes_dim=(16, 56, 56), theta: float = 10000.0
 
 
 def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
-    """x [B,H,S,128]; rotate interleaved pairs (2j, 2j+1) by angle j."""
-    x0, x1 = x[..., 0::2], x[..., 1::2]
+    """x [B,H,S,128]; rotate interleaved pairs (2j, 2j+1) by angle j. Computed in fp32 and cast back to x.dtype
+    (diffusers apply_rotary_emb: `.float()` ... `.type_as(query)`); a no-op cast for the fp32 oracle."""
+    xf = x.float()
+    x0, x1 = xf[..., 0::2], xf[..., 1::2]
     c, s = cos[None, None], sin[None, None]
-    return torch.stack([x0 * c - x1 * s, x1 * c + x0 * s], dim=-1).flatten(-2)
+    return torch.stack([x0 * c - x1 * s, x1 * c + x0 * s], dim=-1).flatten(-2).to(x.dtype)
 
 
 def rms_norm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
-    return x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * w
+    """Variance in fp32 (diffusers RMSNorm upcasts), result in x.dtype."""
+    xf = x.float()
+    return (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).to(x.dtype) * w
 
 
 def layer_norm(x: torch.Tensor) -> torch.Tensor:
@@ -163,9 +167,10 @@ def attention(q, k, v, cos, sin):
 
 
 def temb_vector(p, cfg: FluxConfig, t, g, pooled):
-    vec = _mlp_embed(p, "t_in", timestep_embedding(t))
+    dt = pooled.dtype                       # sinusoids are built in fp32 and cast to the model dtype (diffusers)
+    vec = _mlp_embed(p, "t_in", timestep_embedding(t).to(dt))
     if cfg.guidance:
-        vec = vec + _mlp_embed(p, "g_in", timestep_embedding(g))
+        vec = vec + _mlp_embed(p, "g_in", timestep_embedding(g).to(dt))
     return vec + _mlp_embed(p, "p_in", pooled)
 
 
@@ -176,7 +181,7 @@ def flux_forward(p: Dict[str, torch.Tensor], cfg: FluxConfig, x, ctx, pooled, t,
     txt = F.linear(ctx, p["ctx_in.w"], p["ctx_in.b"])
     vec = temb_vector(p, cfg, t, g, pooled)
     mod = F.linear(F.silu(vec), p["mod.w"], p["mod.b"])            # [B, n_mod]
-    cos, sin = rope_tables(torch.cat([txt_ids, img_ids], 0), cfg.axes_dim, cfg.theta)
+    cos, sin = (a.to(x.device) for a in rope_tables(torch.cat([txt_ids, img_ids], 0).cpu(), cfg.axes_dim, cfg.theta))
     S_txt = txt.shape[1]
 
     def chunks(off, n):
@@ -267,9 +272,10 @@ def sample(p, cfg: FluxConfig, latents_packed, ctx, pooled, guidance: float, num
     sig = flow_match_sigmas(num_steps, latents_packed.shape[1])
     img_ids, txt_ids = image_ids(h2, w2), torch.zeros(ctx.shape[1], 3)
     x = latents_packed
-    g = torch.full((B,), guidance)
+    dev = x.device
+    g = torch.full((B,), guidance, device=dev)
     for i in range(start_step, num_steps):
-        t = torch.full((B,), float(sig[i]))
+        t = torch.full((B,), float(sig[i]), device=dev)
         inp = x if extra_cond is None else torch.cat([x, extra_cond], dim=-1)
         v = flux_forward(p, cfg, inp, ctx, pooled, t, g, img_ids, txt_ids)
         x = euler_step(x, v, float(sig[i]), float(sig[i + 1]))

@@ -47,15 +47,22 @@ def generate(p_flux, cfg, p_vae, prompt_embeds, pooled, guidance, num_steps, hei
 
 
 def fill(p_flux, cfg, p_vae, image_u8: np.ndarray, mask_bool: np.ndarray, prompt_embeds, pooled, guidance, num_steps,
-         strength, generator):
+         strength, generator, device="cpu", flux_dtype=torch.float32):
     """image_u8 [H,W,3] or [B,H,W,3], mask_bool [H,W] or [B,H,W] (True = repaint), H and W multiples of 16.
-    -> (latents, image uint8 [B,H,W,3]). A batch shares one generator: each draw covers the whole batch."""
+    -> (latents, image uint8 [B,H,W,3]). A batch shares one generator: each draw covers the whole batch.
+    device / flux_dtype: the torch-ref legs (oracle/torchref.py) run the same control flow on the GPU - random draws
+    still come from the CPU generator, the VAE stays fp32, the transformer runs in `flux_dtype` on `p_flux` as given
+    (a CastingParams view for bf16 device weights)."""
     if image_u8.ndim == 3:
         image_u8, mask_bool = image_u8[None], mask_bool[None]
     B, H, W = mask_bool.shape
     h, w = H // 8, W // 8
-    img = OV.preprocess_image(torch.from_numpy(np.ascontiguousarray(image_u8)))
-    mask = torch.from_numpy(mask_bool.astype(np.float32))
+    dev = torch.device(device)
+    if dev.type != "cpu":
+        p_vae = {k: v.to(dev) for k, v in p_vae.items()}
+    img = OV.preprocess_image(torch.from_numpy(np.ascontiguousarray(image_u8))).to(dev)
+    mask = torch.from_numpy(mask_bool.astype(np.float32)).to(dev)
+    prompt_embeds, pooled = prompt_embeds.to(dev), pooled.to(dev)
     if prompt_embeds.shape[0] != B:
         prompt_embeds, pooled = prompt_embeds.expand(B, -1, -1), pooled.expand(B, -1)
     start = executed_start(num_steps, strength)
@@ -64,8 +71,8 @@ def fill(p_flux, cfg, p_vae, image_u8: np.ndarray, mask_bool: np.ndarray, prompt
 
     def draw(shape):
         if gens is None:
-            return torch.randn(shape, generator=generator, dtype=torch.bfloat16)
-        return torch.cat([torch.randn((1,) + tuple(shape[1:]), generator=g, dtype=torch.bfloat16) for g in gens])
+            return torch.randn(tuple(shape), generator=generator, dtype=torch.bfloat16).to(dev)
+        return torch.cat([torch.randn((1,) + tuple(shape[1:]), generator=g, dtype=torch.bfloat16) for g in gens]).to(dev)
 
     def vae_sample(x):
         mean, logvar = OV.encoder(x, p_vae).chunk(2, dim=1)
@@ -78,7 +85,9 @@ def fill(p_flux, cfg, p_vae, image_u8: np.ndarray, mask_bool: np.ndarray, prompt
     latents = s0 * noise + (1.0 - s0) * image_latents
     masked = OF.pack_latents(vae_sample(img * (1.0 - mask[:, None])))
     cond = torch.cat([masked, pack_mask(mask)], dim=-1)
-    x = OF.sample(p_flux, cfg, latents, prompt_embeds.float(), pooled.float(), guidance, num_steps, h // 2, w // 2,
-                  extra_cond=cond, start_step=start)
+    # the pipeline holds latents / conditioning in the transformer dtype (bf16 in the reference: the scale_noise blend and
+    # the masked-image latents are rounded once here); a no-op for the fp32 oracle
+    x = OF.sample(p_flux, cfg, latents.to(flux_dtype), prompt_embeds.to(flux_dtype), pooled.to(flux_dtype), guidance,
+                  num_steps, h // 2, w // 2, extra_cond=cond.to(flux_dtype), start_step=start)
     lat = OF.unpack_latents(x, h, w)
-    return lat, OV.postprocess_u8(OV.decode_latents(lat, p_vae))
+    return lat, OV.postprocess_u8(OV.decode_latents(lat.float(), p_vae))
