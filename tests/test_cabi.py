@@ -40,6 +40,29 @@ def test_library_targets_sm100a_and_uses_bulk_copy(lib):
     assert "UBLKCP" in scan  # cp.async.bulk staging of the corpus rows
 
 
+def test_hot_kernels_are_blackwell_native_sass(lib):
+    """the GEMM and attention kernels carry tcgen05 MMA (UTCHMMA), TMEM loads / stores (LDTM / STTM), TMA
+    tensor loads (UTMALDG) and tcgen05.commit barriers (UTCBAR); the CTA-pair GEMM uses the .2CTA forms. Per-kernel
+    counts are committed under profiles/r02_sass_summary.txt (scripts/sass_summary.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sass_summary", str(REPO / "scripts" / "sass_summary.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    counts = mod.kernel_counts()
+    gemm = {k: c for k, c in counts.items() if "gemm_bf16_tcgen05" in k}
+    attn = {k: c for k, c in counts.items() if "attention_tcgen05_kernel" in k}
+    assert len(gemm) >= 4 and len(attn) >= 2
+    for name, c in {**gemm, **attn}.items():
+        assert c["UTCHMMA"] >= 4 and c["LDTM"] >= 4 and c["UTMALDG"] >= 2 and c["UTCBAR"] >= 3, (name, dict(c))
+        assert c["HMMA"] == 0, (name, "legacy mma.sync in a tcgen05 kernel")
+    for name, c in attn.items():
+        assert c["STTM"] >= 1 and c["FFMA2"] >= 32, (name, dict(c))          # P written back to TMEM; packed fp32x2 softmax
+    pair = [c for k, c in gemm.items() if "2cta" in k]
+    assert pair and all(c["UTCHMMA.2CTA"] >= 4 and c["UTCBAR.2CTA.MULTICAST"] >= 1 for c in pair)
+    summary = (REPO / "profiles" / "r02_sass_summary.txt").read_text()
+    assert "UTCHMMA" in summary and "attention_tcgen05_kernel" in summary
+
+
 def test_no_device_is_reported_not_faked(lib):
     import ctypes as C
     import torch
