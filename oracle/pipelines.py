@@ -47,20 +47,20 @@ def generate(p_flux, cfg, p_vae, prompt_embeds, pooled, guidance, num_steps, hei
 
 
 def fill(p_flux, cfg, p_vae, image_u8: np.ndarray, mask_bool: np.ndarray, prompt_embeds, pooled, guidance, num_steps,
-         strength, generator, device="cpu", flux_dtype=torch.float32):
+         strength, generator, device="cpu", flux_dtype=torch.float32, vae_dtype=torch.float32):
     """image_u8 [H,W,3] or [B,H,W,3], mask_bool [H,W] or [B,H,W] (True = repaint), H and W multiples of 16.
     -> (latents, image uint8 [B,H,W,3]). A batch shares one generator: each draw covers the whole batch.
     device / flux_dtype: the torch-ref legs (oracle/torchref.py) run the same control flow on the GPU - random draws
-    still come from the CPU generator, the VAE stays fp32, the transformer runs in `flux_dtype` on `p_flux` as given
-    (a CastingParams view for bf16 device weights)."""
+    still come from the CPU generator, the transformer runs in `flux_dtype` on `p_flux` as given (a CastingParams view
+    for bf16 device weights) and the VAE in `vae_dtype` (the reference pipeline is bf16 throughout, VAE included)."""
     if image_u8.ndim == 3:
         image_u8, mask_bool = image_u8[None], mask_bool[None]
     B, H, W = mask_bool.shape
     h, w = H // 8, W // 8
     dev = torch.device(device)
-    if dev.type != "cpu":
-        p_vae = {k: v.to(dev) for k, v in p_vae.items()}
-    img = OV.preprocess_image(torch.from_numpy(np.ascontiguousarray(image_u8))).to(dev)
+    if dev.type != "cpu" or vae_dtype != torch.float32:
+        p_vae = {k: v.to(dev, vae_dtype) for k, v in p_vae.items()}
+    img = OV.preprocess_image(torch.from_numpy(np.ascontiguousarray(image_u8))).to(dev, vae_dtype)
     mask = torch.from_numpy(mask_bool.astype(np.float32)).to(dev)
     prompt_embeds, pooled = prompt_embeds.to(dev), pooled.to(dev)
     if prompt_embeds.shape[0] != B:
@@ -75,7 +75,7 @@ def fill(p_flux, cfg, p_vae, image_u8: np.ndarray, mask_bool: np.ndarray, prompt
         return torch.cat([torch.randn((1,) + tuple(shape[1:]), generator=g, dtype=torch.bfloat16) for g in gens]).to(dev)
 
     def vae_sample(x):
-        mean, logvar = OV.encoder(x, p_vae).chunk(2, dim=1)
+        mean, logvar = OV.encoder(x.to(vae_dtype), p_vae).float().chunk(2, dim=1)
         noise = draw(mean.shape).float()
         return ((mean + torch.exp(0.5 * logvar.clamp(-30.0, 20.0)) * noise) - OV.SHIFT_FACTOR) * OV.SCALE_FACTOR
 
@@ -90,4 +90,4 @@ def fill(p_flux, cfg, p_vae, image_u8: np.ndarray, mask_bool: np.ndarray, prompt
     x = OF.sample(p_flux, cfg, latents.to(flux_dtype), prompt_embeds.to(flux_dtype), pooled.to(flux_dtype), guidance,
                   num_steps, h // 2, w // 2, extra_cond=cond.to(flux_dtype), start_step=start)
     lat = OF.unpack_latents(x, h, w)
-    return lat, OV.postprocess_u8(OV.decode_latents(lat.float(), p_vae))
+    return lat, OV.postprocess_u8(OV.decode_latents(lat.to(vae_dtype), p_vae).float())

@@ -32,6 +32,16 @@ def bf(p):
     return {k: v.bfloat16().float() for k, v in p.items()}
 
 
+def assert_image_close(got_pil, want_u8, what):
+    """Decoded-image bar of SURVEY 8c in u8 steps: max-abs <= 4/255. Here the product (bf16 transformer AND bf16 VAE, the
+    reference's dtypes) is held against the fp32 CPU oracle, so the bar is applied to 99.9 % of the pixel values, with the
+    absolute maximum <= 8 and the mean <= 1 (a u8 rounding boundary can add a step anywhere)."""
+    d = np.abs(np.asarray(got_pil).astype(np.int32) - want_u8.numpy().astype(np.int32))
+    q = float(np.quantile(d, 0.999))
+    print(f"{what}: image |diff| u8 max {int(d.max())} mean {d.mean():.3f} p99.9 {q:.1f}")
+    assert q <= 4 and d.max() <= 8 and d.mean() <= 1.0, (what, int(d.max()), float(d.mean()), q)
+
+
 def test_redux_prior_matches_oracle(lib):
     from domain_rag_b200 import redux as R
     from domain_rag_b200 import siglip as S
@@ -72,10 +82,9 @@ def test_generate_and_fill_match_oracle(lib):
     want_lat, want_img = OP.generate(p, ocfg, p_vae, ctx, pooled, 2.5, T, H, W, torch.Generator("cpu").manual_seed(0))
     assert len(out.images) == 1 and out.images[0].size == (W, H) and out.steps_run == T
     assert rel_l2(out.latents.cpu(), want_lat) < 3e-2
-    diff = np.abs(np.asarray(out.images[0]).astype(np.int32) - want_img[0].numpy().astype(np.int32))
-    assert diff.mean() < 3.0, diff.mean()
+    assert_image_close(out.images[0], want_img[0], "generate")
 
-    # FluxFillPipeline (strength 0.7 of 3 steps -> 2 executed steps), image 70x100 -> resized to 64x96
+    # FluxFillPipeline (strength 0.6 of 3 steps -> start int(3 - 1.8) = 1 -> 2 executed steps), image 70x100 -> resized to 64x96
     ocfg, cfg = OF.FluxConfig(in_channels=384, **FLUX_SMALL), F.FluxConfig(in_channels=384, **FLUX_SMALL)
     p = bf(OF.init_params(ocfg, seed=3002))
     fill = F.FluxFillPipeline(F.FluxTransformer(cfg, p, max_batch=1, max_img_tokens=(H // 16) * (W // 16), txt_tokens=24), vae)
@@ -84,16 +93,15 @@ def test_generate_and_fill_match_oracle(lib):
     mask, _ = generate_outpaint_mask(image, [(30, 20, 25, 30)])
     res = fill(prompt_embeds=ctx, pooled_prompt_embeds=pooled, image=image, mask_image=mask, height=image.height,
                width=image.width, guidance_scale=30.0, num_inference_steps=T, generator=torch.Generator("cpu").manual_seed(7),
-               strength=0.7)
+               strength=0.6)
     assert res.steps_run == 2 and res.images[0].size == (W, H)
     img_r = np.asarray(image.convert("RGB").resize((W, H), Image.LANCZOS))
     mask_r = np.asarray(mask.resize((W, H), Image.LANCZOS)) >= 128
-    want_lat, want_img = OP.fill(p, ocfg, p_vae, img_r, mask_r, ctx, pooled, 30.0, T, 0.7, torch.Generator("cpu").manual_seed(7))
+    want_lat, want_img = OP.fill(p, ocfg, p_vae, img_r, mask_r, ctx, pooled, 30.0, T, 0.6, torch.Generator("cpu").manual_seed(7))
     assert rel_l2(res.latents.cpu(), want_lat) < 4e-2, rel_l2(res.latents.cpu(), want_lat)
-    diff = np.abs(np.asarray(res.images[0]).astype(np.int32) - want_img[0].numpy().astype(np.int32))
-    assert diff.mean() < 3.0, diff.mean()
+    assert_image_close(res.images[0], want_img[0], "fill")
     with pytest.raises(ValueError):
-        fill(prompt_embeds=ctx, pooled_prompt_embeds=pooled, image=image, mask_image=mask, num_inference_steps=3, strength=0.1)
+        fill(prompt_embeds=ctx, pooled_prompt_embeds=pooled, image=image, mask_image=mask, num_inference_steps=3, strength=0.0)
 
 
 def test_fill_batch_of_compositions_matches_oracle(lib):
@@ -120,8 +128,7 @@ def test_fill_batch_of_compositions_matches_oracle(lib):
     want_lat, want_img = OP.fill(p, ocfg, p_vae, img_r, mask_r, ctx, pooled, 30.0, T, 1.0, torch.Generator("cpu").manual_seed(9))
     assert rel_l2(res.latents.cpu(), want_lat) < 4e-2, rel_l2(res.latents.cpu(), want_lat)
     for i in range(2):
-        diff = np.abs(np.asarray(res.images[i]).astype(np.int32) - want_img[i].numpy().astype(np.int32))
-        assert diff.mean() < 3.0, diff.mean()
+        assert_image_close(res.images[i], want_img[i], f"fill batch row {i}")
     with pytest.raises(ValueError):
         fill(prompt_embeds=ctx, pooled_prompt_embeds=pooled, image=images * 2, mask_image=masks * 2, num_inference_steps=T)
 
@@ -142,7 +149,7 @@ def test_fill_batch_with_generator_list_equals_sequential_calls(lib):
     image = synth_image(5, H, W)
     mask, _ = generate_outpaint_mask(image, [(20, 16, 40, 30)])
     seeds = [101, 202, 303]
-    kw = dict(height=H, width=W, guidance_scale=30.0, num_inference_steps=T, strength=0.7)
+    kw = dict(height=H, width=W, guidance_scale=30.0, num_inference_steps=T, strength=0.6)
     batch = fill(prompt_embeds=ctx, pooled_prompt_embeds=pooled, image=[image] * 3, mask_image=[mask] * 3,
                  generator=[torch.Generator("cpu").manual_seed(s) for s in seeds], **kw)
     assert batch.latents.shape[0] == 3 and len(batch.images) == 3 and batch.steps_run == 2
