@@ -408,6 +408,7 @@ def secondary(pipes, rank, world, local, args):
                    "roofline": {"bound": "hbm", "achieved": pt["kernel_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                 "frac": round(pt["kernel_gbs"] / peaks["hbm_gbs"], 4), "kernel": "ip_scan_topk_kernel",
                                 "kernel_ms": pt["kernel_ms"], "traffic": bench_scan.scan_traffic_from_profile()},
+                   "exchange": pt["exchange"], "nccl_ms_per_search": pt["nccl_ms_per_search"],
                    "verified_sharded_equals_single": pt["verified_sharded_equals_single"]}
     sec["c2"] = bench_retrieve.measure_compact(rank, world, local)
     return sec

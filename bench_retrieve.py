@@ -32,23 +32,24 @@ def vit_flops_per_image(cfg) -> float:
 
 def c2_workload(model: str, embed_batch: int) -> str:
     """config.workload of the retrieve line - shared by the b200 arm and the reference arm."""
-    return (f"C2 per GPU: {N_CORPUS} synthetic 224^2 images -> CLIP {model} embed (batches of {embed_batch}) + "
+    return (f"C2 per GPU: {N_CORPUS} synthetic 224^2 images (uint8 pixels, normalised on the GPU) -> CLIP {model} embed (batches of {embed_batch}) + "
             f"L2 normalise -> resident fp32 index shard; {N_QUERY} queries -> exact top-{TOP_K} "
             f"(sharded: all-gather of per-shard top-k) -> ResNet-50-stem style statistics of "
             f"{N_QUERY}x(1+{TOP_K}) 256^2 images; random-init weights")
 
 
-def synth_images(n, res, seed, device, chunk=500):
-    """Preprocessed image tensors fp32 [n,3,res,res] (what `preprocess(PIL)` stacks to), generated on the device:
-    low-frequency structure + noise so embeddings are spread out."""
+def synth_images(n, res, seed, device, chunk=500, u8=False):
+    """Image tensors [n,3,res,res] generated on the device (low-frequency structure + noise so embeddings are spread out):
+    fp32 = what `preprocess(PIL)` stacks to; u8 = the resized / cropped uint8 pixels of the ingest path (`preprocess_u8`)."""
     import torch
     g = torch.Generator(device=device).manual_seed(seed)
-    out = torch.empty((n, 3, res, res), dtype=torch.float32, device=device)
+    out = torch.empty((n, 3, res, res), dtype=torch.uint8 if u8 else torch.float32, device=device)
     for i in range(0, n, chunk):
         m = min(chunk, n - i)
         low = torch.randn((m, 3, 8, 8), generator=g, device=device)
-        out[i:i + m] = torch.nn.functional.interpolate(low, size=(res, res), mode="bilinear") \
+        x = torch.nn.functional.interpolate(low, size=(res, res), mode="bilinear") \
             + 0.3 * torch.randn((m, 3, res, res), generator=g, device=device)
+        out[i:i + m] = (x * 50 + 128).clamp_(0, 255).to(torch.uint8) if u8 else x
     return out
 
 
@@ -69,8 +70,8 @@ def measure(rank, world, local, MODEL, EMBED_BATCH, steps, warmup, with_e2e=True
     model, _ = clip.load(MODEL, device=dev, seed=2000)
     cfg = clip.CONFIGS[MODEL]
     stem = ResNetEncoder(seed=2000).to(dev).eval()
-    corpus = synth_images(N_CORPUS, cfg.image, 1001 + rank, dev)
-    queries = synth_images(N_QUERY, cfg.image, 1002, dev)
+    corpus = synth_images(N_CORPUS, cfg.image, 1001 + rank, dev, u8=True)     # uint8 ingest
+    queries = synth_images(N_QUERY, cfg.image, 1002, dev, u8=True)
     style_imgs = synth_images(N_QUERY * (1 + TOP_K), 256, 1003, dev).mul_(0.2).add_(0.5).clamp_(0, 1)  # [707,3,256,256] in [0,1]
     torch.cuda.synchronize()
 
@@ -141,7 +142,7 @@ def measure(rank, world, local, MODEL, EMBED_BATCH, steps, warmup, with_e2e=True
     m["stem_bytes"] = style_imgs.shape[0] * (3 * 256 * 256 * 4 + 128 * 4)        # 786 432 B in + 512 B out per image
 
     if with_e2e:            # end to end: pinned host tensors in, ranked lists out
-        corpus_h = torch.empty(corpus.shape, dtype=torch.float32, pin_memory=True)
+        corpus_h = torch.empty(corpus.shape, dtype=corpus.dtype, pin_memory=True)
         corpus_h.copy_(corpus)
         queries_h, style_h = queries.cpu().pin_memory(), style_imgs.cpu().pin_memory()
         job(corpus_h, queries_h, style_h, True)
@@ -153,7 +154,7 @@ def measure(rank, world, local, MODEL, EMBED_BATCH, steps, warmup, with_e2e=True
         B.barrier(world)
         m["e2e_s"] = B.max_over_ranks(time.perf_counter() - t0, world) / n_e2e
         assert len(ranked) == N_QUERY and len(ranked[0]) == TOP_K and ranked[0][0]["rank"] == 1
-        m["h2d"] = (corpus_h.numel() + queries_h.numel() + style_h.numel()) * 4
+        m["h2d"] = corpus_h.numel() * corpus_h.element_size() + queries_h.numel() * queries_h.element_size() + style_h.numel() * 4
     return m
 
 
@@ -189,7 +190,7 @@ def run(args):
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": c2_workload(MODEL, EMBED_BATCH),
-                   "l2_policy": "6 GB of images stream through per step (>> 126 MB L2)",
+                   "l2_policy": "1.5 GB of uint8 images + ~90 GB of activations stream through per step (>> 126 MB L2)",
                    "flops_per_image": vit_flops_per_image(cfg),
                    "achieved_tflops": round(flops / (ms_per_step * 1e-3) / 1e12, 1),
                    "whole_job_frac_of_tensor_peak": round(flops / (ms_per_step * 1e-3) / 1e12 / peak, 4)},

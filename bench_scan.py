@@ -91,10 +91,25 @@ def measure(rank, world, local, n, d, nq, k, steps, warmup, flush_l2=False, e2e=
     q_host = q_dev.cpu().pin_memory()
     flush = torch.empty(2 * L2_BYTES // 4, dtype=torch.float32, device=dev) if flush_l2 else None
 
+    # exchange step at world > 1: the packed NCCL all-gather + merge kernel is timed first (nccl_ms_per_search), then the
+    # fused NVLink peer-memory kernel, which the line reports when symmetric memory is available on this box
+    nccl_ms = None
+    results = []
+    if world > 1:
+        for _ in range(max(warmup, 3)):
+            six.search(q_dev, k)
+        barrier(world)
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        for _ in range(steps):
+            results.append(six.search(q_dev, k))
+        n1.record()
+        barrier(world)
+        nccl_ms = max_over_ranks(n0.elapsed_time(n1), world) / steps
+        six.enable_p2p()
     for _ in range(max(warmup, 3)):
         six.search(q_dev, k)
     barrier(world)
-    results = []
     _lib.launch_count(reset=True)
     if flush is None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -163,6 +178,8 @@ def measure(rank, world, local, n, d, nq, k, steps, warmup, flush_l2=False, e2e=
            "gbs": round(alg * world / (ms * 1e-3) / 1e9, 1), "kernel_gbs": round(alg / (kern_avg * 1e-3) / 1e9, 1),
            "e2e_gbs": None if e2e_s is None else round(alg * world / e2e_s / 1e9, 1),
            "l2": "flushed between searches" if flush is not None else "corpus larger than L2",
+           "exchange": six.exchange if world > 1 else None,
+           "nccl_ms_per_search": None if nccl_ms is None else round(nccl_ms, 4),
            "launches": int(n_launches), "grid": geo["grid"], "ring_stages": geo["stages"],
            "rows_per_stage": geo["rows_per_stage"], "nq_batch": geo["nq_batch"],
            "verified_sharded_equals_single": verified}
@@ -177,6 +194,7 @@ def _line(pt, world, steps, warmup, clocks, peaks, extra_cfg=None):
     cfg = {"workload": f"C5 scan: {n} x {d} fp32 embeddings per GPU, nq={nq}, top-{k}; index row-sharded, all-gather of "
                        f"per-shard top-k", "l2_policy": pt["l2"] + f" ({alg / 1e6:.0f} MB per GPU vs 126 MB)",
            "grid": pt["grid"], "ring_stages": pt["ring_stages"], "rows_per_stage": pt["rows_per_stage"],
+           "exchange": pt["exchange"], "nccl_ms_per_search": pt["nccl_ms_per_search"],
            "verified_sharded_equals_single": pt["verified_sharded_equals_single"]}
     cfg.update(extra_cfg or {})
     return {"metric": METRIC, "value": pt["gbs"], "unit": "GB/s", "n_gpus": world, "steps": steps, "warmup": warmup,

@@ -58,6 +58,13 @@ SIGNATURES = {
     "drag_vit_patchify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "drag_vit_assemble": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p]),
+    "drag_topk_exchange_buffer_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, c_i64_p]),
+    "drag_topk_exchange_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "drag_vit_create": (C.c_int, [C.c_void_p, c_void_pp]),
+    "drag_vit_destroy": (C.c_int, [C.c_void_p]),
+    "drag_vit_set_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "drag_vit_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "drag_flux_create": (C.c_int, [C.c_void_p, c_void_pp]),
     "drag_flux_destroy": (C.c_int, [C.c_void_p]),
     "drag_flux_set_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),

@@ -6,9 +6,12 @@
 
 `load` returns (model, preprocess) with the same call shapes. Weights: an OpenAI-format state dict
 (`visual.*` keys, e.g. from a real checkpoint) or, with no checkpoints offline, a seeded random init.
-Every matmul runs on the tcgen05 GEMM (patch embedding as patchify + GEMM since stride == kernel),
-attention on the tcgen05 attention kernel (head dim 64), LayerNorm / QuickGELU / residual adds are
-fused kernels or GEMM epilogues. No PyTorch arithmetic and no CPU path.
+The whole tower runs inside ONE C call per batch (drag_vit_encode, csrc/vit_engine.cu): every matmul on the
+tcgen05 GEMM (patch embedding as patchify + GEMM since stride == kernel), attention on the tcgen05 attention
+kernel (head dim 64), LayerNorm / QuickGELU / residual adds as fused kernels or GEMM epilogues. `encode_image`
+takes the normalised float tensor `preprocess` returns (the reference contract) or raw uint8 pixels
+(`preprocess_u8`: same resize / crop on the host, ToTensor + Normalize on the GPU - a quarter of the PCIe bytes,
+bit-identical patches). No PyTorch arithmetic and no CPU path.
 """
 from __future__ import annotations
 
@@ -16,6 +19,8 @@ from dataclasses import dataclass
 from typing import Dict, Optional
 
 import torch
+
+import ctypes as C
 
 from . import _lib, ops
 
@@ -74,11 +79,25 @@ def random_state(cfg: ViTConfig, seed: int = 2000) -> Dict[str, torch.Tensor]:
     return s
 
 
-class CLIPVisual:
-    """Image tower of CLIP; `encode_image` mirrors clip.model.CLIP.encode_image."""
+# pointer order of drag_vit_set_weights: 8 globals, then 12 per block
+ENGINE_GLOBALS = ("conv_w", "cls", "pos", "ln_pre.weight", "ln_pre.bias", "ln_post.weight", "ln_post.bias", "proj_t")
+ENGINE_BLOCK = ("ln_1.weight", "ln_1.bias", "attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight",
+                "attn.out_proj.bias", "ln_2.weight", "ln_2.bias", "mlp.c_fc.weight", "mlp.c_fc.bias", "mlp.c_proj.weight",
+                "mlp.c_proj.bias")
+ENGINE_ORDER = ENGINE_GLOBALS + tuple("blocks.<i>." + n for n in ENGINE_BLOCK)
 
-    def __init__(self, cfg: ViTConfig, state: Dict[str, torch.Tensor], device):
-        _lib.load()
+
+class _VitConfigC(C.Structure):
+    _fields_ = [("width", C.c_int), ("layers", C.c_int), ("heads", C.c_int), ("patch", C.c_int), ("image", C.c_int),
+                ("out_dim", C.c_int), ("max_batch", C.c_int), ("mean", C.c_float * 3), ("std", C.c_float * 3)]
+
+
+class CLIPVisual:
+    """Image tower of CLIP; `encode_image` mirrors clip.model.CLIP.encode_image. Owns the bf16 device weights and one C++
+    engine (activation workspace for `max_batch` images; larger batches are chunked inside the library)."""
+
+    def __init__(self, cfg: ViTConfig, state: Dict[str, torch.Tensor], device, max_batch: int = 512):
+        lib = _lib.load()
         self.cfg, self.device = cfg, torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("CLIPVisual runs only on CUDA (sm_100a); there is no CPU path")
@@ -88,61 +107,53 @@ class CLIPVisual:
         self.kpad = (k + 7) // 8 * 8
         conv = torch.zeros(w, self.kpad)
         conv[:, :k] = state["visual.conv1.weight"].float().reshape(w, k)      # columns (c, py, px)
-        self.conv_w = bf(conv)
-        self.cls = bf(state["visual.class_embedding"])
-        self.pos = bf(state["visual.positional_embedding"])
-        self.ln_pre = (bf(state["visual.ln_pre.weight"]), bf(state["visual.ln_pre.bias"]))
-        self.ln_post = (bf(state["visual.ln_post.weight"]), bf(state["visual.ln_post.bias"]))
-        self.proj_t = bf(state["visual.proj"].float().t())                      # [out, w]
-        self.blocks = []
+        self.weights = {"conv_w": bf(conv), "cls": bf(state["visual.class_embedding"]),
+                        "pos": bf(state["visual.positional_embedding"]),
+                        "ln_pre.weight": bf(state["visual.ln_pre.weight"]), "ln_pre.bias": bf(state["visual.ln_pre.bias"]),
+                        "ln_post.weight": bf(state["visual.ln_post.weight"]), "ln_post.bias": bf(state["visual.ln_post.bias"]),
+                        "proj_t": bf(state["visual.proj"].float().t())}                 # [out, w]
         for i in range(cfg.layers):
             q = f"visual.transformer.resblocks.{i}."
-            self.blocks.append({n: bf(state[q + n]) for n in (
-                "ln_1.weight", "ln_1.bias", "ln_2.weight", "ln_2.bias", "attn.in_proj_weight", "attn.in_proj_bias",
-                "attn.out_proj.weight", "attn.out_proj.bias", "mlp.c_fc.weight", "mlp.c_fc.bias",
-                "mlp.c_proj.weight", "mlp.c_proj.bias")})
+            for n in ENGINE_BLOCK:
+                self.weights[f"blocks.{i}.{n}"] = bf(state[q + n])
+        order = list(ENGINE_GLOBALS) + [f"blocks.{i}.{n}" for i in range(cfg.layers) for n in ENGINE_BLOCK]
+        self.max_batch = int(max_batch)
+        c = _VitConfigC(cfg.width, cfg.layers, cfg.heads, cfg.patch, cfg.image, cfg.out_dim, self.max_batch,
+                        (C.c_float * 3)(*CLIP_MEAN), (C.c_float * 3)(*CLIP_STD))
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.drag_vit_create(C.byref(c), C.byref(self._h)), "drag_vit_create")
+        ptrs = (C.c_void_p * len(order))(*[self.weights[n].data_ptr() for n in order])
+        _lib.check(lib.drag_vit_set_weights(self._h, ptrs, len(order)), "drag_vit_set_weights")
 
     def eval(self):
         return self
 
     @torch.no_grad()
     def encode_image(self, image: torch.Tensor, normalize: bool = False) -> torch.Tensor:
-        """image [B,3,R,R] float (already CLIP-normalised, as `preprocess` produces) -> float32 [B,out_dim]."""
-        cfg, lib = self.cfg, _lib.load()
+        """image [B,3,R,R]: float (already CLIP-normalised, as `preprocess` produces) or uint8 raw pixels (as
+        `preprocess_u8` produces; normalised on the GPU) -> float32 [B,out_dim]."""
+        cfg = self.cfg
         if not image.is_cuda:
             raise RuntimeError("encode_image: input must be a CUDA tensor (no CPU path)")
-        x = image.to(torch.float32).contiguous()
-        B, w, H, L, g = x.shape[0], cfg.width, cfg.heads, cfg.tokens, cfg.grid
-        if x.shape[1:] != (3, cfg.image, cfg.image):
-            raise ValueError(f"expected [B,3,{cfg.image},{cfg.image}], got {tuple(x.shape)}")
-        dev, st = x.device, _lib.current_stream_ptr(x.device)
-        patches = torch.empty((B * g * g, self.kpad), dtype=torch.bfloat16, device=dev)
-        _lib.check(lib.drag_vit_patchify(_lib.ptr(x), _lib.ptr(patches), B, cfg.image, cfg.patch, self.kpad, st),
-                   "drag_vit_patchify")
-        pe = ops.linear(patches, self.conv_w)
-        h = torch.empty((B * L, w), dtype=torch.bfloat16, device=dev)
-        _lib.check(lib.drag_vit_assemble(_lib.ptr(pe), _lib.ptr(self.cls), _lib.ptr(self.pos), _lib.ptr(h), B, g * g,
-                                         w, st), "drag_vit_assemble")
-        ops.layernorm(h, self.ln_pre[0], self.ln_pre[1], eps=1e-5, out=h)
-        y = torch.empty_like(h)
-        q = torch.empty((B, H, L, w // H), dtype=torch.bfloat16, device=dev)
-        k, v = torch.empty_like(q), torch.empty_like(q)
-        a = torch.empty_like(h)
-        u = torch.empty((B * L, 4 * w), dtype=torch.bfloat16, device=dev)
-        for blk in self.blocks:
-            ops.layernorm(h, blk["ln_1.weight"], blk["ln_1.bias"], eps=1e-5, out=y)
-            _lib.check(lib.drag_gemm_qkv_split(_lib.ptr(y), w, _lib.ptr(blk["attn.in_proj_weight"]), w, B * L, w, H,
-                                               w // H, _lib.ptr(blk["attn.in_proj_bias"]), _lib.ptr(q), _lib.ptr(k),
-                                               _lib.ptr(v), L, 0, L, st), "drag_gemm_qkv_split")
-            ops.attention(q, k, v, 0, out1=a)
-            ops.linear(a, blk["attn.out_proj.weight"], blk["attn.out_proj.bias"], mode=ops.EPI_GATE_RESID, resid=h, out=h)
-            ops.layernorm(h, blk["ln_2.weight"], blk["ln_2.bias"], eps=1e-5, out=y)
-            ops.linear(y, blk["mlp.c_fc.weight"], blk["mlp.c_fc.bias"], mode=ops.EPI_QUICK_GELU, out=u)
-            ops.linear(u, blk["mlp.c_proj.weight"], blk["mlp.c_proj.bias"], mode=ops.EPI_GATE_RESID, resid=h, out=h)
-        cls_rows = h.view(B, L, w)[:, 0, :]                                   # strided view, ld = L*w
-        c = ops.layernorm(cls_rows, self.ln_post[0], self.ln_post[1], eps=1e-5)
-        emb = ops.linear(c, self.proj_t, None, mode=ops.EPI_BIAS_F32)
-        return ops.l2_normalize(emb) if normalize else emb
+        if tuple(image.shape[1:]) != (3, cfg.image, cfg.image):
+            raise ValueError(f"expected [B,3,{cfg.image},{cfg.image}], got {tuple(image.shape)}")
+        kind = 1 if image.dtype == torch.uint8 else 0
+        x = image.contiguous() if kind == 1 else image.to(torch.float32).contiguous()
+        B = x.shape[0]
+        out = torch.empty((B, cfg.out_dim), dtype=torch.float32, device=x.device)
+        if B:
+            _lib.check(_lib.load().drag_vit_encode(self._h, _lib.ptr(x), kind, B, _lib.ptr(out), int(normalize),
+                                                   _lib.current_stream_ptr(x.device)), "drag_vit_encode")
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                _lib.load().drag_vit_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
 
 
 class CLIP:
@@ -165,10 +176,24 @@ def _transform(n_px: int):
                       lambda im: im.convert("RGB"), T.ToTensor(), T.Normalize(CLIP_MEAN, CLIP_STD)])
 
 
-def load(name: str = "ViT-B/32", device="cuda", state_dict: Optional[Dict[str, torch.Tensor]] = None, seed: int = 2000):
+def _transform_u8(n_px: int):
+    """The host half of clip._transform only: Resize(bicubic, short side) -> CenterCrop -> RGB -> uint8 CHW. ToTensor and
+    Normalize run on the GPU inside encode_image (same fp32 formula, so the embeddings equal the float path's)."""
+    from torchvision import transforms as T
+    return T.Compose([T.Resize(n_px, interpolation=T.InterpolationMode.BICUBIC), T.CenterCrop(n_px),
+                      lambda im: im.convert("RGB"), T.PILToTensor()])
+
+
+def preprocess_u8(model: "CLIP"):
+    """uint8 ingest transform for `model`: PIL -> uint8 [3,R,R]; stack, pin, one H2D per batch, encode_image."""
+    return _transform_u8(model.visual.cfg.image)
+
+
+def load(name: str = "ViT-B/32", device="cuda", state_dict: Optional[Dict[str, torch.Tensor]] = None, seed: int = 2000,
+         max_batch: int = 512):
     """(model, preprocess) like clip.load(name, device). `state_dict` takes OpenAI `visual.*` keys."""
     if name not in CONFIGS:
         raise RuntimeError(f"Model {name} not found; available models = {available_models()}")
     cfg = CONFIGS[name]
     state = state_dict if state_dict is not None else random_state(cfg, seed)
-    return CLIP(CLIPVisual(cfg, state, device)), _transform(cfg.image)
+    return CLIP(CLIPVisual(cfg, state, device, max_batch=max_batch)), _transform(cfg.image)

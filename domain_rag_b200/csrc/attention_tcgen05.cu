@@ -157,6 +157,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     const int bh = blockIdx.y;
     const int n_tiles = (a.S + AT_TILE - 1) / AT_TILE;
     const bool has_b = PP && (q0 + AT_TILE) < a.S;     // second query tile holds at least one row
+    // The last key tile is as narrow as the sequence end allows: S_x = Q_x K^T runs with N = keys rounded up to 16 and
+    // O_x += P_x V with one k-step per 16 keys; the softmax touches only the 32-column chunks that hold keys. CLIP ViT-L/14
+    // (257 tokens) has ONE key in its third tile: a full-width tile tripled the cost of that key.
+    const int last_keys = a.S - (n_tiles - 1) * AT_TILE;              // 1 .. 128
+    const int last_n16 = (last_keys + 15) & ~15;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmQ);
@@ -233,13 +238,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const uint64_t q_desc0 = umma_desc_k_sw128(smem_u32(smem + Cfg::Q_OFF));
         const uint64_t k_desc0 = umma_desc_k_sw128(smem_u32(smem + Cfg::K_OFF));
         const uint64_t v_desc0 = umma_desc_mn_sw128(smem_u32(smem + Cfg::V_OFF), Cfg::NH > 1 ? AT_HALF_BYTES : 0, 1024);
-        auto issue_qk = [&](int x, int st) {     // S_x = Q_x K^T  (K tile already waited for)
+        const uint32_t idesc_qk_last = umma_idesc_bf16(128, static_cast<uint32_t>(last_n16), 0, 0);
+        auto issue_qk = [&](int x, int st, int j) {     // S_x = Q_x K_j^T  (K tile already waited for)
             const uint64_t qd = q_desc0 + ((x * TILE_BYTES) >> 4), kd = k_desc0 + ((st * TILE_BYTES) >> 4);
+            const uint32_t idesc = (j == n_tiles - 1) ? idesc_qk_last : idesc_qk;
             if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < HD / 16; ++ks) {
                     const uint32_t off = ((ks >> 2) * AT_HALF_BYTES + (ks & 3) * 32) >> 4;
-                    tc_mma_f16(tmem_base + x * 128, qd + off, kd + off, idesc_qk, ks != 0);
+                    tc_mma_f16(tmem_base + x * 128, qd + off, kd + off, idesc, ks != 0);
                 }
                 tc_commit(&s_full[x]);
             }
@@ -248,12 +255,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         // O_x += P_x V, keys [half*64, half*64+64) of the tile   (P_x: packed bf16 in S_x columns [0,64))
         auto issue_pv = [&](int x, int st, int j, int half, bool last) {
             const uint64_t vd = v_desc0 + ((st * TILE_BYTES) >> 4);
+            const int ksteps = (j == n_tiles - 1) ? (last_n16 >> 4) : (AT_TILE / 16);   // 16 keys per k-step
             if (elect_one()) {
 #pragma unroll
                 for (int kk = 0; kk < AT_TILE / 32; ++kk) {    // 16 kv rows per k-step = 2048 B inside each half
                     const int ks = half * (AT_TILE / 32) + kk;
-                    tc_mma_f16_ts(tmem_base + Cfg::O_COL + x * 128, tmem_base + x * 128 + ks * 8, vd + ((ks * 2048) >> 4), idesc_pv,
-                                  (j | ks) != 0);
+                    if (ks < ksteps)
+                        tc_mma_f16_ts(tmem_base + Cfg::O_COL + x * 128, tmem_base + x * 128 + ks * 8, vd + ((ks * 2048) >> 4),
+                                      idesc_pv, (j | ks) != 0);
                 }
                 if (last) tc_commit(&pv_done[x]);
             }
@@ -262,8 +271,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         mbar_wait(q_full, 0);
         mbar_wait(&k_full[0], 0);
         tc_fence_after();
-        issue_qk(0, 0);
-        if (has_b) issue_qk(1, 0);
+        issue_qk(0, 0, 0);
+        if (has_b) issue_qk(1, 0, 0);
         if (elect_one()) tc_commit(&k_empty[0]);
         __syncwarp();
         for (int j = 0; j < n_tiles; ++j) {
@@ -280,7 +289,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             if (more) {
                 mbar_wait(&k_full[nst], npar);
                 tc_fence_after();
-                issue_qk(0, nst);
+                issue_qk(0, nst, j + 1);
             }
             if (has_b) {
                 mbar_wait(&p_half[1], j & 1);
@@ -289,7 +298,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 mbar_wait(&p_full[1], j & 1);
                 tc_fence_after();
                 issue_pv(1, st, j, 1, true);
-                if (more) issue_qk(1, nst);
+                if (more) issue_qk(1, nst, j + 1);
             }
             if (elect_one()) {
                 tc_commit(&v_empty[st]);
@@ -309,14 +318,33 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const uint32_t t_s = t_lane + x * 128;             // S / P
         const uint32_t t_o = t_lane + Cfg::O_COL + x * 128;  // O
         float m = -INFINITY, l = 0.f;
+        // a warp whose 32 query rows all lie past the sequence end (the tail tile of S = 257 holds ONE row) only keeps the
+        // barrier protocol going: its P / O lanes are never stored, so it issues no softmax work at all
+        const bool warp_has_rows = (q0 + x * AT_TILE + quarter * 32) < a.S;
         for (int j = 0; j < n_tiles; ++j) {
             mbar_wait(&s_full[x], j & 1);
             tc_fence_after();
+            if (!warp_has_rows) {
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&p_half[x]);
+                    mbar_arrive(&p_full[x]);
+                }
+                continue;
+            }
             const int kv_valid = a.S - j * AT_TILE;        // columns >= kv_valid are past the sequence end
+            const int cols = (j == n_tiles - 1) ? last_n16 : AT_TILE;   // score columns the MMA wrote (warp-uniform)
             // the whole 128-wide score row of this thread in registers: ONE TMEM pass per key tile
             uint32_t v[AT_TILE];
 #pragma unroll
-            for (int c = 0; c < AT_TILE; c += 32) tmem_ld_32x32_ptr(t_s + c, &v[c]);
+            for (int c = 0; c < AT_TILE; c += 32) {
+                if (c < cols) {
+                    tmem_ld_32x32_ptr(t_s + c, &v[c]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[c + i] = 0xff800000u;
+                }
+            }
             tmem_ld_wait();
             if (kv_valid < AT_TILE) {
 #pragma unroll
@@ -365,18 +393,20 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             // half is still being exponentiated.
 #pragma unroll
             for (int c = 0; c < AT_TILE; c += 32) {
-                uint32_t packed[16];
+                if (c < cols) {                      // chunks past the last key column hold no P (the MMA never reads them)
+                    uint32_t packed[16];
 #pragma unroll
-                for (int pr = 0; pr < 16; ++pr) {            // pairs of row elements
-                    const float2 x = ffma2(make_float2(__uint_as_float(v[c + 2 * pr]), __uint_as_float(v[c + 2 * pr + 1])),
-                                           sc2, nm2);
-                    const float2 e = ((AT_POLY_MASK >> (pr & 7)) & 1) ? ex2_poly2(x)
-                                                                      : make_float2(ex2_approx(x.x), ex2_approx(x.y));
-                    if (pr & 1) sum_b = fadd2(sum_b, e);
-                    else sum_a = fadd2(sum_a, e);
-                    packed[pr] = pack_bf16x2(e);
+                    for (int pr = 0; pr < 16; ++pr) {            // pairs of row elements
+                        const float2 x = ffma2(make_float2(__uint_as_float(v[c + 2 * pr]), __uint_as_float(v[c + 2 * pr + 1])),
+                                               sc2, nm2);
+                        const float2 e = ((AT_POLY_MASK >> (pr & 7)) & 1) ? ex2_poly2(x)
+                                                                          : make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                        if (pr & 1) sum_b = fadd2(sum_b, e);
+                        else sum_a = fadd2(sum_a, e);
+                        packed[pr] = pack_bf16x2(e);
+                    }
+                    tmem_st_32x16(t_s + (c >> 1), packed);
                 }
-                tmem_st_32x16(t_s + (c >> 1), packed);
                 if (c == 32) {                       // keys [0,64) of this tile are in TMEM
                     tmem_st_wait();
                     tc_fence_before();

@@ -7,6 +7,7 @@
 #include "../../include/domainrag_b200.h"
 #include "common.cuh"
 #include "flux_engine.cuh"
+#include "vit_engine.cuh"
 #include "flux_ops.cuh"
 #include "gemm.cuh"
 #include "vae_ops.cuh"
@@ -329,6 +330,40 @@ int drag_vit_patchify(const float* img, void* out, int B, int R, int patch, int 
 int drag_vit_assemble(const void* patch_emb, const void* cls, const void* pos, void* x, int B, int n_patch, int w,
                       void* stream) {
     return vit_assemble(BF(patch_emb), BF(cls), BF(pos), BFM(x), B, n_patch, w, ST(stream));
+}
+
+int drag_topk_exchange_buffer_bytes(int world, int nq_cap, int k_cap, int64_t* bytes) {
+    DRAG_REQUIRE(bytes && world >= 1 && nq_cap >= 1 && k_cap >= 1, "drag_topk_exchange_buffer_bytes: bad arguments");
+    *bytes = static_cast<int64_t>(topk_exchange_buffer_bytes(world, nq_cap, k_cap));
+    return DRAG_OK;
+}
+int drag_topk_exchange_merge(const float* D_loc, const int64_t* I_loc, int nq, int k, void* const* peer_bufs, int world,
+                             int rank, int nq_cap, int k_cap, uint32_t epoch, float* D_dev, int64_t* I_dev, void* stream) {
+    return topk_exchange_merge(D_loc, I_loc, nq, k, peer_bufs, world, rank, nq_cap, k_cap, epoch, D_dev, I_dev, ST(stream));
+}
+
+// ------------------------------------------------------------------------------------ CLIP ViT engine
+int drag_vit_create(const drag_vit_config* cfg, drag_vit_t** out) {
+    DRAG_REQUIRE(cfg && out, "drag_vit_create: null pointer");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(DRAG_ERR_NO_DEVICE, "drag_vit_create: no CUDA device (this library has no CPU path)");
+    VitCfg c;
+    c.width = cfg->width; c.layers = cfg->layers; c.heads = cfg->heads; c.patch = cfg->patch; c.image = cfg->image;
+    c.out_dim = cfg->out_dim; c.max_batch = cfg->max_batch;
+    for (int i = 0; i < 3; ++i) { c.mean[i] = cfg->mean[i]; c.std[i] = cfg->std[i]; }
+    VitEngine* e = nullptr;
+    int rc = vit_create(c, &e);
+    if (rc) return rc;
+    *out = reinterpret_cast<drag_vit_t*>(e);
+    return DRAG_OK;
+}
+int drag_vit_destroy(drag_vit_t* h) { return vit_destroy(reinterpret_cast<VitEngine*>(h)); }
+int drag_vit_set_weights(drag_vit_t* h, const void* const* ptrs, int n) {
+    return vit_set_weights(reinterpret_cast<VitEngine*>(h), ptrs, n);
+}
+int drag_vit_encode(drag_vit_t* h, const void* img, int img_kind, int B, float* out, int l2_normalize, void* stream) {
+    return vit_encode(reinterpret_cast<VitEngine*>(h), img, img_kind, B, out, l2_normalize, ST(stream));
 }
 
 // ------------------------------------------------------------------------------------ flux engine

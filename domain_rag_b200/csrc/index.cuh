@@ -35,6 +35,10 @@ int index_search_device(Index* ix, const float* q, int nq, int k, float* D, int6
 int index_ensure_io(Index* ix, int nq, int k);
 int merge_pairs_device(const float* scores, const int64_t* ids, int nq, int lists, int k_in, int k_out,
                        float* D, int64_t* I, cudaStream_t st);
+// Fused exchange + merge of per-shard top-k lists over NVLink peer memory (topk_exchange.cu).
+size_t topk_exchange_buffer_bytes(int world, int nq_cap, int k_cap);
+int topk_exchange_merge(const float* D_loc, const int64_t* I_loc, int nq, int k, void* const* peer_bufs, int world, int rank,
+                        int nq_cap, int k_cap, uint32_t epoch, float* D, int64_t* I, cudaStream_t st);
 int stem_stats_device(const float* img, int B, int H, int W, const float* w_fold, const float* b_fold,
                       float eps, float* out, cudaStream_t st);
 

@@ -155,10 +155,14 @@ def shard_bounds(n: int, world: int) -> list:
 class ShardedIndexFlatIP:
     """Row-sharded exact IP index: rank r owns rows [lo_r, hi_r) of the global corpus.
 
-    search() = local scan x top-k on every rank -> one all-gather of (score, id) [nq, k] per rank
-    (NCCL on GPUs) -> identical merge on every rank. The merged result is bit-identical to a single
-    index over the whole corpus because per-row scores do not depend on the partition and the merge
-    uses the same (score desc, id asc) order.
+    search() = local scan x top-k on every rank -> exchange of the per-shard (score, id) [nq, k] lists -> identical
+    merge on every rank. The merged result is bit-identical to a single index over the whole corpus because per-row
+    scores do not depend on the partition and the merge uses the same (score desc, id asc) order. Two exchanges:
+      "p2p"  (after enable_p2p(): ranks of ONE node with NVLink peer access) one fused kernel - every rank stores its
+             lists straight into every peer's symmetric buffer, raises a flag, waits for the peers' flags and merges
+             (drag_topk_exchange_merge): no collective launch, no packing kernels;
+      "nccl" one packed all_gather + drag_topk_merge_device (any topology; also the fallback when nq or k exceed the
+             symmetric buffer's capacity).
 
     `local_search` / `merge` default to the CUDA kernels; tests inject oracle callables to exercise
     the partition / id-offset / gather logic under gloo on CPU.
@@ -177,6 +181,48 @@ class ShardedIndexFlatIP:
         self._rows = None
         self.lo = self.hi = 0
         self.ntotal_global = 0
+        self._p2p = None            # (symmetric buffer, handle, ctypes pointer array, nq_cap, k_cap)
+        self._epoch = 0
+        self.exchange = "nccl"
+
+    def enable_p2p(self, group=None, nq_cap: int = 64, k_cap: int = 1024) -> bool:
+        """Collective. Allocate one symmetric buffer per rank (torch.distributed._symmetric_memory: the same allocation
+        mapped into every peer of the node) for the fused NVLink exchange. Returns False (and keeps the NCCL exchange) when
+        symmetric memory is unavailable for this group - e.g. ranks on different nodes."""
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+        if self.world == 1 or self._index is None:
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm
+            lib = _lib.load()
+            nbytes = C.c_int64(0)
+            _lib.check(lib.drag_topk_exchange_buffer_bytes(self.world, nq_cap, k_cap, C.byref(nbytes)),
+                       "drag_topk_exchange_buffer_bytes")
+            dev = torch.device("cuda", self._index.device)
+            buf = symm.empty(int(nbytes.value), dtype=torch.uint8, device=dev)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            ptrs = (C.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+            torch.cuda.synchronize(dev)
+            dist.barrier(group)                      # every rank's flags are zero before anyone pushes
+            self._p2p = (buf, hdl, ptrs, int(nq_cap), int(k_cap))
+            ok = True
+        except Exception as e:                       # noqa: BLE001 - report and keep the NCCL exchange
+            print(f"[ShardedIndexFlatIP] symmetric-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL all_gather")
+            self._p2p = None
+            ok = False
+        # every rank must take the same exchange: agree on the minimum
+        flag = torch.tensor([int(ok)], device=torch.device("cuda", self._index.device))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        ok = bool(flag.item())
+        if not ok:
+            self._p2p = None
+        self._epoch = 0
+        self.exchange = "p2p" if ok else "nccl"
+        return ok
 
     def add_local(self, x_local, lo: int, ntotal_global: int) -> None:
         """Register this rank's shard: rows [lo, lo + len(x_local)) of a corpus of ntotal_global."""
@@ -196,6 +242,15 @@ class ShardedIndexFlatIP:
             D, I = self._local_search(self._rows, q, k, self.lo)
         if self.world == 1:
             return D, I
+        if (self._p2p is not None and self.exchange == "p2p" and q.shape[0] <= self._p2p[3] and k <= self._p2p[4]
+                and self.world * k <= 8192):
+            _, _, ptrs, nq_cap, k_cap = self._p2p
+            self._epoch += 1
+            Do, Io = torch.empty_like(D), torch.empty_like(I)
+            _lib.check(_lib.load().drag_topk_exchange_merge(_lib.ptr(D), _lib.ptr(I), q.shape[0], int(k), ptrs, self.world,
+                                                            self.rank, nq_cap, k_cap, self._epoch, _lib.ptr(Do), _lib.ptr(Io),
+                                                            _lib.current_stream_ptr(D.device)), "drag_topk_exchange_merge")
+            return Do, Io
         if self._all_gather is not None:
             Dg, Ig = self._all_gather(D), self._all_gather(I)
         else:

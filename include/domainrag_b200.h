@@ -65,6 +65,17 @@ int drag_index_last_scan_ms(drag_index_t* h, float* ms);
 int drag_topk_merge_device(const float* scores, const int64_t* ids, int nq, int lists, int k_in, int k_out,
                            float* D_dev, int64_t* I_dev, void* stream);
 
+/* The exchange step of the sharded search as ONE kernel over NVLink peer memory (no NCCL collective): every rank pushes its
+ * per-query (score, id) lists into every peer's symmetric buffer with P2P stores, raises a flag, waits for the peers' flags
+ * and merges - bit-identical to drag_topk_merge_device over an all-gather. peer_bufs: HOST array of `world` device pointers,
+ * entry p = rank p's buffer as mapped into this process (torch.distributed._symmetric_memory or cudaIpc), each of
+ * drag_topk_exchange_buffer_bytes(world, nq_cap, k_cap) bytes and zero-initialised once. epoch: 1, 2, 3, ... - the same on
+ * every rank, incremented per call (the call is a collective). nq <= nq_cap <= 64 (one resident CTA per query), k <= k_cap,
+ * world * k <= 8192, world <= 16. */
+int drag_topk_exchange_buffer_bytes(int world, int nq_cap, int k_cap, int64_t* bytes);
+int drag_topk_exchange_merge(const float* D_loc, const int64_t* I_loc, int nq, int k, void* const* peer_bufs, int world,
+                             int rank, int nq_cap, int k_cap, uint32_t epoch, float* D_dev, int64_t* I_dev, void* stream);
+
 /* ---- ResNet-50 stem + style statistics --------------------------------------------------------
  * Replaces ResNetEncoder()(x) + calc_mean_std (retrieval/clip100_resnet_style_all_shots.py:51-74,
  * 197-200): img fp32 [B][3][256][256] in [0,1] -> out fp32 [B][128] = cat(mean[64], std[64]),
@@ -125,6 +136,25 @@ int drag_vit_patchify(const float* img, void* out, int B, int R, int patch, int 
 /* x[b][0] = class_embedding + pos[0]; x[b][1+i] = patch_emb[b][i] + pos[1+i]  (bf16 [B][n_patch+1][w]). */
 int drag_vit_assemble(const void* patch_emb, const void* cls, const void* pos, void* x, int B, int n_patch, int w,
                       void* stream);
+
+/* ---- CLIP ViT image tower (one call per batch) -----------------------------------------------------
+ * model.encode_image(x) [+ x / x.norm(dim=-1)] of the reference's embedding loops (retrieval/clip100_resnet_style_all_shots.py:
+ * 161-177, 270-296, 326-349; model from clip.load at :209): the whole tower - patch embedding, class token + positions,
+ * ln_pre, `layers` pre-LN blocks (QKV GEMM -> head-dim-64 attention -> out projection + residual -> QuickGELU MLP +
+ * residual), ln_post of the class token, projection, optional L2 normalise - orchestrated inside the library.
+ * Weights: caller-owned bf16 device pointers in the order of domain_rag_b200/clip.py::ENGINE_ORDER (8 globals, 12 per
+ * block). img_kind 0: fp32 [B][3][image][image] already normalised (what `preprocess` returns); img_kind 1: raw uint8
+ * pixels [B][3][image][image] - ToTensor + Normalize((u8/255 - mean) / std, IEEE fp32) run inside the patch kernel.
+ * out fp32 [B][out_dim]. B may exceed max_batch (processed in chunks of max_batch). */
+typedef struct drag_vit drag_vit_t;
+typedef struct {
+    int width, layers, heads, patch, image, out_dim, max_batch;
+    float mean[3], std[3];
+} drag_vit_config;
+int drag_vit_create(const drag_vit_config* cfg, drag_vit_t** out);
+int drag_vit_destroy(drag_vit_t* h);
+int drag_vit_set_weights(drag_vit_t* h, const void* const* ptrs, int n);
+int drag_vit_encode(drag_vit_t* h, const void* img, int img_kind, int B, float* out, int l2_normalize, void* stream);
 
 /* ---- Flux MMDiT engine --------------------------------------------------------------------------
  * One FluxTransformer2DModel.forward per call (the denoising step inside pipe(...) /

@@ -42,6 +42,29 @@ def test_preprocess_matches_clip_transform(lib):
     assert float((t - ref).abs().max()) < 0.05
 
 
+def test_uint8_ingest_equals_float_preprocess_and_chunks(lib):
+    """uint8 pixels over PCIe + ToTensor/Normalize inside the patch kernel give the SAME embeddings as the
+    reference contract preprocess(PIL) -> float tensor (same fp32 formula -> identical bf16 patches), and a batch larger than
+    the engine's workspace is processed in chunks with identical rows."""
+    from PIL import Image
+    from domain_rag_b200 import clip
+    model, preprocess = clip.load("ViT-B/32", device="cuda", seed=2000, max_batch=4)
+    pre_u8 = clip.preprocess_u8(model)
+    rng = np.random.default_rng(5)
+    ims = [Image.fromarray((rng.random((200 + 13 * i, 260 - 7 * i, 3)) * 255).astype(np.uint8)) for i in range(11)]
+    xf = torch.stack([preprocess(im) for im in ims])
+    xu = torch.stack([pre_u8(im) for im in ims])
+    assert xu.dtype == torch.uint8 and xu.shape == xf.shape == (11, 3, 224, 224)
+    ef = model.encode_image(xf.cuda(), normalize=True)
+    eu = model.encode_image(xu.cuda(), normalize=True)
+    assert torch.equal(ef, eu), float((ef - eu).abs().max())
+    one = torch.cat([model.encode_image(xu[i:i + 1].cuda(), normalize=True) for i in range(11)])
+    assert float((one - eu).abs().max()) <= 2e-3            # batch-1 calls vs chunks of 4 (tile shapes differ)
+    assert model.encode_image(xu[:0].cuda()).shape == (0, 512)
+    with pytest.raises(ValueError):
+        model.encode_image(torch.zeros(1, 3, 32, 32, device="cuda"))
+
+
 def test_c1_embed_then_top10_recall(lib):
     """BASELINE config C1 shape (ViT-L/14 width 768, top-10) on a reduced corpus: retrieval with GPU
     embeddings agrees with retrieval on oracle embeddings (recall@10 overlap; exact index parity is only
@@ -63,6 +86,7 @@ def test_c1_embed_then_top10_recall(lib):
     I = I.cpu().numpy()
     assert [int(r[0]) for r in I] == [0, 1, 2, 3]                 # self-retrieval first
     overlap = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(I, Io)])
+    print(f"C1 recall@10 overlap vs fp32 oracle embeddings: {overlap:.3f}")
     assert overlap >= 0.8, overlap
     # exactness at the scan boundary: same GPU embeddings through the oracle scan give identical indices
     De, Ie = OT.ip_topk(emb.cpu().numpy(), emb[:4].cpu().numpy(), 10)
