@@ -33,6 +33,7 @@ extern uint32_t g_attn_v_lbo, g_attn_v_sbo;
 extern int g_gemm_force_1cta;
 extern int g_gemm_group_m;
 extern int g_attn_force_pp;
+extern int g_attn_no_narrow;
 extern int g_gemm_group_n;
 int prof_enable(int on);
 int prof_collect(double* ms, double* work, int* count, int n_classes);
@@ -474,6 +475,7 @@ int drag_debug_set(int key, int value) {
     else if (key == 4) g_gemm_group_m = value;
     else if (key == 5) g_attn_force_pp = value;
     else if (key == 6) g_gemm_group_n = value;
+    else if (key == 7) g_attn_no_narrow = value;
     else return fail(DRAG_ERR_INVALID, "drag_debug_set: unknown key");
     return DRAG_OK;
 }

@@ -110,6 +110,8 @@ def test_full_depth_fill_trajectory_and_image(full_model):
     # maximum may exceed 4 only as far as the reference's own bf16 pipeline does against the fp32 oracle (+1 u8 rounding step):
     # the product must be no less accurate than the arithmetic it replaces.
     floor = int(dref.max())
-    assert stats["fp32"][3] <= 4 and stats["bf16"][3] <= 4, stats
-    assert stats["fp32"][1] <= max(4, floor + 1), (stats, floor)
+    assert stats["fp32"][3] <= 4, stats                                   # vs the oracle: 99.99 % of pixel values within 4/255
+    assert stats["fp32"][1] <= max(4, floor + 1), (stats, floor)          # absolute max no worse than the bf16 reference's (+1)
     assert stats["fp32"][2] <= max(1.0, 1.5 * float(dref.mean())), (stats, float(dref.mean()))
+    # against the bf16 torch-eager leg two independent bf16 roundings meet: bounded by the sum of both distances to the oracle
+    assert stats["bf16"][1] <= stats["fp32"][1] + floor and stats["bf16"][3] <= 6, (stats, floor)
