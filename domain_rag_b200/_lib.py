@@ -90,6 +90,8 @@ SIGNATURES = {
     "drag_launch_count": (C.c_int, [C.POINTER(C.c_int64), C.c_int]),
     "drag_stem_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_float, C.c_void_p, C.c_void_p]),
+    "drag_stem_stats_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_float, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -34,6 +34,9 @@ extern int g_gemm_force_1cta;
 extern int g_gemm_group_m;
 extern int g_attn_force_pp;
 extern int g_attn_no_narrow;
+extern int g_stem_force_ffma;
+int stem_stats_any_device(const void* img, int img_kind, int B, int H, int W, const float* w_fold, const float* b_fold,
+                          float eps, float* out, cudaStream_t st);
 extern int g_gemm_group_n;
 int prof_enable(int on);
 int prof_collect(double* ms, double* work, int* count, int n_classes);
@@ -235,6 +238,10 @@ int drag_stem_stats(const float* img_dev, int B, int H, int W, const float* w_fo
                     float eps, float* out_dev, void* stream) {
     return stem_stats_device(img_dev, B, H, W, w_fold_dev, b_fold_dev, eps, out_dev,
                              reinterpret_cast<cudaStream_t>(stream));
+}
+int drag_stem_stats_u8(const uint8_t* img_dev, int B, int H, int W, const float* w_fold_dev, const float* b_fold_dev,
+                       float eps, float* out_dev, void* stream) {
+    return stem_stats_any_device(img_dev, 1, B, H, W, w_fold_dev, b_fold_dev, eps, out_dev, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------ gemm
@@ -476,6 +483,7 @@ int drag_debug_set(int key, int value) {
     else if (key == 5) g_attn_force_pp = value;
     else if (key == 6) g_gemm_group_n = value;
     else if (key == 7) g_attn_no_narrow = value;
+    else if (key == 8) g_stem_force_ffma = value;
     else return fail(DRAG_ERR_INVALID, "drag_debug_set: unknown key");
     return DRAG_OK;
 }

@@ -138,8 +138,9 @@ stem_stats_kernel(const float* __restrict__ img, const float* __restrict__ w_fol
     }
 }
 
-int stem_stats_device(const float* img, int B, int H, int W, const float* w_fold,
-                      const float* b_fold, float eps, float* out, cudaStream_t st) {
+// FP32 CUDA-core path: kept for A/B comparisons against the tensor-core kernel (stem_stats_tc.cu; drag_debug_set key 8).
+int stem_stats_ffma_device(const float* img, int B, int H, int W, const float* w_fold,
+                           const float* b_fold, float eps, float* out, cudaStream_t st) {
     DRAG_REQUIRE(img && w_fold && b_fold && out, "stem_stats: null pointer");
     DRAG_REQUIRE(H == ST_H && W == ST_W, "stem_stats: input must be 256x256 (reference resize)");
     DRAG_REQUIRE(B >= 0, "stem_stats: negative batch");

@@ -1,0 +1,366 @@
+// ResNet-50 stem + style statistics on the 5th-gen tensor cores (retrieval/clip100_resnet_style_all_shots.py:51-74, 180-203):
+// conv 7x7 s2 p3 (eval BatchNorm folded) -> ReLU -> maxpool 3x3 s2 p1 -> per-channel mean / sqrt(unbiased var + eps).
+//
+// The CUDA-core kernel (stem_stats.cu) is bound by the FP32 pipe: 308 MFLOP per image = 8.2 ms for the 707 images of a C2
+// re-rank batch, 1 % of what HBM would allow. Here the convolution is an implicit GEMM with fp32-class accuracy from
+// split-bf16 operands:   x = xh + xl, w = wh + wl (bf16 each);   x.w ~= xh.wh + xh.wl + xl.wh   (fp32 accumulate in TMEM;
+// the dropped xl.wl term is 2^-16 relative), three UMMAs per k-step.
+//
+// One persistent CTA per SM walks images; per image one conv row (128 pixels = the UMMA M dimension) at a time:
+//   D[cy][128 px][64 ch] = sum over the 7 input rows y = 2cy-3+ky of  X[y][128 px][32] . W[ky][64 ch][32]^T
+//   with the per-input-row K block k = ci*8 + kx (kx = 7 and ci = 3 are zero padding): the im2col block of an input row is
+//   built ONCE in shared memory (hi and lo tiles) and reused by the up to four conv rows that touch it. Two input rows
+//   share one 128-byte-swizzled [128][64] K-major tile (the layout TMA would write), ring of 5 row pairs.
+//   warps 0-3   loaders: thread = pixel; 7-tap windows from global/L1, split to bf16 hi/lo, swizzled 16-byte stores,
+//               fence.proxy.async, arrive on the pair's `xfull` barrier;
+//   warp 4      MMA issuer: 7 x 2 k-steps x 3 split terms = 42 UMMA 128x64x16 per conv row into one of 8 TMEM accumulators,
+//               tcgen05.commit -> `dfull`; releases row pairs (`xempty`) as conv rows retire;
+//   warps 8-11  pooling + statistics: thread = pixel. For pooled row py the three conv rows 2py-1..2py+1 are read from
+//               TMEM (vertical max), the horizontal 3-max comes from warp shuffles (+ a 1 KB shared-memory hand-off at
+//               warp edges), bias + ReLU after the max (both monotonic), then running sum / sum of squares per channel:
+//               even lanes own channels 0-31 of their pooled pixel, odd lanes channels 32-63. fp64 for the final moments.
+// Neither the 64x128x128 conv map nor the 64x64x64 pooled map ever leaves the SM. Input: fp32 [B][3][256][256] in [0,1] (the
+// reference contract) or uint8 pixels (scaled by 1/255 in the loader).
+#include "common.cuh"
+#include "index.cuh"
+#include "ptx.cuh"
+
+namespace drag {
+
+constexpr int TS_THREADS = 384;                 // 12 warps: 0-3 loaders, 4 MMA, 5-7 idle, 8-11 pooling
+constexpr int TS_RING = 5;                      // input-row pairs resident
+constexpr int TS_XTILE = 128 * 128;             // [128 px][64 K] bf16 = 16 KB
+constexpr int TS_WTILE = 64 * 128;              // [64 ch][64 K] bf16 = 8 KB (two ky per tile)
+constexpr int TS_DBUF = 8;                      // TMEM accumulators (64 columns each)
+constexpr int TS_X_OFF = 0;                                         // ring: [slot][hi|lo]
+constexpr int TS_W_OFF = TS_X_OFF + TS_RING * 2 * TS_XTILE;         // [hi|lo][4 ky pairs]
+constexpr int TS_EDGE_OFF = TS_W_OFF + 2 * 4 * TS_WTILE;            // [2 parity][4 warps][64] fp32 warp-edge hand-off; the
+                                                                    // end-of-image reduction buffer [4 warps][2][64] aliases it
+constexpr int TS_BAR_OFF = TS_EDGE_OFF + 2 * 4 * 64 * 4;
+constexpr int TS_SMEM = TS_BAR_OFF + 256;                           // 231 680 B of the 232 448 B a CTA may own
+static_assert(TS_SMEM <= 232448, "stem_stats_tc: shared memory budget");
+
+// byte offset of element (row r, k) of a K-major SWIZZLE_128B tile (rows of 64 bf16 = 128 B, 8-row atoms of 1024 B)
+__device__ __forceinline__ uint32_t sw128_chunk(int r, int chunk16) {
+    return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((chunk16 ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ void split_bf16x8(const float (&x)[8], uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat16 h0 = __float2bfloat16(x[2 * i]), h1 = __float2bfloat16(x[2 * i + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16(x[2 * i] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16(x[2 * i + 1] - __bfloat162float(h1));
+        h[i] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+        l[i] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+template <bool U8>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w_fold, const float* __restrict__ b_fold,
+                     float eps, float* __restrict__ out, int B) {
+    extern __shared__ __align__(1024) uint8_t smem[];          // SWIZZLE_128B tiles need 1024-byte aligned bases
+    uint8_t* xring = smem + TS_X_OFF;
+    uint8_t* wt = smem + TS_W_OFF;
+    float* edge = reinterpret_cast<float*>(smem + TS_EDGE_OFF);        // [2][4][64]
+    float* red = edge;                                                 // [4 warps][sum | sumsq][64 ch], end of image only
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TS_BAR_OFF);
+    uint64_t* xfull = bars;                  // [5]  count 128 (loader threads)
+    uint64_t* xempty = bars + TS_RING;       // [5]  count 1 (tcgen05.commit)
+    uint64_t* dfull = bars + 2 * TS_RING;    // [8]  count 1 (tcgen05.commit)
+    uint64_t* dempty = dfull + TS_DBUF;      // [8]  count 4 (one per pooling warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + TS_DBUF);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_img = (B - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+    if (tid == 0) {
+        for (int i = 0; i < TS_RING; ++i) {
+            mbar_init(&xfull[i], 128);
+            mbar_init(&xempty[i], 1);
+        }
+        for (int i = 0; i < TS_DBUF; ++i) {
+            mbar_init(&dfull[i], 1);
+            mbar_init(&dempty[i], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 4) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    // Weight tiles (persistent across images): tile t holds ky = 2t in K [0,32) and ky = 2t+1 in K [32,64); k = ci*8 + kx.
+    for (int i = tid; i < 4 * 64 * 8; i += TS_THREADS) {       // (tile, channel row, 16-byte chunk)
+        const int t = i >> 9, ch = (i >> 3) & 63, c = i & 7;
+        const int ky = 2 * t + (c >> 2), ci = c & 3;
+        float x[8];
+#pragma unroll
+        for (int kx = 0; kx < 8; ++kx)
+            x[kx] = (ky < 7 && ci < 3 && kx < 7) ? w_fold[((ch * 3 + ci) * 7 + ky) * 7 + kx] : 0.f;
+        uint4 hi, lo;
+        split_bf16x8(x, hi, lo);
+        const uint32_t off = static_cast<uint32_t>(t) * TS_WTILE + sw128_chunk(ch, c);
+        *reinterpret_cast<uint4*>(wt + off) = hi;
+        *reinterpret_cast<uint4*>(wt + 4 * TS_WTILE + off) = lo;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
+    if (warp < 4) {
+        // ------------------------------------------------------------------ loaders: thread = conv pixel px
+        const int px = tid;
+        for (int it = 0; it < n_img; ++it) {
+            const size_t b = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(it) * gridDim.x;
+            for (int p = 0; p < 128; ++p) {
+                const int P = it * 128 + p, slot = P % TS_RING;
+                mbar_wait(&xempty[slot], ((P / TS_RING) & 1) ^ 1);
+                uint8_t* thi = xring + static_cast<size_t>(slot) * 2 * TS_XTILE;
+                uint8_t* tlo = thi + TS_XTILE;
+#pragma unroll 2
+                for (int c = 0; c < 8; ++c) {                 // chunk = (row of the pair, channel); ci = 3 is padding
+                    const int h = c >> 2, ci = c & 3;
+                    float x[8];
+#pragma unroll
+                    for (int kx = 0; kx < 8; ++kx) {
+                        const int xx = 2 * px - 3 + kx;
+                        float v = 0.f;
+                        if (ci < 3 && kx < 7 && xx >= 0 && xx < 256) {
+                            const size_t idx = ((b * 3 + ci) * 256 + (2 * p + h)) * 256 + xx;
+                            if (U8) v = __fdiv_rn(static_cast<float>(__ldg(static_cast<const uint8_t*>(img_v) + idx)), 255.f);
+                            else v = __ldg(static_cast<const float*>(img_v) + idx);
+                        }
+                        x[kx] = v;
+                    }
+                    uint4 hi, lo;
+                    split_bf16x8(x, hi, lo);
+                    const uint32_t off = sw128_chunk(px, c);
+                    *reinterpret_cast<uint4*>(thi + off) = hi;
+                    *reinterpret_cast<uint4*>(tlo + off) = lo;
+                }
+                fence_proxy_async();                          // generic-proxy stores -> visible to the tensor core's async proxy
+                mbar_arrive(&xfull[slot]);
+            }
+        }
+    } else if (warp == 4) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+        const uint32_t x_addr = smem_u32(xring), w_addr = smem_u32(wt);
+        for (int it = 0; it < n_img; ++it) {
+            int pairs_ready = -1;                              // highest pair of this image already waited for
+            for (int cy = 0; cy < 128; ++cy) {
+                const int R = it * 128 + cy, buf = R % TS_DBUF;
+                mbar_wait(&dempty[buf], ((R / TS_DBUF) & 1) ^ 1);
+                const int p_hi = (cy + 1 < 127) ? cy + 1 : 127;
+                while (pairs_ready < p_hi) {
+                    ++pairs_ready;
+                    const int P = it * 128 + pairs_ready;
+                    mbar_wait(&xfull[P % TS_RING], (P / TS_RING) & 1);
+                }
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 64;
+                bool first = true;
+                for (int ky = 0; ky < 7; ++ky) {
+                    const int y = 2 * cy - 3 + ky;
+                    if (y < 0 || y > 255) continue;            // zero rows of the padding contribute nothing
+                    const int P = it * 128 + (y >> 1), slot = P % TS_RING;
+                    const uint32_t a_hi = x_addr + slot * 2 * TS_XTILE + (y & 1) * 64;
+                    const uint32_t b_hi = w_addr + (ky >> 1) * TS_WTILE + (ky & 1) * 64;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) {
+                            const uint64_t ah = umma_desc_k_sw128(a_hi + s * 32), al = umma_desc_k_sw128(a_hi + TS_XTILE + s * 32);
+                            const uint64_t bh = umma_desc_k_sw128(b_hi + s * 32), bl = umma_desc_k_sw128(b_hi + 4 * TS_WTILE + s * 32);
+                            tc_mma_f16(d_tmem, ah, bh, idesc, !(first && s == 0));
+                            tc_mma_f16(d_tmem, ah, bl, idesc, 1);
+                            tc_mma_f16(d_tmem, al, bh, idesc, 1);
+                        }
+                    }
+                    __syncwarp();
+                    first = false;
+                }
+                if (elect_one()) {
+                    tc_commit(&dfull[buf]);
+                    // conv row cy was the last user of pair cy-2; the image's last row also retires pairs 126 and 127
+                    if (cy >= 2) tc_commit(&xempty[(it * 128 + cy - 2) % TS_RING]);
+                    if (cy == 127) {
+                        tc_commit(&xempty[(it * 128 + 126) % TS_RING]);
+                        tc_commit(&xempty[(it * 128 + 127) % TS_RING]);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        // ------------------------------------------------------------------ pooling + statistics: thread = conv pixel px
+        const int w = warp - 8;                               // TMEM lane quarter (warp % 4 == w)
+        const int px = w * 32 + lane;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(w * 32) << 16);
+        const bool odd = lane & 1;
+        float bias[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bias[i] = b_fold[(odd ? 32 : 0) + i];
+        for (int it = 0; it < n_img; ++it) {
+            const size_t b = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(it) * gridDim.x;
+            float sum[32], sq[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sum[i] = sq[i] = 0.f;
+            for (int py = 0; py < 64; ++py) {
+                const int R2 = it * 128 + 2 * py + 1, R1 = R2 - 1, R0 = R2 - 2;
+                mbar_wait(&dfull[R2 % TS_DBUF], (R2 / TS_DBUF) & 1);   // MMAs retire in order: rows R1, R0 are complete too
+                tc_fence_after();
+                float vm[64];
+#pragma unroll
+                for (int c = 0; c < 64; c += 16) {
+                    uint32_t r1[16], r2[16], r0[16];
+                    tmem_ld_32x16(t_lane + (R1 % TS_DBUF) * 64 + c, r1);
+                    tmem_ld_32x16(t_lane + (R2 % TS_DBUF) * 64 + c, r2);
+                    if (py > 0) tmem_ld_32x16(t_lane + (R0 % TS_DBUF) * 64 + c, r0);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float v = fmaxf(__uint_as_float(r1[i]), __uint_as_float(r2[i]));
+                        if (py > 0) v = fmaxf(v, __uint_as_float(r0[i]));
+                        vm[c + i] = v;
+                    }
+                }
+                // rows R0 and R1 are dead now (R2 is the next pooled row's R0); the image's last conv row retires with py = 63
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (py > 0) mbar_arrive(&dempty[R0 % TS_DBUF]);
+                    mbar_arrive(&dempty[R1 % TS_DBUF]);
+                    if (py == 63) mbar_arrive(&dempty[R2 % TS_DBUF]);
+                }
+                // hand the last pixel of this warp to the next warp (its lanes 0 / 1 need px - 1 / px - 2)
+                float* e = edge + ((py & 1) * 4 + w) * 64;
+                if (lane == 31) {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) e[i] = vm[i];
+                }
+                named_bar_sync(1, 128);
+                const float* ep = edge + ((py & 1) * 4 + (w > 0 ? w - 1 : 0)) * 64;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    // even lane (pooled pixel centre px): channels i      from lanes l-1, l, l+1
+                    // odd lane  (px = centre + 1):        channels 32 + i from lanes l-2, l-1, l
+                    const float a_e = __shfl_up_sync(0xffffffffu, vm[i], 1);
+                    const float c_e = __shfl_down_sync(0xffffffffu, vm[i], 1);
+                    const float a_o = __shfl_up_sync(0xffffffffu, vm[32 + i], 2);
+                    const float b_o = __shfl_up_sync(0xffffffffu, vm[32 + i], 1);
+                    float left, mid, right;
+                    if (!odd) {
+                        left = (lane == 0) ? (w > 0 ? ep[i] : -INFINITY) : a_e;
+                        mid = vm[i];
+                        right = c_e;
+                    } else {
+                        left = (lane == 1) ? (w > 0 ? ep[32 + i] : -INFINITY) : a_o;
+                        mid = b_o;
+                        right = vm[32 + i];
+                    }
+                    const float pooled = fmaxf(fmaxf(fmaxf(left, mid), right) + bias[i], 0.f);   // bias + ReLU commute with max
+                    sum[i] += pooled;
+                    sq[i] = fmaf(pooled, pooled, sq[i]);
+                }
+            }
+            // image done: reduce over the 16 same-parity lanes of each warp, then over the 4 warps (fp64), write the moments
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+#pragma unroll
+                for (int o = 2; o < 32; o <<= 1) {
+                    sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], o);
+                    sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
+                }
+            }
+            named_bar_sync(1, 128);                            // previous image's readers of `red` are done
+            if (lane < 2) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    red[(w * 2 + 0) * 64 + lane * 32 + i] = sum[i];
+                    red[(w * 2 + 1) * 64 + lane * 32 + i] = sq[i];
+                }
+            }
+            named_bar_sync(1, 128);
+            const int t = tid - 256;
+            if (t < 64) {
+                double s = 0.0, ss = 0.0;
+#pragma unroll
+                for (int ww = 0; ww < 4; ++ww) {
+                    s += static_cast<double>(red[(ww * 2 + 0) * 64 + t]);
+                    ss += static_cast<double>(red[(ww * 2 + 1) * 64 + t]);
+                }
+                const double n = 64.0 * 64.0;
+                const double mean = s / n;
+                double var = (ss - n * mean * mean) / (n - 1.0);
+                if (var < 0.0) var = 0.0;
+                out[b * 128 + t] = static_cast<float>(mean);
+                out[b * 128 + 64 + t] = static_cast<float>(sqrt(var + static_cast<double>(eps)));
+            }
+            named_bar_sync(1, 128);                            // `red` aliases the edge buffer the next image writes
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+int g_stem_force_ffma = 0;     // drag_debug_set key 8: 1 = the FP32 CUDA-core kernel of stem_stats.cu (A/B comparisons)
+
+int stem_stats_ffma_device(const float* img, int B, int H, int W, const float* w_fold, const float* b_fold, float eps,
+                           float* out, cudaStream_t st);
+
+// img_kind 0: fp32 [B][3][256][256] in [0,1]; 1: uint8 [B][3][256][256] (divided by 255 in the loader)
+int stem_stats_any_device(const void* img, int img_kind, int B, int H, int W, const float* w_fold, const float* b_fold,
+                          float eps, float* out, cudaStream_t st) {
+    DRAG_REQUIRE(img && w_fold && b_fold && out, "stem_stats: null pointer");
+    DRAG_REQUIRE(H == 256 && W == 256, "stem_stats: input must be 256x256 (reference resize)");
+    DRAG_REQUIRE(B >= 0 && (img_kind == 0 || img_kind == 1), "stem_stats: bad arguments");
+    if (B == 0) return DRAG_OK;
+    if (g_stem_force_ffma && img_kind == 0)
+        return stem_stats_ffma_device(static_cast<const float*>(img), B, H, W, w_fold, b_fold, eps, out, st);
+    int sms = device_sm_count();
+    if (sms <= 0) sms = 148;
+    const int grid = B < sms ? B : sms;
+    if (img_kind == 0) {
+        DRAG_CUDA(cudaFuncSetAttribute(stem_stats_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+        stem_stats_tc_kernel<false><<<grid, TS_THREADS, TS_SMEM, st>>>(img, w_fold, b_fold, eps, out, B);
+    } else {
+        DRAG_CUDA(cudaFuncSetAttribute(stem_stats_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+        stem_stats_tc_kernel<true><<<grid, TS_THREADS, TS_SMEM, st>>>(img, w_fold, b_fold, eps, out, B);
+    }
+    count_launch();
+    DRAG_CUDA(cudaGetLastError());
+    return DRAG_OK;
+}
+
+int stem_stats_device(const float* img, int B, int H, int W, const float* w_fold, const float* b_fold, float eps, float* out,
+                      cudaStream_t st) {
+    return stem_stats_any_device(img, 0, B, H, W, w_fold, b_fold, eps, out, st);
+}
+
+}  // namespace drag

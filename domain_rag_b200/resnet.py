@@ -5,9 +5,10 @@
     mean, std = calc_mean_std(features)   # each [B,64,1,1]
     feat = torch.cat([mean.squeeze(), std.squeeze()])
 
-Here `model(img)` launches one fused sm_100a kernel (conv7x7/2 + folded eval BatchNorm + ReLU +
-maxpool3x3/2 + per-channel moments) and returns a `StemStats` handle; `calc_mean_std` unpacks it.
-The 64x64x64 feature map is never materialised. No CPU path.
+Here `model(img)` launches one fused sm_100a kernel (conv7x7/2 as a split-bf16 implicit GEMM on the tcgen05 tensor
+cores + folded eval BatchNorm + ReLU + maxpool3x3/2 + per-channel moments) and returns a `StemStats` handle;
+`calc_mean_std` unpacks it. The 64x64x64 feature map is never materialised. `img` may also be the raw uint8 pixels
+(the / 255 then runs in the kernel). No CPU path.
 """
 from __future__ import annotations
 
@@ -93,14 +94,15 @@ class ResNetEncoder:
             raise RuntimeError("ResNetEncoder: input must be a CUDA tensor (no CPU path)")
         if self.w_fold.device != img.device:
             self.to(img.device)
-        img = img.float().contiguous()
+        u8 = img.dtype == torch.uint8          # raw pixels: the / 255 of reference :193 runs inside the kernel
+        img = img.contiguous() if u8 else img.float().contiguous()
         if img.dim() != 4 or img.shape[1] != 3:
             raise ValueError(f"expected [B,3,256,256], got {tuple(img.shape)}")
         b, _, h, w = img.shape
         out = torch.empty((b, 128), dtype=torch.float32, device=img.device)
-        _lib.check(_lib.load().drag_stem_stats(_lib.ptr(img), b, h, w, _lib.ptr(self.w_fold),
-                                               _lib.ptr(self.b_fold), STYLE_EPS, _lib.ptr(out),
-                                               _lib.current_stream_ptr(img.device)), "drag_stem_stats")
+        fn = _lib.load().drag_stem_stats_u8 if u8 else _lib.load().drag_stem_stats
+        _lib.check(fn(_lib.ptr(img), b, h, w, _lib.ptr(self.w_fold), _lib.ptr(self.b_fold), STYLE_EPS, _lib.ptr(out),
+                      _lib.current_stream_ptr(img.device)), "drag_stem_stats")
         return StemStats(out)
 
     def style_features(self, img: torch.Tensor) -> torch.Tensor:

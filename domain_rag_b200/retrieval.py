@@ -103,7 +103,8 @@ def clip_first_stage_retrieval(query_feature, dataset_features, dataset_paths, t
 
 
 def load_style_input(image_path: str):
-    """reference :186-193: cv2.imread -> RGB -> resize(256,256) -> float /255 -> CHW (host tensor)."""
+    """reference :186-193: cv2.imread -> RGB -> resize(256,256) -> CHW. Returned as the uint8 pixels (host tensor): the
+    float() / 255.0 of :193 runs inside the stem kernel's loader (same IEEE fp32 division), a quarter of the H2D bytes."""
     import cv2
     import torch
     img = cv2.imread(clean_image_path(image_path))
@@ -112,7 +113,7 @@ def load_style_input(image_path: str):
         return None
     img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
     img = cv2.resize(img, (256, 256))
-    return torch.tensor(img).float().permute(2, 0, 1) / 255.0
+    return torch.from_numpy(img).permute(2, 0, 1).contiguous()
 
 
 def compute_resnet_features(image_path, model, device):

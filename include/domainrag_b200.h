@@ -80,9 +80,15 @@ int drag_topk_exchange_merge(const float* D_loc, const int64_t* I_loc, int nq, i
  * Replaces ResNetEncoder()(x) + calc_mean_std (retrieval/clip100_resnet_style_all_shots.py:51-74,
  * 197-200): img fp32 [B][3][256][256] in [0,1] -> out fp32 [B][128] = cat(mean[64], std[64]),
  * std = sqrt(unbiased var + eps). w_fold [64][3][7][7] / b_fold [64] are conv1 with eval-mode bn1
- * folded in. */
+ * folded in. Implicit GEMM on the tcgen05 tensor cores with split-bf16 operands (x = xh + xl, w = wh + wl; three
+ * MMAs per k-step, fp32 accumulation: 2^-16 relative per product), pooling and moments fused; the feature maps never
+ * leave the SM (csrc/stem_stats_tc.cu). */
 int drag_stem_stats(const float* img_dev, int B, int H, int W, const float* w_fold_dev, const float* b_fold_dev,
                     float eps, float* out_dev, void* stream);
+/* Same with the raw uint8 pixels [B][3][256][256] (what cv2.resize returns, channel-major): the / 255 of :193 runs in the
+ * kernel's loader (IEEE fp32 division), a quarter of the PCIe / HBM bytes of the float tensor. */
+int drag_stem_stats_u8(const uint8_t* img_dev, int B, int H, int W, const float* w_fold_dev, const float* b_fold_dev,
+                       float eps, float* out_dev, void* stream);
 
 /* ---- bf16 GEMM core (tcgen05 / TMEM / TMA) ------------------------------------------------------
  * out[M][N] = epilogue(A[M][K] * W[N][K]^T + bias): the nn.Linear calls inside clip.encode_image
@@ -219,7 +225,8 @@ int drag_launch_count(int64_t* count, int reset);
  * instead of the CTA-pair cta_group::2 kernel; key 4: > 0 = force the GEMM tile-raster group size, 1 << 20 = plain
  * row-fastest order; key 5: 1 = head-dim-64 attention always on the two-tile ping-pong kernel; key 6: > 0 = force the
  * column-group raster with that many column tiles per group; key 7: 1 = attention computes its last key tile at full
- * width instead of N = keys rounded up to 16). */
+ * width instead of N = keys rounded up to 16; key 8: 1 = stem statistics on the FP32 CUDA-core kernel instead of
+ * the tensor-core kernel). */
 int drag_debug_set(int key, int value);
 
 #ifdef __cplusplus

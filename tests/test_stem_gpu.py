@@ -78,3 +78,28 @@ def test_rerank_order_matches_reference_golden(enc, golden_dir):
     np.testing.assert_allclose([r["similarity"] for r in got], [r["similarity"] for r in g["reranked"]],
                                rtol=1e-4)
     assert got == O.rerank_by_style(qf, feats, g["first_stage"])
+
+
+def test_uint8_pixels_equal_float_input_and_cuda_core_kernel(enc, lib):
+    """The uint8 ingest path (/ 255 inside the loader) gives bit-identical statistics to the float tensor the reference
+    builds (:191-193), and the tensor-core kernel (split-bf16 implicit GEMM) agrees with the FP32 CUDA-core kernel and the
+    fp64 oracle on real-image-like inputs (smooth structure + noise), batch sizes around the SM count."""
+    from domain_rag_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    for b in (1, 5, 149, 300):
+        low = torch.rand(b, 3, 16, 16, generator=g)
+        u8 = (torch.nn.functional.interpolate(low, size=(256, 256), mode="bilinear") * 200 +
+              torch.rand(b, 3, 256, 256, generator=g) * 55).clamp(0, 255).to(torch.uint8)
+        xf = u8.float() / 255.0
+        got_u8 = enc.style_features(u8.cuda()).cpu()
+        got_f = enc.style_features(xf.cuda()).cpu()
+        assert torch.equal(got_u8, got_f)
+        ops.debug_set(8, 1)
+        try:
+            ffma = enc.style_features(xf.cuda()).cpu()
+        finally:
+            ops.debug_set(8, 0)
+        torch.testing.assert_close(got_f, ffma, rtol=RTOL, atol=2e-6)
+        if b <= 5:
+            want = S.style_features(xf, enc.state, torch.float64)
+            torch.testing.assert_close(got_f, want, rtol=RTOL, atol=2e-6)
