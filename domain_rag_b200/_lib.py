@@ -64,6 +64,7 @@ SIGNATURES = {
     "drag_vit_create": (C.c_int, [C.c_void_p, c_void_pp]),
     "drag_vit_destroy": (C.c_int, [C.c_void_p]),
     "drag_vit_set_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "drag_vit_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "drag_vit_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "drag_flux_create": (C.c_int, [C.c_void_p, c_void_pp]),
     "drag_flux_destroy": (C.c_int, [C.c_void_p]),

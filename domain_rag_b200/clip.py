@@ -84,7 +84,9 @@ ENGINE_GLOBALS = ("conv_w", "cls", "pos", "ln_pre.weight", "ln_pre.bias", "ln_po
 ENGINE_BLOCK = ("ln_1.weight", "ln_1.bias", "attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight",
                 "attn.out_proj.bias", "ln_2.weight", "ln_2.bias", "mlp.c_fc.weight", "mlp.c_fc.bias", "mlp.c_proj.weight",
                 "mlp.c_proj.bias")
-ENGINE_ORDER = ENGINE_GLOBALS + tuple("blocks.<i>." + n for n in ENGINE_BLOCK)
+# ... followed by the LayerNorm-folded operands of the block (CLIPVisual._fold): gamma-scaled weights (bf16) and fp32 s / c
+ENGINE_FOLDED = ("qkv_wf", "qkv_s", "qkv_c", "fc_wf", "fc_s", "fc_c")
+ENGINE_ORDER = ENGINE_GLOBALS + tuple("blocks.<i>." + n for n in ENGINE_BLOCK + ENGINE_FOLDED)
 
 
 class _VitConfigC(C.Structure):
@@ -116,7 +118,13 @@ class CLIPVisual:
             q = f"visual.transformer.resblocks.{i}."
             for n in ENGINE_BLOCK:
                 self.weights[f"blocks.{i}.{n}"] = bf(state[q + n])
-        order = list(ENGINE_GLOBALS) + [f"blocks.{i}.{n}" for i in range(cfg.layers) for n in ENGINE_BLOCK]
+            for tag, ln, lin in (("qkv", "ln_1", "attn.in_proj_"), ("fc", "ln_2", "mlp.c_fc.")):
+                wf, sv, cv = self._fold(state[q + ln + ".weight"], state[q + ln + ".bias"],
+                                        state[q + lin + "weight"], state[q + lin + "bias"])
+                self.weights[f"blocks.{i}.{tag}_wf"] = wf.to(self.device).contiguous()
+                self.weights[f"blocks.{i}.{tag}_s"] = sv.to(self.device).contiguous()
+                self.weights[f"blocks.{i}.{tag}_c"] = cv.to(self.device).contiguous()
+        order = list(ENGINE_GLOBALS) + [f"blocks.{i}.{n}" for i in range(cfg.layers) for n in ENGINE_BLOCK + ENGINE_FOLDED]
         self.max_batch = int(max_batch)
         c = _VitConfigC(cfg.width, cfg.layers, cfg.heads, cfg.patch, cfg.image, cfg.out_dim, self.max_batch,
                         (C.c_float * 3)(*CLIP_MEAN), (C.c_float * 3)(*CLIP_STD))
@@ -125,6 +133,22 @@ class CLIPVisual:
             _lib.check(lib.drag_vit_create(C.byref(c), C.byref(self._h)), "drag_vit_create")
         ptrs = (C.c_void_p * len(order))(*[self.weights[n].data_ptr() for n in order])
         _lib.check(lib.drag_vit_set_weights(self._h, ptrs, len(order)), "drag_vit_set_weights")
+
+    @staticmethod
+    def _fold(gamma, beta, weight, bias):
+        """LayerNorm(x; gamma, beta) @ W^T + b  ==  rstd * (x @ W'^T - mean * s) + c  with W' = W * gamma (rounded to bf16,
+        the GEMM operand), s[n] = sum_k W'[n,k] (of the ROUNDED operand, so a constant row cancels exactly) and
+        c[n] = sum_k beta[k] W[n,k] + b[n]. Both sides start from the bf16 weights the unfused path uses."""
+        W = weight.to(torch.bfloat16).double()
+        g, bt = gamma.to(torch.bfloat16).double(), beta.to(torch.bfloat16).double()
+        wf = (W * g[None, :]).to(torch.bfloat16)
+        s = wf.double().sum(1).float()
+        c = (W @ bt + bias.to(torch.bfloat16).double()).float()
+        return wf, s, c
+
+    def fold_layernorm(self, on: bool = True) -> None:
+        """A/B switch: True (default) = ln_1 / ln_2 folded into the GEMMs around them, False = separate LayerNorm kernels."""
+        _lib.check(_lib.load().drag_vit_set_option(self._h, 1, int(on)), "drag_vit_set_option")
 
     def eval(self):
         return self

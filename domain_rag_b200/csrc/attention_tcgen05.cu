@@ -62,7 +62,6 @@ struct AttnArgs {
     __nv_bfloat16* out1;   // tokens [split, S): row b*(S-split) + s-split, leading dim ld1
     int ld0, ld1, split;
     int S, H;
-    int no_narrow;         // drag_debug_set key 7: 1 = full-width last key tile (A/B comparisons)
     float scale_log2;      // log2(e) / sqrt(head_dim)
 };
 
@@ -132,103 +131,6 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v
         : "memory");
 }
 
-// Softmax of one key tile for this thread's query row (tile x of the CTA): S from TMEM -> running max / lazy rescale of the
-// TMEM-resident O -> P written in place as packed bf16. FULL = all 128 score columns are valid MMA output (every tile but a
-// narrow last one); !FULL = the last key tile was computed with N = cols < 128 (see the kernel): only the 32-column chunks
-// below `cols` are read, exponentiated and stored.
-template <int HD, bool FULL>
-__device__ __forceinline__ void softmax_tile(const AttnArgs& a, int j, int cols, uint32_t t_s, uint32_t t_o, int x, int lane,
-                                             float& m, float& l, uint64_t* p_half, uint64_t* p_full, uint64_t* pv_done) {
-    const int kv_valid = a.S - j * AT_TILE;        // columns >= kv_valid are past the sequence end
-    // the whole 128-wide score row of this thread in registers: ONE TMEM pass per key tile
-    uint32_t v[AT_TILE];
-#pragma unroll
-    for (int c = 0; c < AT_TILE; c += 32) {
-        if (FULL || c < cols) {
-            tmem_ld_32x32_ptr(t_s + c, &v[c]);
-        } else {                                 // no score columns here: the narrow MMA never wrote them
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[c + i] = 0xff800000u;
-        }
-    }
-    tmem_ld_wait();
-    if (kv_valid < AT_TILE) {
-#pragma unroll
-        for (int i = 0; i < AT_TILE; ++i)
-            if (i >= kv_valid) v[i] = 0xff800000u;   // -inf: exp2 -> 0, never the maximum
-    }
-    // four independent chains (the FMNMX3 latency chain was as long as the exponential pass)
-    float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
-    float m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
-    float m2 = fmaxf(__uint_as_float(v[4]), __uint_as_float(v[5]));
-    float m3 = fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7]));
-#pragma unroll
-    for (int i = 8; i < AT_TILE; i += 8) {
-        m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-        m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-        m2 = fmax3(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
-        m3 = fmax3(m3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
-    }
-    m0 = fmaxf(m0, m2);
-    m1 = fmaxf(m1, m3);
-    const float m_new = fmaxf(m, fmaxf(m0, m1) * a.scale_log2);
-    if (__any_sync(0xffffffffu, m_new > m + AT_RESCALE_THRESHOLD)) {
-        const float alpha = ex2_approx(m - m_new);   // 0 on the first tile (m = -inf)
-        if (j > 0) {
-            mbar_wait(&pv_done[x], (j - 1) & 1);     // O_x += P_x(j-1) V_{j-1} has landed
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < HD / 32; ++c) {
-                uint32_t o[32];
-                tmem_ld_32x32(t_o + c * 32, o);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                tmem_st_32x32(t_o + c * 32, o);
-            }
-        }
-        l *= alpha;
-        m = m_new;
-    }
-    const float2 sc2 = splat2(a.scale_log2), nm2 = splat2(-m);
-    float2 sum_a = splat2(0.f), sum_b = splat2(0.f);
-    // P as packed bf16 written IN PLACE over the first 64 columns of S. Packed fp32x2 arithmetic throughout; of
-    // every eight pairs six take their exponentials from the MUFU pipe and two from a Cody-Waite + cubic
-    // polynomial on the FMA pipe (exp2 is the co-bottleneck of the tensor core at head dim 128). The first half
-    // of the row is published on its own barrier so that the P V product of keys [0,64) starts while the second
-    // half is still being exponentiated.
-#pragma unroll
-    for (int c = 0; c < AT_TILE; c += 32) {
-        if (FULL || c < cols) {                  // chunks past the last key column hold no P (the narrow P V never reads them)
-            uint32_t packed[16];
-#pragma unroll
-            for (int pr = 0; pr < 16; ++pr) {            // pairs of row elements
-                const float2 xx = ffma2(make_float2(__uint_as_float(v[c + 2 * pr]), __uint_as_float(v[c + 2 * pr + 1])),
-                                        sc2, nm2);
-                const float2 e = ((AT_POLY_MASK >> (pr & 7)) & 1) ? ex2_poly2(xx)
-                                                                  : make_float2(ex2_approx(xx.x), ex2_approx(xx.y));
-                if (pr & 1) sum_b = fadd2(sum_b, e);
-                else sum_a = fadd2(sum_a, e);
-                packed[pr] = pack_bf16x2(e);
-            }
-            tmem_st_32x16(t_s + (c >> 1), packed);
-        }
-        if (c == 32) {                       // keys [0,64) of this tile are in TMEM
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_half[x]);
-        }
-    }
-    const float2 sum2 = fadd2(sum_a, sum_b);
-    const float sum0 = sum2.x, sum1 = sum2.y;
-    l += sum0 + sum1;
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&p_full[x]);
-}
-
 template <int HD, bool PP>
 __global__ void __launch_bounds__(PP ? AT_THREADS : 256, PP ? 1 : 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -255,11 +157,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     const int bh = blockIdx.y;
     const int n_tiles = (a.S + AT_TILE - 1) / AT_TILE;
     const bool has_b = PP && (q0 + AT_TILE) < a.S;     // second query tile holds at least one row
-    // The last key tile is as narrow as the sequence end allows: S_x = Q_x K^T runs with N = keys rounded up to 16 and
-    // O_x += P_x V with one k-step per 16 keys; the softmax touches only the 32-column chunks that hold keys. CLIP ViT-L/14
-    // (257 tokens) has ONE key in its third tile: a full-width tile tripled the cost of that key.
-    const int last_n16 = ((a.S - (n_tiles - 1) * AT_TILE) + 15) & ~15;     // 16 .. 128
-    const bool narrow_last = last_n16 < AT_TILE && !a.no_narrow;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmQ);
@@ -362,46 +259,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             }
             __syncwarp();
         };
-        const uint32_t idesc_qk_last = umma_idesc_bf16(128, static_cast<uint32_t>(last_n16), 0, 0);
-        auto issue_qk_last = [&](int x, int st) {     // narrow last tile: N = last_n16 keys
-            const uint64_t qd = q_desc0 + ((x * TILE_BYTES) >> 4), kd = k_desc0 + ((st * TILE_BYTES) >> 4);
-            if (elect_one()) {
-#pragma unroll
-                for (int ks = 0; ks < HD / 16; ++ks) {
-                    const uint32_t off = ((ks >> 2) * AT_HALF_BYTES + (ks & 3) * 32) >> 4;
-                    tc_mma_f16(tmem_base + x * 128, qd + off, kd + off, idesc_qk_last, ks != 0);
-                }
-                tc_commit(&s_full[x]);
-            }
-            __syncwarp();
-        };
-        auto issue_pv_last = [&](int x, int st, int j, int half, bool last) {   // one k-step per 16 keys of the narrow tile
-            const uint64_t vd = v_desc0 + ((st * TILE_BYTES) >> 4);
-            const int ksteps = last_n16 >> 4;
-            if (elect_one()) {
-                for (int kk = 0; kk < AT_TILE / 32; ++kk) {
-                    const int ks = half * (AT_TILE / 32) + kk;
-                    if (ks < ksteps)
-                        tc_mma_f16_ts(tmem_base + Cfg::O_COL + x * 128, tmem_base + x * 128 + ks * 8, vd + ((ks * 2048) >> 4),
-                                      idesc_pv, (j | ks) != 0);
-                }
-                if (last) tc_commit(&pv_done[x]);
-            }
-            __syncwarp();
-        };
-        auto qk = [&](int x, int st, int j) {
-            if (narrow_last && j == n_tiles - 1) issue_qk_last(x, st);
-            else issue_qk(x, st);
-        };
-        auto pv = [&](int x, int st, int j, int half, bool last) {
-            if (narrow_last && j == n_tiles - 1) issue_pv_last(x, st, j, half, last);
-            else issue_pv(x, st, j, half, last);
-        };
         mbar_wait(q_full, 0);
         mbar_wait(&k_full[0], 0);
         tc_fence_after();
-        qk(0, 0, 0);
-        if (has_b) qk(1, 0, 0);
+        issue_qk(0, 0);
+        if (has_b) issue_qk(1, 0);
         if (elect_one()) tc_commit(&k_empty[0]);
         __syncwarp();
         for (int j = 0; j < n_tiles; ++j) {
@@ -411,23 +273,23 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             mbar_wait(&v_full[st], par);
             mbar_wait(&p_half[0], j & 1);
             tc_fence_after();
-            pv(0, st, j, 0, false);
+            issue_pv(0, st, j, 0, false);
             mbar_wait(&p_full[0], j & 1);
             tc_fence_after();
-            pv(0, st, j, 1, true);
+            issue_pv(0, st, j, 1, true);
             if (more) {
                 mbar_wait(&k_full[nst], npar);
                 tc_fence_after();
-                qk(0, nst, j + 1);
+                issue_qk(0, nst);
             }
             if (has_b) {
                 mbar_wait(&p_half[1], j & 1);
                 tc_fence_after();
-                pv(1, st, j, 0, false);
+                issue_pv(1, st, j, 0, false);
                 mbar_wait(&p_full[1], j & 1);
                 tc_fence_after();
-                pv(1, st, j, 1, true);
-                if (more) qk(1, nst, j + 1);
+                issue_pv(1, st, j, 1, true);
+                if (more) issue_qk(1, nst);
             }
             if (elect_one()) {
                 tc_commit(&v_empty[st]);
@@ -447,26 +309,88 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const uint32_t t_s = t_lane + x * 128;             // S / P
         const uint32_t t_o = t_lane + Cfg::O_COL + x * 128;  // O
         float m = -INFINITY, l = 0.f;
-        // a warp whose 32 query rows all lie past the sequence end (the tail tile of S = 257 holds ONE row) only keeps the
-        // barrier protocol going: its P / O lanes are never stored, so it issues no softmax work at all
-        const bool warp_has_rows = (q0 + x * AT_TILE + quarter * 32) < a.S;
         for (int j = 0; j < n_tiles; ++j) {
             mbar_wait(&s_full[x], j & 1);
             tc_fence_after();
-            if (!warp_has_rows) {
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&p_half[x]);
-                    mbar_arrive(&p_full[x]);
-                }
-                continue;
+            const int kv_valid = a.S - j * AT_TILE;        // columns >= kv_valid are past the sequence end
+            // the whole 128-wide score row of this thread in registers: ONE TMEM pass per key tile
+            uint32_t v[AT_TILE];
+#pragma unroll
+            for (int c = 0; c < AT_TILE; c += 32) tmem_ld_32x32_ptr(t_s + c, &v[c]);
+            tmem_ld_wait();
+            if (kv_valid < AT_TILE) {
+#pragma unroll
+                for (int i = 0; i < AT_TILE; ++i)
+                    if (i >= kv_valid) v[i] = 0xff800000u;   // -inf: exp2 -> 0, never the maximum
             }
-            // The hot loop (full 128-key tiles) is the FULL = true instantiation, byte for byte the round-1 code; only a narrow
-            // last tile takes the guarded instantiation (runtime column count).
-            if (narrow_last && j == n_tiles - 1)
-                softmax_tile<HD, false>(a, j, last_n16, t_s, t_o, x, lane, m, l, p_half, p_full, pv_done);
-            else
-                softmax_tile<HD, true>(a, j, AT_TILE, t_s, t_o, x, lane, m, l, p_half, p_full, pv_done);
+            // four independent chains (the FMNMX3 latency chain was as long as the exponential pass)
+            float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+            float m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+            float m2 = fmaxf(__uint_as_float(v[4]), __uint_as_float(v[5]));
+            float m3 = fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7]));
+#pragma unroll
+            for (int i = 8; i < AT_TILE; i += 8) {
+                m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                m2 = fmax3(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+                m3 = fmax3(m3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+            }
+            m0 = fmaxf(m0, m2);
+            m1 = fmaxf(m1, m3);
+            const float m_new = fmaxf(m, fmaxf(m0, m1) * a.scale_log2);
+            if (__any_sync(0xffffffffu, m_new > m + AT_RESCALE_THRESHOLD)) {
+                const float alpha = ex2_approx(m - m_new);   // 0 on the first tile (m = -inf)
+                if (j > 0) {
+                    mbar_wait(&pv_done[x], (j - 1) & 1);     // O_x += P_x(j-1) V_{j-1} has landed
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int c = 0; c < HD / 32; ++c) {
+                        uint32_t o[32];
+                        tmem_ld_32x32(t_o + c * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st_32x32(t_o + c * 32, o);
+                    }
+                }
+                l *= alpha;
+                m = m_new;
+            }
+            const float2 sc2 = splat2(a.scale_log2), nm2 = splat2(-m);
+            float2 sum_a = splat2(0.f), sum_b = splat2(0.f);
+            // P as packed bf16 written IN PLACE over the first 64 columns of S. Packed fp32x2 arithmetic throughout; of
+            // every eight pairs six take their exponentials from the MUFU pipe and two from a Cody-Waite + cubic
+            // polynomial on the FMA pipe (exp2 is the co-bottleneck of the tensor core at head dim 128). The first half
+            // of the row is published on its own barrier so that the P V product of keys [0,64) starts while the second
+            // half is still being exponentiated.
+#pragma unroll
+            for (int c = 0; c < AT_TILE; c += 32) {
+                uint32_t packed[16];
+#pragma unroll
+                for (int pr = 0; pr < 16; ++pr) {            // pairs of row elements
+                    const float2 x = ffma2(make_float2(__uint_as_float(v[c + 2 * pr]), __uint_as_float(v[c + 2 * pr + 1])),
+                                           sc2, nm2);
+                    const float2 e = ((AT_POLY_MASK >> (pr & 7)) & 1) ? ex2_poly2(x)
+                                                                      : make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                    if (pr & 1) sum_b = fadd2(sum_b, e);
+                    else sum_a = fadd2(sum_a, e);
+                    packed[pr] = pack_bf16x2(e);
+                }
+                tmem_st_32x16(t_s + (c >> 1), packed);
+                if (c == 32) {                       // keys [0,64) of this tile are in TMEM
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p_half[x]);
+                }
+            }
+            const float2 sum2 = fadd2(sum_a, sum_b);
+            const float sum0 = sum2.x, sum1 = sum2.y;
+            l += sum0 + sum1;
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[x]);
         }
         mbar_wait(&pv_done[x], (n_tiles - 1) & 1);
         tc_fence_after();
@@ -540,7 +464,6 @@ static int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, cons
 // Debug knobs kept for ABI stability (drag_debug_set keys 1/2); unused by the current kernel.
 uint32_t g_attn_v_lbo = 0, g_attn_v_sbo = 1024;
 int g_attn_force_pp = 0;      // drag_debug_set key 5: 1 = always the two-tile ping-pong kernel (A/B comparisons)
-int g_attn_no_narrow = 0;     // drag_debug_set key 7: 1 = full-width last key tile (A/B comparisons)
 
 int attention_bf16(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int B, int H, int S,
                    int head_dim, int split, __nv_bfloat16* out0, int ld0, __nv_bfloat16* out1, int ld1,
@@ -554,7 +477,6 @@ int attention_bf16(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bf
     a.out0 = out0; a.out1 = out1; a.ld0 = ld0; a.ld1 = ld1; a.split = split;
     a.S = S;
     a.H = H;
-    a.no_narrow = g_attn_no_narrow;
     a.scale_log2 = 0.f;
     if (head_dim == 128) return launch_attention<128, true>(q, k, v, B, H, S, a, st);
     // head dim 64 = the CLIP ViT towers: short sequences -> two single-tile CTAs per SM; long ones keep the ping-pong

@@ -33,7 +33,6 @@ extern uint32_t g_attn_v_lbo, g_attn_v_sbo;
 extern int g_gemm_force_1cta;
 extern int g_gemm_group_m;
 extern int g_attn_force_pp;
-extern int g_attn_no_narrow;
 extern int g_stem_force_ffma;
 int stem_stats_any_device(const void* img, int img_kind, int B, int H, int W, const float* w_fold, const float* b_fold,
                           float eps, float* out, cudaStream_t st);
@@ -370,6 +369,7 @@ int drag_vit_destroy(drag_vit_t* h) { return vit_destroy(reinterpret_cast<VitEng
 int drag_vit_set_weights(drag_vit_t* h, const void* const* ptrs, int n) {
     return vit_set_weights(reinterpret_cast<VitEngine*>(h), ptrs, n);
 }
+int drag_vit_set_option(drag_vit_t* h, int key, int value) { return vit_set_option(reinterpret_cast<VitEngine*>(h), key, value); }
 int drag_vit_encode(drag_vit_t* h, const void* img, int img_kind, int B, float* out, int l2_normalize, void* stream) {
     return vit_encode(reinterpret_cast<VitEngine*>(h), img, img_kind, B, out, l2_normalize, ST(stream));
 }
@@ -482,7 +482,6 @@ int drag_debug_set(int key, int value) {
     else if (key == 4) g_gemm_group_m = value;
     else if (key == 5) g_attn_force_pp = value;
     else if (key == 6) g_gemm_group_n = value;
-    else if (key == 7) g_attn_no_narrow = value;
     else if (key == 8) g_stem_force_ffma = value;
     else return fail(DRAG_ERR_INVALID, "drag_debug_set: unknown key");
     return DRAG_OK;

@@ -40,6 +40,22 @@ struct GemmEpi {
     int heads = 0, s_total = 0, tok_offset = 0;
     int head_dim = 128;                   // EPI_QKV_SPLIT: 64 or 128
     float rms_eps = 1e-6f;
+    // LayerNorm folded into the GEMMs on either side of it (CLIP ViT blocks; any mode that goes through the generic epilogue).
+    //   producer: stats_out != null -> every epilogue thread also writes the (sum, sum of squares) of the bf16-rounded values
+    //             it stores for its row and its BN/2 columns: stats_out[(row * stats_parts + part) * 2 + {0,1}], part =
+    //             column / (BN/2), stats_parts = N / (BN/2) (checked by gemm_bf16). Deterministic: no atomics.
+    //   consumer: ln_stats != null -> A holds the RAW rows x (not normalised); W holds gamma-scaled weights W' = W * gamma.
+    //             With mean / rstd from the ln_parts partials over ln_k columns:
+    //                 LN(x) W^T + b  =  rstd * (x W'^T - mean * ln_s) + ln_c,   ln_s[n] = sum_k W'[n][k],
+    //                                                                          ln_c[n] = sum_k beta[k] W[n][k] + b[n]
+    //             applied to the accumulator before the activation / scatter (bias must be null: it lives in ln_c).
+    float* stats_out = nullptr;
+    int stats_parts = 0;
+    const float* ln_stats = nullptr;
+    int ln_parts = 0, ln_k = 0;
+    const float* ln_s = nullptr;          // [N] fp32
+    const float* ln_c = nullptr;          // [N] fp32
+    float ln_eps = 1e-5f;
 };
 
 // C[M,N] = A[M,K] (bf16 row-major, lda) x W[N,K]^T (bf16 row-major, ldw), fp32 accumulate in TMEM.

@@ -10,7 +10,7 @@
 //                    tcgen05.ld (32 lanes x 32 columns per instruction, double buffered), fused
 //                    bias / activation / gate*x+residual / per-head RMSNorm+RoPE, bf16 stores.
 // The epilogue of tile i overlaps the MMAs of tile i+1 through the double-buffered accumulator.
-// Tile order is M-fastest so that concurrently running CTAs share the same W tile in L2.
+// Tile order: see tile_coords (row-fastest while A fits L2, column groups beyond that).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -167,7 +167,19 @@ __device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* src, float* v) 
 }
 
 // Generic epilogue on one 32-column chunk held in registers (this thread = one row).
-__device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, float (&v)[32], int row, int col0, int N) {
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, float (&v)[32], int row, int col0, int N, float ln_mean,
+                                               float ln_rstd, float& st_sum, float& st_sq) {
+    if (e.ln_stats) {           // folded LayerNorm of the A rows: rstd * (acc - mean * s[n]) + c[n]
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(e.ln_s + col0 + j));
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(e.ln_c + col0 + j));
+            v[j] = fmaf(ln_rstd, fmaf(-ln_mean, s4.x, v[j]), c4.x);
+            v[j + 1] = fmaf(ln_rstd, fmaf(-ln_mean, s4.y, v[j + 1]), c4.y);
+            v[j + 2] = fmaf(ln_rstd, fmaf(-ln_mean, s4.z, v[j + 2]), c4.z);
+            v[j + 3] = fmaf(ln_rstd, fmaf(-ln_mean, s4.w, v[j + 3]), c4.w);
+        }
+    }
     if (e.bias) {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
@@ -224,6 +236,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, float (&v)[32],
         __nv_bfloat16* dst = e.out + static_cast<size_t>(row) * e.ldo + col0;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) store_bf16x8(dst + j, &v[j]);
+        if (e.stats_out) {      // moments of the values as stored (bf16), for the LayerNorm folded into the next GEMM
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float r = bf16_round(v[j]);
+                st_sum += r;
+                st_sq = fmaf(r, r, st_sq);
+            }
+        }
     }
 }
 
@@ -322,6 +342,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, const GemmShap
         // chunk i is processed (tcgen05.wait::ld covers every earlier load of this thread)
         constexpr int NC = BN / 64;
         const int c0 = half * (BN / 2);
+        float ln_mean = 0.f, ln_rstd = 1.f, st_sum = 0.f, st_sq = 0.f;
+        if (epi.ln_stats && row_ok) {
+            float s1 = 0.f, s2 = 0.f;
+            const float2* ps = reinterpret_cast<const float2*>(epi.ln_stats) + static_cast<size_t>(row) * epi.ln_parts;
+            for (int p = 0; p < epi.ln_parts; ++p) {       // fixed order: deterministic
+                const float2 t = __ldg(ps + p);
+                s1 += t.x;
+                s2 += t.y;
+            }
+            const float inv_k = 1.f / static_cast<float>(epi.ln_k);
+            ln_mean = s1 * inv_k;
+            ln_rstd = rsqrtf(fmaxf(s2 * inv_k - ln_mean * ln_mean, 0.f) + epi.ln_eps);
+        }
         uint32_t ra[32], rb[32];
         tmem_ld_32x32(t_addr + c0, ra);
 #pragma unroll
@@ -335,8 +368,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, const GemmShap
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]);
-                epilogue_chunk(epi, v, row, col0, sh.N);
+                epilogue_chunk(epi, v, row, col0, sh.N, ln_mean, ln_rstd, st_sum, st_sq);
             }
+        }
+        if (epi.stats_out && row_ok && n_blk * BN + c0 < sh.N) {
+            const int part = (n_blk * BN + c0) / (BN / 2);
+            *reinterpret_cast<float2*>(epi.stats_out + (static_cast<size_t>(row) * epi.stats_parts + part) * 2) =
+                make_float2(st_sum, st_sq);
         }
     }
 }
@@ -804,6 +842,16 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
         DRAG_REQUIRE(epi.out || epi.out_f32, "gemm: null output");
         if (N % 256 != 0 || N <= 256) bn = (N % 128 == 0 && N > 128) ? 128 : 64;
         if (N % bn != 0 && N > bn) bn = 64;   // N % 32 == 0: tail columns masked per 32-column chunk
+    }
+    if (epi.stats_out) {
+        DRAG_REQUIRE(epi.mode == EPI_BIAS || epi.mode == EPI_GATE_RESID, "gemm: row statistics need a bf16 row-major output");
+        DRAG_REQUIRE(N % (bn / 2) == 0 && epi.stats_parts == N / (bn / 2),
+                     "gemm: stats_parts must equal N / (BN/2) = " + std::to_string(N / (bn / 2)));
+    }
+    if (epi.ln_stats) {
+        DRAG_REQUIRE(epi.mode != EPI_QKV_ROPE, "gemm: folded LayerNorm is not available with the RoPE epilogue");
+        DRAG_REQUIRE(epi.ln_s && epi.ln_c && epi.ln_parts >= 1 && epi.ln_k == K && !epi.bias,
+                     "gemm: folded LayerNorm needs ln_s, ln_c, ln_parts, ln_k == K and no separate bias");
     }
     GemmShape sh{};
     sh.M = M; sh.N = N; sh.K = K;

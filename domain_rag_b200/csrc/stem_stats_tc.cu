@@ -91,6 +91,7 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
     const int n_img = (B - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
     if (tid == 0) {
+        if (smem_u32(smem) & 1023u) __trap();                  // swizzled tiles would be read from the wrong banks: fail loudly
         for (int i = 0; i < TS_RING; ++i) {
             mbar_init(&xfull[i], 128);
             mbar_init(&xempty[i], 1);
@@ -130,31 +131,69 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
     if (warp < 4) {
         // ------------------------------------------------------------------ loaders: thread = conv pixel px
         const int px = tid;
+        // the zero chunks (ci = 3 of either row) of every ring slot are written once: no later store touches them
+        for (int slot = 0; slot < TS_RING; ++slot) {
+            uint8_t* t0 = xring + static_cast<size_t>(slot) * 2 * TS_XTILE;
+            *reinterpret_cast<uint4*>(t0 + sw128_chunk(px, 3)) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(t0 + sw128_chunk(px, 7)) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(t0 + TS_XTILE + sw128_chunk(px, 3)) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(t0 + TS_XTILE + sw128_chunk(px, 7)) = make_uint4(0, 0, 0, 0);
+        }
+        // window of conv pixel px: input columns 2px-3 .. 2px+3, fetched as the 4 aligned pairs covering 2px-4 .. 2px+3
+        // (rows have 256 columns, so a pair is either wholly inside the row or wholly padding)
+        const int x0 = 2 * px - 4;
+        const bool ok0 = x0 >= 0, ok3 = x0 + 6 < 256;       // pairs 1, 2 are always inside
         for (int it = 0; it < n_img; ++it) {
             const size_t b = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(it) * gridDim.x;
             for (int p = 0; p < 128; ++p) {
                 const int P = it * 128 + p, slot = P % TS_RING;
+                // all 24 loads of the pair in flight before the first conversion: ONE memory latency per row pair
+                float w[6][8];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {                 // (row of the pair, channel)
+                    const int h = c / 3, ci = c - h * 3;
+                    const size_t row = ((b * 3 + ci) * 256 + (2 * p + h)) * 256;
+                    if (U8) {
+                        const uint8_t* src = static_cast<const uint8_t*>(img_v) + row;
+                        unsigned short q[4];
+                        q[0] = ok0 ? __ldg(reinterpret_cast<const unsigned short*>(src + x0)) : static_cast<unsigned short>(0);
+                        q[1] = (x0 + 2 >= 0) ? __ldg(reinterpret_cast<const unsigned short*>(src + x0 + 2)) : static_cast<unsigned short>(0);
+                        q[2] = __ldg(reinterpret_cast<const unsigned short*>(src + x0 + 4));
+                        q[3] = ok3 ? __ldg(reinterpret_cast<const unsigned short*>(src + x0 + 6)) : static_cast<unsigned short>(0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            // u8 / 255 exactly as IEEE division rounds it, without the division sequence: q = u * r,
+                            // one Newton correction with the exact remainder (verified for all 256 values)
+                            const float r = 1.0f / 255.0f;
+                            const float u0 = static_cast<float>(q[j] & 0xff), u1 = static_cast<float>(q[j] >> 8);
+                            const float q0 = u0 * r, q1 = u1 * r;
+                            w[c][2 * j] = fmaf(fmaf(-q0, 255.f, u0), r, q0);
+                            w[c][2 * j + 1] = fmaf(fmaf(-q1, 255.f, u1), r, q1);
+                        }
+                    } else {
+                        const float* src = static_cast<const float*>(img_v) + row;
+                        const float2 z = make_float2(0.f, 0.f);
+                        const float2 a0 = ok0 ? __ldg(reinterpret_cast<const float2*>(src + x0)) : z;
+                        const float2 a1 = (x0 + 2 >= 0) ? __ldg(reinterpret_cast<const float2*>(src + x0 + 2)) : z;
+                        const float2 a2 = __ldg(reinterpret_cast<const float2*>(src + x0 + 4));
+                        const float2 a3 = ok3 ? __ldg(reinterpret_cast<const float2*>(src + x0 + 6)) : z;
+                        w[c][0] = a0.x; w[c][1] = a0.y; w[c][2] = a1.x; w[c][3] = a1.y;
+                        w[c][4] = a2.x; w[c][5] = a2.y; w[c][6] = a3.x; w[c][7] = a3.y;
+                    }
+                }
                 mbar_wait(&xempty[slot], ((P / TS_RING) & 1) ^ 1);
                 uint8_t* thi = xring + static_cast<size_t>(slot) * 2 * TS_XTILE;
                 uint8_t* tlo = thi + TS_XTILE;
-#pragma unroll 2
-                for (int c = 0; c < 8; ++c) {                 // chunk = (row of the pair, channel); ci = 3 is padding
-                    const int h = c >> 2, ci = c & 3;
-                    float x[8];
 #pragma unroll
-                    for (int kx = 0; kx < 8; ++kx) {
-                        const int xx = 2 * px - 3 + kx;
-                        float v = 0.f;
-                        if (ci < 3 && kx < 7 && xx >= 0 && xx < 256) {
-                            const size_t idx = ((b * 3 + ci) * 256 + (2 * p + h)) * 256 + xx;
-                            if (U8) v = __fdiv_rn(static_cast<float>(__ldg(static_cast<const uint8_t*>(img_v) + idx)), 255.f);
-                            else v = __ldg(static_cast<const float*>(img_v) + idx);
-                        }
-                        x[kx] = v;
-                    }
+                for (int c = 0; c < 6; ++c) {
+                    const int h = c / 3, ci = c - h * 3;
+                    float x[8];                               // taps kx = 0..6 are window elements 1..7; kx = 7 is padding
+#pragma unroll
+                    for (int kx = 0; kx < 7; ++kx) x[kx] = w[c][kx + 1];
+                    x[7] = 0.f;
                     uint4 hi, lo;
                     split_bf16x8(x, hi, lo);
-                    const uint32_t off = sw128_chunk(px, c);
+                    const uint32_t off = sw128_chunk(px, h * 4 + ci);
                     *reinterpret_cast<uint4*>(thi + off) = hi;
                     *reinterpret_cast<uint4*>(tlo + off) = lo;
                 }
@@ -219,14 +258,15 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
         const int px = w * 32 + lane;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(w * 32) << 16);
         const bool odd = lane & 1;
-        float bias[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) bias[i] = b_fold[(odd ? 32 : 0) + i];
+        const float* bias = b_fold + (odd ? 32 : 0);           // 32 L1-resident loads per pooled row: cheaper than 32 registers
         for (int it = 0; it < n_img; ++it) {
             const size_t b = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(it) * gridDim.x;
-            float sum[32], sq[32];
+            // Moments of the thread's 64 pooled values per channel, accumulated around a per-thread SHIFT (its first pooled
+            // value): sum of (x - shift) and of (x - shift)^2 stay small for smooth maps, so fp32 accumulation does not
+            // cancel when the variance is formed (a constant image has var ~ 1e-6 next to mean^2 ~ 1).
+            float shift[32], sum[32], sq[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) sum[i] = sq[i] = 0.f;
+            for (int i = 0; i < 32; ++i) shift[i] = sum[i] = sq[i] = 0.f;
             for (int py = 0; py < 64; ++py) {
                 const int R2 = it * 128 + 2 * py + 1, R1 = R2 - 1, R0 = R2 - 2;
                 mbar_wait(&dfull[R2 % TS_DBUF], (R2 / TS_DBUF) & 1);   // MMAs retire in order: rows R1, R0 are complete too
@@ -280,40 +320,57 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
                         mid = b_o;
                         right = vm[32 + i];
                     }
-                    const float pooled = fmaxf(fmaxf(fmaxf(left, mid), right) + bias[i], 0.f);   // bias + ReLU commute with max
-                    sum[i] += pooled;
-                    sq[i] = fmaf(pooled, pooled, sq[i]);
+                    const float pooled = fmaxf(fmaxf(fmaxf(left, mid), right) + __ldg(bias + i), 0.f);   // bias + ReLU commute with max
+                    if (py == 0) shift[i] = pooled;
+                    const float dlt = pooled - shift[i];
+                    sum[i] += dlt;
+                    sq[i] = fmaf(dlt, dlt, sq[i]);
                 }
             }
-            // image done: reduce over the 16 same-parity lanes of each warp, then over the 4 warps (fp64), write the moments
+            // image done. Per thread and channel: n = 64 values, mean = shift + S / n, M2 = Q - S^2 / n (fp64). Partials are
+            // merged pairwise (Chan et al.): equal counts at every level -> mean' = (ma + mb) / 2, M2' = M2a + M2b +
+            // (mb - ma)^2 * n / 2: first across the 16 same-parity lanes of the warp (butterfly), then across the 4 warps.
+            double cnt = 64.0;
+            float mean_f[32], m2_f[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
+                double mean = static_cast<double>(shift[i]) + static_cast<double>(sum[i]) / 64.0;
+                double m2 = static_cast<double>(sq[i]) - static_cast<double>(sum[i]) * static_cast<double>(sum[i]) / 64.0;
+                double n = 64.0;
 #pragma unroll
                 for (int o = 2; o < 32; o <<= 1) {
-                    sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], o);
-                    sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
+                    const double mo = __shfl_xor_sync(0xffffffffu, mean, o);
+                    const double qo = __shfl_xor_sync(0xffffffffu, m2, o);
+                    const double dl = mo - mean;
+                    m2 = m2 + qo + dl * dl * (n * 0.5);
+                    mean = 0.5 * (mean + mo);
+                    n *= 2.0;
                 }
+                cnt = n;
+                mean_f[i] = static_cast<float>(mean);
+                m2_f[i] = static_cast<float>(m2);
             }
-            named_bar_sync(1, 128);                            // previous image's readers of `red` are done
+            named_bar_sync(1, 128);                            // the last pooled row's readers of the edge buffer are done
             if (lane < 2) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    red[(w * 2 + 0) * 64 + lane * 32 + i] = sum[i];
-                    red[(w * 2 + 1) * 64 + lane * 32 + i] = sq[i];
+                    red[(w * 2 + 0) * 64 + lane * 32 + i] = mean_f[i];
+                    red[(w * 2 + 1) * 64 + lane * 32 + i] = m2_f[i];
                 }
             }
             named_bar_sync(1, 128);
             const int t = tid - 256;
             if (t < 64) {
-                double s = 0.0, ss = 0.0;
-#pragma unroll
-                for (int ww = 0; ww < 4; ++ww) {
-                    s += static_cast<double>(red[(ww * 2 + 0) * 64 + t]);
-                    ss += static_cast<double>(red[(ww * 2 + 1) * 64 + t]);
+                double mean = static_cast<double>(red[(0 * 2 + 0) * 64 + t]), m2 = static_cast<double>(red[(0 * 2 + 1) * 64 + t]);
+                double n = cnt;                                // 1024 values per warp partial
+                for (int ww = 1; ww < 4; ++ww) {
+                    const double mb = static_cast<double>(red[(ww * 2 + 0) * 64 + t]), qb = static_cast<double>(red[(ww * 2 + 1) * 64 + t]);
+                    const double dl = mb - mean, nt = n + cnt;
+                    m2 = m2 + qb + dl * dl * (n * cnt / nt);
+                    mean = mean + dl * (cnt / nt);
+                    n = nt;
                 }
-                const double n = 64.0 * 64.0;
-                const double mean = s / n;
-                double var = (ss - n * mean * mean) / (n - 1.0);
+                double var = m2 / (n - 1.0);
                 if (var < 0.0) var = 0.0;
                 out[b * 128 + t] = static_cast<float>(mean);
                 out[b * 128 + 64 + t] = static_cast<float>(sqrt(var + static_cast<double>(eps)));
@@ -340,6 +397,7 @@ int stem_stats_any_device(const void* img, int img_kind, int B, int H, int W, co
     DRAG_REQUIRE(img && w_fold && b_fold && out, "stem_stats: null pointer");
     DRAG_REQUIRE(H == 256 && W == 256, "stem_stats: input must be 256x256 (reference resize)");
     DRAG_REQUIRE(B >= 0 && (img_kind == 0 || img_kind == 1), "stem_stats: bad arguments");
+    DRAG_REQUIRE((reinterpret_cast<uintptr_t>(img) & 7) == 0, "stem_stats: image pointer must be 8-byte aligned");
     if (B == 0) return DRAG_OK;
     if (g_stem_force_ffma && img_kind == 0)
         return stem_stats_ffma_device(static_cast<const float*>(img), B, H, W, w_fold, b_fold, eps, out, st);

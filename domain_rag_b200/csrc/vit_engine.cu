@@ -37,6 +37,27 @@ __global__ void vit_patchify_u8_kernel(const uint8_t* __restrict__ img, __nv_bfl
     out[i] = __float2bfloat16(v);
 }
 
+// (sum, sum of squares) of each bf16 row into part 0 of the row's partial-moment slots, the other parts zeroed: the
+// input of the first block's folded LayerNorm (later blocks get their moments from the producing GEMM's epilogue).
+__global__ void vit_row_stats_kernel(const __nv_bfloat16* __restrict__ x, int ld, int M, int d, int parts,
+                                     float* __restrict__ stats) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    float s = 0.f, ss = 0.f;
+    for (int c = lane * 2; c < d; c += 64) {
+        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + static_cast<size_t>(row) * ld + c));
+        s += v.x + v.y;
+        ss = fmaf(v.x, v.x, fmaf(v.y, v.y, ss));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    float2* dst = reinterpret_cast<float2*>(stats) + static_cast<size_t>(row) * parts;
+    for (int p = lane; p < parts; p += 32) dst[p] = (p == 0) ? make_float2(s, ss) : make_float2(0.f, 0.f);
+}
+
 static int alloc_bytes(void** p, size_t n) {
     DRAG_CUDA(cudaMalloc(p, n));
     return DRAG_OK;
@@ -44,8 +65,8 @@ static int alloc_bytes(void** p, size_t n) {
 
 int vit_create(const VitCfg& cfg, VitEngine** out) {
     DRAG_REQUIRE(out, "vit_create: null out");
-    DRAG_REQUIRE(cfg.width % 64 == 0 && cfg.heads >= 1 && cfg.width == cfg.heads * 64,
-                 "vit_create: width must be heads * 64 (CLIP ViT towers)");
+    DRAG_REQUIRE(cfg.width % 256 == 0 && cfg.heads >= 1 && cfg.width == cfg.heads * 64,
+                 "vit_create: width must be heads * 64 and a multiple of 256 (CLIP ViT towers: 768, 1024)");
     DRAG_REQUIRE(cfg.layers >= 1 && cfg.patch >= 1 && cfg.image >= cfg.patch && cfg.out_dim % 32 == 0 && cfg.max_batch >= 1,
                  "vit_create: bad configuration");
     VitEngine* e = new VitEngine();
@@ -67,6 +88,8 @@ int vit_create(const VitCfg& cfg, VitEngine** out) {
     rc |= alloc_bytes(reinterpret_cast<void**>(&e->u), B * L * 4 * w * 2);
     rc |= alloc_bytes(reinterpret_cast<void**>(&e->cls_ln), B * w * 2);
     rc |= alloc_bytes(reinterpret_cast<void**>(&e->emb), B * cfg.out_dim * 4);
+    rc |= alloc_bytes(reinterpret_cast<void**>(&e->stats_a), B * L * (w / 128) * 2 * 4);
+    rc |= alloc_bytes(reinterpret_cast<void**>(&e->stats_b), B * L * (w / 128) * 2 * 4);
     if (rc) {
         vit_destroy(e);
         return fail(DRAG_ERR_CUDA, "vit_create: workspace allocation failed");
@@ -77,7 +100,7 @@ int vit_create(const VitCfg& cfg, VitEngine** out) {
 
 int vit_destroy(VitEngine* e) {
     if (!e) return DRAG_OK;
-    void* bufs[] = {e->patches, e->pe, e->h, e->y, e->q, e->k, e->v, e->a, e->u, e->cls_ln, e->emb};
+    void* bufs[] = {e->patches, e->pe, e->h, e->y, e->q, e->k, e->v, e->a, e->u, e->cls_ln, e->emb, e->stats_a, e->stats_b};
     for (void* b : bufs)
         if (b) cudaFree(b);
     delete e;
@@ -86,7 +109,7 @@ int vit_destroy(VitEngine* e) {
 
 int vit_set_weights(VitEngine* e, const void* const* ptrs, int n) {
     DRAG_REQUIRE(e && ptrs, "vit_set_weights: null pointer");
-    const int expect = 8 + 12 * e->cfg.layers;
+    const int expect = 8 + 18 * e->cfg.layers;
     DRAG_REQUIRE(n == expect, "vit_set_weights: expected " + std::to_string(expect) + " pointers");
     for (int j = 0; j < n; ++j) DRAG_REQUIRE(ptrs[j], "vit_set_weights: null weight pointer at slot " + std::to_string(j));
     int i = 0;
@@ -96,6 +119,8 @@ int vit_set_weights(VitEngine* e, const void* const* ptrs, int n) {
     for (VitBlockW& b : e->blocks) {
         b.ln1_w = next(); b.ln1_b = next(); b.qkv_w = next(); b.qkv_b = next(); b.out_w = next(); b.out_b = next();
         b.ln2_w = next(); b.ln2_b = next(); b.fc_w = next(); b.fc_b = next(); b.proj_w = next(); b.proj_b = next();
+        b.qkv_wf = next(); b.qkv_s = reinterpret_cast<const float*>(next()); b.qkv_c = reinterpret_cast<const float*>(next());
+        b.fc_wf = next(); b.fc_s = reinterpret_cast<const float*>(next()); b.fc_c = reinterpret_cast<const float*>(next());
     }
     e->weights_set = true;
     return DRAG_OK;
@@ -135,23 +160,49 @@ static int encode_chunk(VitEngine* e, const void* img, int img_kind, int B, floa
     VX(lin(e->patches, e->kpad, e->conv_w, e->kpad, B * np, w, nullptr, EPI_BIAS, e->pe, w, nullptr, st));
     VX(vit_assemble(e->pe, e->cls, e->pos, e->h, B, np, w, st));
     VX(layernorm_bf16(e->h, w, e->h, w, M, w, e->ln_pre_w, 0, e->ln_pre_b, 0, 0, 0, 1e-5f, st));
+    const int parts = w / 128;          // the N = w GEMMs run 256-wide tiles: one partial per 128 columns (BN / 2)
+    if (e->fold_ln) {
+        vit_row_stats_kernel<<<ceil_div(M, 8), 256, 0, st>>>(e->h, w, M, w, parts, e->stats_a);
+        count_launch();
+        DRAG_CUDA(cudaGetLastError());
+    }
     for (const VitBlockW& b : e->blocks) {
-        VX(layernorm_bf16(e->h, w, e->y, w, M, w, b.ln1_w, 0, b.ln1_b, 0, 0, 0, 1e-5f, st));
         GemmEpi qe;
         qe.mode = EPI_QKV_SPLIT;
-        qe.bias = b.qkv_b;
         qe.q_out = e->q; qe.k_out = e->k; qe.v_out = e->v;
         qe.heads = H;
         qe.head_dim = 64;
         qe.s_total = L;
         qe.tok_offset = 0;
         qe.rows_per_batch = L;
-        VX(gemm_bf16(e->y, w, b.qkv_w, w, M, 3 * w, w, qe, st));
-        VX(attention_bf16(e->q, e->k, e->v, B, H, L, 64, 0, nullptr, 8, e->a, w, st));
-        VX(lin(e->a, w, b.out_w, w, M, w, b.out_b, EPI_GATE_RESID, e->h, w, e->h, st));
-        VX(layernorm_bf16(e->h, w, e->y, w, M, w, b.ln2_w, 0, b.ln2_b, 0, 0, 0, 1e-5f, st));
-        VX(lin(e->y, w, b.fc_w, w, M, 4 * w, b.fc_b, EPI_QUICK_GELU, e->u, 4 * w, nullptr, st));
-        VX(lin(e->u, 4 * w, b.proj_w, 4 * w, M, w, b.proj_b, EPI_GATE_RESID, e->h, w, e->h, st));
+        if (e->fold_ln) {
+            // ln_1 lives in the QKV GEMM's epilogue (moments of h from the previous producer), ln_2 in the MLP-up GEMM's;
+            // the two residual GEMMs emit the moments of the rows they store
+            qe.ln_stats = e->stats_a; qe.ln_parts = parts; qe.ln_k = w; qe.ln_s = b.qkv_s; qe.ln_c = b.qkv_c; qe.ln_eps = 1e-5f;
+            VX(gemm_bf16(e->h, w, b.qkv_wf, w, M, 3 * w, w, qe, st));
+            VX(attention_bf16(e->q, e->k, e->v, B, H, L, 64, 0, nullptr, 8, e->a, w, st));
+            GemmEpi oe;
+            oe.mode = EPI_GATE_RESID; oe.bias = b.out_b; oe.out = e->h; oe.ldo = w; oe.resid = e->h; oe.ldr = w;
+            oe.stats_out = e->stats_b; oe.stats_parts = parts;
+            VX(gemm_bf16(e->a, w, b.out_w, w, M, w, w, oe, st));
+            GemmEpi fe;
+            fe.mode = EPI_QUICK_GELU; fe.out = e->u; fe.ldo = 4 * w;
+            fe.ln_stats = e->stats_b; fe.ln_parts = parts; fe.ln_k = w; fe.ln_s = b.fc_s; fe.ln_c = b.fc_c; fe.ln_eps = 1e-5f;
+            VX(gemm_bf16(e->h, w, b.fc_wf, w, M, 4 * w, w, fe, st));
+            GemmEpi pe2;
+            pe2.mode = EPI_GATE_RESID; pe2.bias = b.proj_b; pe2.out = e->h; pe2.ldo = w; pe2.resid = e->h; pe2.ldr = w;
+            pe2.stats_out = e->stats_a; pe2.stats_parts = parts;
+            VX(gemm_bf16(e->u, 4 * w, b.proj_w, 4 * w, M, w, 4 * w, pe2, st));
+        } else {
+            VX(layernorm_bf16(e->h, w, e->y, w, M, w, b.ln1_w, 0, b.ln1_b, 0, 0, 0, 1e-5f, st));
+            qe.bias = b.qkv_b;
+            VX(gemm_bf16(e->y, w, b.qkv_w, w, M, 3 * w, w, qe, st));
+            VX(attention_bf16(e->q, e->k, e->v, B, H, L, 64, 0, nullptr, 8, e->a, w, st));
+            VX(lin(e->a, w, b.out_w, w, M, w, b.out_b, EPI_GATE_RESID, e->h, w, e->h, st));
+            VX(layernorm_bf16(e->h, w, e->y, w, M, w, b.ln2_w, 0, b.ln2_b, 0, 0, 0, 1e-5f, st));
+            VX(lin(e->y, w, b.fc_w, w, M, 4 * w, b.fc_b, EPI_QUICK_GELU, e->u, 4 * w, nullptr, st));
+            VX(lin(e->u, 4 * w, b.proj_w, 4 * w, M, w, b.proj_b, EPI_GATE_RESID, e->h, w, e->h, st));
+        }
     }
     // class-token rows (stride L*w) -> ln_post -> projection (fp32 out) -> optional L2 normalise
     VX(layernorm_bf16(e->h, L * w, e->cls_ln, w, B, w, e->ln_post_w, 0, e->ln_post_b, 0, 0, 0, 1e-5f, st));
@@ -161,6 +212,13 @@ static int encode_chunk(VitEngine* e, const void* img, int img_kind, int B, floa
     pe.ldo = c.out_dim;
     VX(gemm_bf16(e->cls_ln, w, e->proj_t, w, B, c.out_dim, w, pe, st));
     if (normalize) VX(l2_normalize(e->emb, out, B, c.out_dim, st));
+    return DRAG_OK;
+}
+
+int vit_set_option(VitEngine* e, int key, int value) {
+    DRAG_REQUIRE(e, "vit_set_option: null engine");
+    DRAG_REQUIRE(key == 1, "vit_set_option: unknown key (1 = fold LayerNorm into the GEMMs: 1 on, 0 off)");
+    e->fold_ln = value ? 1 : 0;
     return DRAG_OK;
 }
 

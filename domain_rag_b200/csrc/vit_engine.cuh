@@ -16,6 +16,9 @@ struct VitCfg {
 
 struct VitBlockW {
     const __nv_bfloat16 *ln1_w, *ln1_b, *qkv_w, *qkv_b, *out_w, *out_b, *ln2_w, *ln2_b, *fc_w, *fc_b, *proj_w, *proj_b;
+    // LayerNorm folded into the GEMM that consumes it (see GemmEpi): gamma-scaled weights and the two fp32 vectors
+    const __nv_bfloat16 *qkv_wf, *fc_wf;
+    const float *qkv_s, *qkv_c, *fc_s, *fc_c;
 };
 
 struct VitEngine {
@@ -28,12 +31,15 @@ struct VitEngine {
     __nv_bfloat16 *patches = nullptr, *pe = nullptr, *h = nullptr, *y = nullptr, *q = nullptr, *k = nullptr, *v = nullptr,
                   *a = nullptr, *u = nullptr, *cls_ln = nullptr;
     float* emb = nullptr;
+    float *stats_a = nullptr, *stats_b = nullptr;   // [max_batch * tokens][width / 128][2] row moments (LN folding)
+    int fold_ln = 1;                                  // 0: separate LayerNorm kernels (A/B comparisons, drag_vit_set_option)
 };
 
 int vit_create(const VitCfg& cfg, VitEngine** out);
 int vit_destroy(VitEngine* e);
 int vit_set_weights(VitEngine* e, const void* const* ptrs, int n);
 // img_kind 0: fp32 [B][3][R][R] already normalised (what `preprocess` returns); 1: uint8 [B][3][R][R] raw pixels.
+int vit_set_option(VitEngine* e, int key, int value);
 int vit_encode(VitEngine* e, const void* img, int img_kind, int B, float* out, int normalize, cudaStream_t st);
 
 }  // namespace drag

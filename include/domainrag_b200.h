@@ -148,8 +148,8 @@ int drag_vit_assemble(const void* patch_emb, const void* cls, const void* pos, v
  * 161-177, 270-296, 326-349; model from clip.load at :209): the whole tower - patch embedding, class token + positions,
  * ln_pre, `layers` pre-LN blocks (QKV GEMM -> head-dim-64 attention -> out projection + residual -> QuickGELU MLP +
  * residual), ln_post of the class token, projection, optional L2 normalise - orchestrated inside the library.
- * Weights: caller-owned bf16 device pointers in the order of domain_rag_b200/clip.py::ENGINE_ORDER (8 globals, 12 per
- * block). img_kind 0: fp32 [B][3][image][image] already normalised (what `preprocess` returns); img_kind 1: raw uint8
+ * Weights: caller-owned device pointers in the order of domain_rag_b200/clip.py::ENGINE_ORDER (8 globals, 18 per block:
+ * the 12 bf16 tensors of the block, then the LayerNorm-folded QKV / MLP-up weights (bf16) each with its fp32 s and c vectors). img_kind 0: fp32 [B][3][image][image] already normalised (what `preprocess` returns); img_kind 1: raw uint8
  * pixels [B][3][image][image] - ToTensor + Normalize((u8/255 - mean) / std, IEEE fp32) run inside the patch kernel.
  * out fp32 [B][out_dim]. B may exceed max_batch (processed in chunks of max_batch). */
 typedef struct drag_vit drag_vit_t;
@@ -160,6 +160,10 @@ typedef struct {
 int drag_vit_create(const drag_vit_config* cfg, drag_vit_t** out);
 int drag_vit_destroy(drag_vit_t* h);
 int drag_vit_set_weights(drag_vit_t* h, const void* const* ptrs, int n);
+/* key 1: fold ln_1 / ln_2 into the GEMMs around them (default 1): the residual GEMMs' epilogues emit per-row moments, the QKV
+ * and MLP-up GEMMs run on the raw residual rows with gamma-scaled weights and apply rstd * (acc - mean * s) + c. 0 = separate
+ * LayerNorm kernels (A/B comparisons). */
+int drag_vit_set_option(drag_vit_t* h, int key, int value);
 int drag_vit_encode(drag_vit_t* h, const void* img, int img_kind, int B, float* out, int l2_normalize, void* stream);
 
 /* ---- Flux MMDiT engine --------------------------------------------------------------------------
@@ -224,8 +228,7 @@ int drag_launch_count(int64_t* count, int reset);
 /* Debug knobs for bring-up and A/B comparisons (key 1/2: unused; key 3: 1 = force the single-CTA GEMM kernel
  * instead of the CTA-pair cta_group::2 kernel; key 4: > 0 = force the GEMM tile-raster group size, 1 << 20 = plain
  * row-fastest order; key 5: 1 = head-dim-64 attention always on the two-tile ping-pong kernel; key 6: > 0 = force the
- * column-group raster with that many column tiles per group; key 7: 1 = attention computes its last key tile at full
- * width instead of N = keys rounded up to 16; key 8: 1 = stem statistics on the FP32 CUDA-core kernel instead of
+ * column-group raster with that many column tiles per group; key 8: 1 = stem statistics on the FP32 CUDA-core kernel instead of
  * the tensor-core kernel). */
 int drag_debug_set(int key, int value);
 
