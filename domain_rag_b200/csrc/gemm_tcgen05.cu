@@ -251,9 +251,30 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, float (&v)[32],
 // 8 epilogue warps are two groups of 4 (one warp per TMEM lane quarter each): group `half` owns columns
 // [half*BN/2, (half+1)*BN/2) of the tile, so every SM sub-partition has two warps to hide TMEM / global latency.
 // t_addr: TMEM address of this warp's lane quarter at column 0 of the accumulator.
+// Folded LayerNorm: mean / rstd of A row `row` from its partial moments. Called BEFORE the accumulator wait so that the (up
+// to 8, all in flight at once) loads overlap the tile's MMAs; summed in a fixed order (deterministic).
+__device__ __forceinline__ void ln_row_moments(const GemmEpi& epi, int row, bool row_ok, float& ln_mean, float& ln_rstd) {
+    ln_mean = 0.f;
+    ln_rstd = 1.f;
+    if (!epi.ln_stats || !row_ok) return;
+    const float2* ps = reinterpret_cast<const float2*>(epi.ln_stats) + static_cast<size_t>(row) * epi.ln_parts;
+    float2 t[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) t[p] = (p < epi.ln_parts) ? __ldg(ps + p) : make_float2(0.f, 0.f);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        s1 += t[p].x;
+        s2 += t[p].y;
+    }
+    const float inv_k = 1.f / static_cast<float>(epi.ln_k);
+    ln_mean = s1 * inv_k;
+    ln_rstd = rsqrtf(fmaxf(s2 * inv_k - ln_mean * ln_mean, 0.f) + epi.ln_eps);
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, const GemmShape& sh, uint32_t t_addr, int row,
-                                              bool row_ok, int n_blk, int half) {
+                                              bool row_ok, int n_blk, int half, float ln_mean, float ln_rstd) {
     if (epi.mode == EPI_QKV_ROPE) {
         // BN covers BN/128 whole heads (one per warp group at BN = 256); columns [0,H*128) q, [H*128,2H*128) k, rest v.
         // The whole 128-wide head row lives in registers: one TMEM pass for sum of squares, RMSNorm, RoPE and store.
@@ -342,19 +363,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, const GemmShap
         // chunk i is processed (tcgen05.wait::ld covers every earlier load of this thread)
         constexpr int NC = BN / 64;
         const int c0 = half * (BN / 2);
-        float ln_mean = 0.f, ln_rstd = 1.f, st_sum = 0.f, st_sq = 0.f;
-        if (epi.ln_stats && row_ok) {
-            float s1 = 0.f, s2 = 0.f;
-            const float2* ps = reinterpret_cast<const float2*>(epi.ln_stats) + static_cast<size_t>(row) * epi.ln_parts;
-            for (int p = 0; p < epi.ln_parts; ++p) {       // fixed order: deterministic
-                const float2 t = __ldg(ps + p);
-                s1 += t.x;
-                s2 += t.y;
-            }
-            const float inv_k = 1.f / static_cast<float>(epi.ln_k);
-            ln_mean = s1 * inv_k;
-            ln_rstd = rsqrtf(fmaxf(s2 * inv_k - ln_mean * ln_mean, 0.f) + epi.ln_eps);
-        }
+        float st_sum = 0.f, st_sq = 0.f;
         uint32_t ra[32], rb[32];
         tmem_ld_32x32(t_addr + c0, ra);
 #pragma unroll
@@ -489,10 +498,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             int base, count, ib, iy, ix;
             tile_rows(sh, m_blk, base, count, ib, iy, ix);
             const int r_in = quarter * 32 + lane;
+            float ln_mean, ln_rstd;
+            ln_row_moments(epi, base + r_in, r_in < count, ln_mean, ln_rstd);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-            epilogue_tile<BN>(epi, sh, t_addr, base + r_in, r_in < count, n_blk, (warp - G_EPI_WARP0) >> 2);
+            epilogue_tile<BN>(epi, sh, t_addr, base + r_in, r_in < count, n_blk, (warp - G_EPI_WARP0) >> 2, ln_mean, ln_rstd);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -642,10 +653,12 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             int base, count, ib, iy, ix;
             tile_rows(sh, m_blk * 2 + rank, base, count, ib, iy, ix);
             const int r_in = quarter * 32 + lane;
+            float ln_mean, ln_rstd;
+            ln_row_moments(epi, base + r_in, r_in < count, ln_mean, ln_rstd);
             mbar_wait_cluster(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-            epilogue_tile<BN>(epi, sh, t_addr, base + r_in, r_in < count, n_blk, (warp - G_EPI_WARP0) >> 2);
+            epilogue_tile<BN>(epi, sh, t_addr, base + r_in, r_in < count, n_blk, (warp - G_EPI_WARP0) >> 2, ln_mean, ln_rstd);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
@@ -850,7 +863,7 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
     }
     if (epi.ln_stats) {
         DRAG_REQUIRE(epi.mode != EPI_QKV_ROPE, "gemm: folded LayerNorm is not available with the RoPE epilogue");
-        DRAG_REQUIRE(epi.ln_s && epi.ln_c && epi.ln_parts >= 1 && epi.ln_k == K && !epi.bias,
+        DRAG_REQUIRE(epi.ln_s && epi.ln_c && epi.ln_parts >= 1 && epi.ln_parts <= 8 && epi.ln_k == K && !epi.bias,
                      "gemm: folded LayerNorm needs ln_s, ln_c, ln_parts, ln_k == K and no separate bias");
     }
     GemmShape sh{};

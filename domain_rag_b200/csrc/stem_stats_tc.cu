@@ -11,11 +11,13 @@
 //   with the per-input-row K block k = ci*8 + kx (kx = 7 and ci = 3 are zero padding): the im2col block of an input row is
 //   built ONCE in shared memory (hi and lo tiles) and reused by the up to four conv rows that touch it. Two input rows
 //   share one 128-byte-swizzled [128][64] K-major tile (the layout TMA would write), ring of 5 row pairs.
-//   warps 0-3   loaders: thread = pixel; 7-tap windows from global/L1, split to bf16 hi/lo, swizzled 16-byte stores,
-//               fence.proxy.async, arrive on the pair's `xfull` barrier;
-//   warp 4      MMA issuer: 7 x 2 k-steps x 3 split terms = 42 UMMA 128x64x16 per conv row into one of 8 TMEM accumulators,
+//   warps 0-7   two loader groups of 128 threads (thread = pixel), even / odd row pairs: 7-tap windows from global/L1 (all
+//               loads of a pair in flight at once), split to bf16 hi/lo, swizzled 16-byte stores, fence.proxy.async, arrive
+//               on the pair's `xfull` barrier. One group alone exposes a full memory latency per pair and leaves the
+//               tensor core idle three quarters of the time;
+//   warp 8      MMA issuer: 7 x 2 k-steps x 3 split terms = 42 UMMA 128x64x16 per conv row into one of 8 TMEM accumulators,
 //               tcgen05.commit -> `dfull`; releases row pairs (`xempty`) as conv rows retire;
-//   warps 8-11  pooling + statistics: thread = pixel. For pooled row py the three conv rows 2py-1..2py+1 are read from
+//   warps 12-15 pooling + statistics: thread = pixel. For pooled row py the three conv rows 2py-1..2py+1 are read from
 //               TMEM (vertical max), the horizontal 3-max comes from warp shuffles (+ a 1 KB shared-memory hand-off at
 //               warp edges), bias + ReLU after the max (both monotonic), then running sum / sum of squares per channel:
 //               even lanes own channels 0-31 of their pooled pixel, odd lanes channels 32-63. fp64 for the final moments.
@@ -27,7 +29,8 @@
 
 namespace drag {
 
-constexpr int TS_THREADS = 384;                 // 12 warps: 0-3 loaders, 4 MMA, 5-7 idle, 8-11 pooling
+constexpr int TS_THREADS = 512;                 // 16 warps: 0-3 / 4-7 loader groups (even / odd row pairs), 8 MMA, 9-11 idle,
+                                                // 12-15 pooling
 constexpr int TS_RING = 5;                      // input-row pairs resident
 constexpr int TS_XTILE = 128 * 128;             // [128 px][64 K] bf16 = 16 KB
 constexpr int TS_WTILE = 64 * 128;              // [64 ch][64 K] bf16 = 8 KB (two ky per tile)
@@ -102,7 +105,7 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
         }
         fence_mbar_init();
     }
-    if (warp == 4) {
+    if (warp == 8) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
@@ -126,13 +129,13 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    if (warp < 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     if (warp < 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
-    if (warp < 4) {
         // ------------------------------------------------------------------ loaders: thread = conv pixel px
-        const int px = tid;
+        const int px = tid & 127, grp = tid >> 7;             // group 0: even row pairs, group 1: odd row pairs
         // the zero chunks (ci = 3 of either row) of every ring slot are written once: no later store touches them
-        for (int slot = 0; slot < TS_RING; ++slot) {
+        for (int slot = grp; slot < TS_RING; slot += 2) {
             uint8_t* t0 = xring + static_cast<size_t>(slot) * 2 * TS_XTILE;
             *reinterpret_cast<uint4*>(t0 + sw128_chunk(px, 3)) = make_uint4(0, 0, 0, 0);
             *reinterpret_cast<uint4*>(t0 + sw128_chunk(px, 7)) = make_uint4(0, 0, 0, 0);
@@ -145,7 +148,7 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
         const bool ok0 = x0 >= 0, ok3 = x0 + 6 < 256;       // pairs 1, 2 are always inside
         for (int it = 0; it < n_img; ++it) {
             const size_t b = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(it) * gridDim.x;
-            for (int p = 0; p < 128; ++p) {
+            for (int p = grp; p < 128; p += 2) {
                 const int P = it * 128 + p, slot = P % TS_RING;
                 // all 24 loads of the pair in flight before the first conversion: ONE memory latency per row pair
                 float w[6][8];
@@ -201,7 +204,7 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
                 mbar_arrive(&xfull[slot]);
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ------------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
         const uint32_t x_addr = smem_u32(xring), w_addr = smem_u32(wt);
@@ -254,7 +257,7 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         // ------------------------------------------------------------------ pooling + statistics: thread = conv pixel px
-        const int w = warp - 8;                               // TMEM lane quarter (warp % 4 == w)
+        const int w = warp - 12;                              // TMEM lane quarter (warp % 4 == w)
         const int px = w * 32 + lane;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(w * 32) << 16);
         const bool odd = lane & 1;
@@ -359,7 +362,7 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
                 }
             }
             named_bar_sync(1, 128);
-            const int t = tid - 256;
+            const int t = tid - 384;
             if (t < 64) {
                 double mean = static_cast<double>(red[(0 * 2 + 0) * 64 + t]), m2 = static_cast<double>(red[(0 * 2 + 1) * 64 + t]);
                 double n = cnt;                                // 1024 values per warp partial
@@ -380,7 +383,7 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }

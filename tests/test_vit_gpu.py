@@ -42,6 +42,39 @@ def test_preprocess_matches_clip_transform(lib):
     assert float((t - ref).abs().max()) < 0.05
 
 
+@pytest.mark.parametrize("name,B", [("ViT-B/32", 9), ("ViT-L/14", 4)])
+def test_layernorm_folded_into_gemms_matches_separate_layernorm_and_oracle(lib, name, B):
+    """ln_1 / ln_2 folded into the QKV / MLP-up GEMM epilogues (row moments emitted by the residual GEMMs; gamma-scaled
+    weights; rstd * (acc - mean * s) + c) against the same tower with separate LayerNorm kernels and against the fp32 oracle,
+    with non-trivial gamma / beta and a residual stream whose row mean is far from zero."""
+    from domain_rag_b200 import clip
+    cfg = OV.CONFIGS[name]
+    state = OV.init_state(cfg, 2000)
+    g = torch.Generator().manual_seed(11)
+    for k in state:
+        if ".ln_" in k and k.endswith("weight"):
+            state[k] = 1.0 + 0.3 * torch.randn(state[k].shape, generator=g)
+        elif ".ln_" in k and k.endswith("bias"):
+            state[k] = 0.2 * torch.randn(state[k].shape, generator=g)
+    state["visual.class_embedding"] = state["visual.class_embedding"] + 0.5      # shifts the row mean of the class token
+    state = {k: v.bfloat16().float() for k, v in state.items()}
+    model, _ = clip.load(name, device="cuda", state_dict=state)
+    x = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(4))
+    want = OV.embed(state, cfg, x)
+    folded = model.encode_image(x.cuda(), normalize=True).cpu()
+    model.visual.fold_layernorm(False)
+    plain = model.encode_image(x.cuda(), normalize=True).cpu()
+    model.visual.fold_layernorm(True)
+    again = model.encode_image(x.cuda(), normalize=True).cpu()
+    assert torch.equal(folded, again)                                       # deterministic: no atomics in the moments
+    cos_fp = (folded * plain).sum(-1)
+    cos_fo, cos_po = (folded * want).sum(-1), (plain * want).sum(-1)
+    print(f"{name}: cosine folded-vs-plain {float(cos_fp.min()):.6f}, folded-vs-oracle {float(cos_fo.min()):.6f}, "
+          f"plain-vs-oracle {float(cos_po.min()):.6f}")
+    assert float(cos_fp.min()) >= 0.9995 and float(cos_fo.min()) >= 0.999 and float(cos_po.min()) >= 0.999
+    assert float((folded - want).abs().max()) <= 2e-2
+
+
 def test_uint8_ingest_equals_float_preprocess_and_chunks(lib):
     """uint8 pixels over PCIe + ToTensor/Normalize inside the patch kernel give the SAME embeddings as the
     reference contract preprocess(PIL) -> float tensor (same fp32 formula -> identical bf16 patches), and a batch larger than
