@@ -34,6 +34,7 @@ extern int g_gemm_force_1cta;
 extern int g_gemm_group_m;
 extern int g_attn_force_pp;
 extern int g_stem_force_ffma;
+extern int g_attn_split;
 int stem_stats_any_device(const void* img, int img_kind, int B, int H, int W, const float* w_fold, const float* b_fold,
                           float eps, float* out, cudaStream_t st);
 extern int g_gemm_group_n;
@@ -482,6 +483,7 @@ int drag_debug_set(int key, int value) {
     else if (key == 4) g_gemm_group_m = value;
     else if (key == 5) g_attn_force_pp = value;
     else if (key == 6) g_gemm_group_n = value;
+    else if (key == 7) g_attn_split = value;
     else if (key == 8) g_stem_force_ffma = value;
     else return fail(DRAG_ERR_INVALID, "drag_debug_set: unknown key");
     return DRAG_OK;

@@ -211,3 +211,27 @@ def test_flux_full_size_properties(lib):
     assert torch.equal(v1[0], v1[2]), "identical compositions in one batch differ"
     assert torch.equal(v1[1:2], one), "a batch row differs from its batch-1 run"
     assert torch.isfinite(v1.float()).all() and 1e-3 < float(v1.float().std()) < 1e3
+
+
+@pytest.mark.parametrize("B,H,S,split", [(1, 2, 128, 0), (2, 3, 300, 77), (1, 4, 1000, 0), (1, 24, 2265, 1241), (1, 2, 5337, 1241),
+                                         (2, 2, 89, 89), (1, 1, 64, 0), (1, 1, 65, 0), (1, 2, 193, 0)])
+def test_attention_both_head_dim_128_kernels_match_sdpa(ops, B, H, S, split):
+    """drag_debug_set key 7: the split-row kernel (two softmax warpgroups per query tile, default) and the one-thread-per-row
+    kernel are held to the same bar against fp32 SDPA, including sequence ends inside either column half of the last key tile."""
+    q, k, v = rnd((B, H, S, 128), 31), rnd((B, H, S, 128), 32), rnd((B, H, S, 128), 33)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    ref = ref.permute(0, 2, 1, 3).reshape(B, S, H * 128)
+    outs = []
+    for split_kernel in (1, 0):
+        ops.debug_set(7, split_kernel)
+        try:
+            o0, o1 = ops.attention(q, k, v, split)
+            torch.cuda.synchronize()
+        finally:
+            ops.debug_set(7, 1)
+        got = torch.cat([o0.view(B, split, -1), o1.view(B, S - split, -1)], 1) if 0 < split < S else \\
+            (o0.view(B, S, -1) if split == S else o1.view(B, S, -1))
+        assert rel_l2(got, ref) < 1e-2
+        assert (got.float() - ref).abs().max().item() < 2e-2
+        outs.append(got)
+    assert rel_l2(outs[0], outs[1]) < 5e-3
