@@ -147,7 +147,7 @@ class CLIPVisual:
         return wf, s, c
 
     def fold_layernorm(self, on: bool = True) -> None:
-        """A/B switch: True (default) = ln_1 / ln_2 folded into the GEMMs around them, False = separate LayerNorm kernels."""
+        """A/B switch: True = ln_1 / ln_2 folded into the GEMMs around them, False (default) = separate LayerNorm kernels."""
         _lib.check(_lib.load().drag_vit_set_option(self._h, 1, int(on)), "drag_vit_set_option")
 
     def eval(self):

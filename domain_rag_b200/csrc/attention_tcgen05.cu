@@ -443,7 +443,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 // "half 1 done" and the MMA issuer is unchanged. O is rescaled and stored in halves. 20 warps: {TMA, MMA, 2 idle} + 4 x 4.
 constexpr int AT_SPLIT_THREADS = 640;
 template <int HD>
-__global__ void __launch_bounds__(AT_SPLIT_THREADS, 1)
+// 640 threads x 80 registers at launch leave 14336 registers free; the data-movement warpgroup releases 128 x 16 more; the
+// 512 softmax threads then take 24 each (12288): a margin of 4096 (a re-balancing that needs EXACTLY the free pool never
+// completes - the first version of this kernel hung in setmaxnreg.inc).
+__global__ void __maxnreg__(80)
 attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, AttnArgs a) {
     constexpr bool PP = true;
@@ -613,7 +616,7 @@ attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __
         }
     }
     } else {
-    setmaxnreg_inc<112>();
+    setmaxnreg_inc<104>();
     const int wg = (warp - 4) >> 2;                        // 0..3
     const int x = wg >> 1, hf = wg & 1;                    // query tile, column half
     if (x == 0 || has_b) {

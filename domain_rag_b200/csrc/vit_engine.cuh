@@ -32,7 +32,8 @@ struct VitEngine {
                   *a = nullptr, *u = nullptr, *cls_ln = nullptr;
     float* emb = nullptr;
     float *stats_a = nullptr, *stats_b = nullptr;   // [max_batch * tokens][width / 128][2] row moments (LN folding)
-    int fold_ln = 1;                                  // 0: separate LayerNorm kernels (A/B comparisons, drag_vit_set_option)
+    int fold_ln = 0;                                  // 1: ln_1 / ln_2 folded into the GEMM epilogues (drag_vit_set_option key 1).
+                                                      // Measured on C2 (ViT-L/14): no faster than the separate kernels - off by default
 };
 
 int vit_create(const VitCfg& cfg, VitEngine** out);

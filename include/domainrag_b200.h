@@ -160,7 +160,7 @@ typedef struct {
 int drag_vit_create(const drag_vit_config* cfg, drag_vit_t** out);
 int drag_vit_destroy(drag_vit_t* h);
 int drag_vit_set_weights(drag_vit_t* h, const void* const* ptrs, int n);
-/* key 1: fold ln_1 / ln_2 into the GEMMs around them (default 1): the residual GEMMs' epilogues emit per-row moments, the QKV
+/* key 1: fold ln_1 / ln_2 into the GEMMs around them (default 0 - measured no faster on C2; kept for A/B): the residual GEMMs' epilogues emit per-row moments, the QKV
  * and MLP-up GEMMs run on the raw residual rows with gamma-scaled weights and apply rstd * (acc - mean * s) + c. 0 = separate
  * LayerNorm kernels (A/B comparisons). */
 int drag_vit_set_option(drag_vit_t* h, int key, int value);

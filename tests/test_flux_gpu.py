@@ -229,8 +229,10 @@ def test_attention_both_head_dim_128_kernels_match_sdpa(ops, B, H, S, split):
             torch.cuda.synchronize()
         finally:
             ops.debug_set(7, 1)
-        got = torch.cat([o0.view(B, split, -1), o1.view(B, S - split, -1)], 1) if 0 < split < S else \\
-            (o0.view(B, S, -1) if split == S else o1.view(B, S, -1))
+        if 0 < split < S:
+            got = torch.cat([o0.view(B, split, -1), o1.view(B, S - split, -1)], 1)
+        else:
+            got = o0.view(B, S, -1) if split == S else o1.view(B, S, -1)
         assert rel_l2(got, ref) < 1e-2
         assert (got.float() - ref).abs().max().item() < 2e-2
         outs.append(got)

@@ -61,11 +61,13 @@ def test_layernorm_folded_into_gemms_matches_separate_layernorm_and_oracle(lib, 
     model, _ = clip.load(name, device="cuda", state_dict=state)
     x = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(4))
     want = OV.embed(state, cfg, x)
+    model.visual.fold_layernorm(True)
     folded = model.encode_image(x.cuda(), normalize=True).cpu()
     model.visual.fold_layernorm(False)
     plain = model.encode_image(x.cuda(), normalize=True).cpu()
     model.visual.fold_layernorm(True)
     again = model.encode_image(x.cuda(), normalize=True).cpu()
+    model.visual.fold_layernorm(False)
     assert torch.equal(folded, again)                                       # deterministic: no atomics in the moments
     cos_fp = (folded * plain).sum(-1)
     cos_fo, cos_po = (folded * want).sum(-1), (plain * want).sum(-1)
