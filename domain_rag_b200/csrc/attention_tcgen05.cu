@@ -443,10 +443,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 // "half 1 done" and the MMA issuer is unchanged. O is rescaled and stored in halves. 20 warps: {TMA, MMA, 2 idle} + 4 x 4.
 constexpr int AT_SPLIT_THREADS = 640;
 template <int HD>
-// 640 threads x 80 registers at launch leave 14336 registers free; the data-movement warpgroup releases 128 x 16 more; the
-// 512 softmax threads then take 24 each (12288): a margin of 4096 (a re-balancing that needs EXACTLY the free pool never
-// completes - the first version of this kernel hung in setmaxnreg.inc).
-__global__ void __maxnreg__(80)
+// Register re-balancing: setmaxnreg.inc can only take what setmaxnreg.dec of the same CTA has released (registers of the SM
+// that were never allocated to the CTA do not count; a request beyond the released pool waits forever - the first two
+// versions of this kernel hung there). 640 threads launch with 96 registers; the data-movement warpgroup drops to 64
+// (releases 128 x 32 = 4096) and the 512 softmax threads rise to 104 (take 512 x 8 = 4096).
+__global__ void __launch_bounds__(AT_SPLIT_THREADS, 1)
 attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, AttnArgs a) {
     constexpr bool PP = true;

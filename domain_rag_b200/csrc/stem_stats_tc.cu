@@ -206,51 +206,65 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
         }
     } else if (warp == 8) {
         // ------------------------------------------------------------------ MMA issuer
+        // Everything the issue loop needs is kept in running counters updated with add / compare / select only (no % or /),
+        // and the tap loop is fully unrolled, so that ring slots, phases and UMMA descriptors live in UNIFORM registers:
+        // descriptor arithmetic in vector registers costs an R2UR per operand and made this loop, not the tensor core, the
+        // bottleneck (148 cycles per 32-cycle MMA in the first version).
         constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
-        const uint32_t x_addr = smem_u32(xring), w_addr = smem_u32(wt);
+        const uint64_t x_desc0 = umma_desc_k_sw128(smem_u32(xring)), w_desc0 = umma_desc_k_sw128(smem_u32(wt));
+        int s0 = TS_RING - 2;                                  // ring slot of pair (cy - 2); pairs run on across images
+        int w_slot = 0, w_phase = 0;                           // next pair to wait for: its slot and barrier phase
+        int buf = 0, d_phase = 0;                              // accumulator of the current conv row and its phase
         for (int it = 0; it < n_img; ++it) {
             int pairs_ready = -1;                              // highest pair of this image already waited for
             for (int cy = 0; cy < 128; ++cy) {
-                const int R = it * 128 + cy, buf = R % TS_DBUF;
-                mbar_wait(&dempty[buf], ((R / TS_DBUF) & 1) ^ 1);
+                mbar_wait(&dempty[buf], d_phase ^ 1);
                 const int p_hi = (cy + 1 < 127) ? cy + 1 : 127;
                 while (pairs_ready < p_hi) {
                     ++pairs_ready;
-                    const int P = it * 128 + pairs_ready;
-                    mbar_wait(&xfull[P % TS_RING], (P / TS_RING) & 1);
+                    mbar_wait(&xfull[w_slot], w_phase);
+                    if (++w_slot == TS_RING) { w_slot = 0; w_phase ^= 1; }
                 }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * 64;
-                bool first = true;
-                for (int ky = 0; ky < 7; ++ky) {
-                    const int y = 2 * cy - 3 + ky;
-                    if (y < 0 || y > 255) continue;            // zero rows of the padding contribute nothing
-                    const int P = it * 128 + (y >> 1), slot = P % TS_RING;
-                    const uint32_t a_hi = x_addr + slot * 2 * TS_XTILE + (y & 1) * 64;
-                    const uint32_t b_hi = w_addr + (ky >> 1) * TS_WTILE + (ky & 1) * 64;
-                    if (elect_one()) {
+                uint32_t acc = 0;
 #pragma unroll
-                        for (int s = 0; s < 2; ++s) {
-                            const uint64_t ah = umma_desc_k_sw128(a_hi + s * 32), al = umma_desc_k_sw128(a_hi + TS_XTILE + s * 32);
-                            const uint64_t bh = umma_desc_k_sw128(b_hi + s * 32), bl = umma_desc_k_sw128(b_hi + 4 * TS_WTILE + s * 32);
-                            tc_mma_f16(d_tmem, ah, bh, idesc, !(first && s == 0));
+                for (int ky = 0; ky < 7; ++ky) {
+                    // input row y = 2cy - 3 + ky lives in pair (cy - 2) + (ky + 1) / 2, half (ky + 1) & 1
+                    const bool valid = (2 * cy - 3 + ky >= 0) && (2 * cy - 3 + ky <= 255);   // padding rows contribute nothing
+                    int slot = s0 + ((ky + 1) >> 1);
+                    slot = slot >= TS_RING ? slot - TS_RING : slot;
+                    const uint64_t ah = x_desc0 + static_cast<uint64_t>((slot * 2 * TS_XTILE + ((ky + 1) & 1) * 64) >> 4);
+                    const uint64_t al = ah + (TS_XTILE >> 4);
+                    const uint64_t bh = w_desc0 + (((ky >> 1) * TS_WTILE + (ky & 1) * 64) >> 4);
+                    const uint64_t bl = bh + ((4 * TS_WTILE) >> 4);
+                    if (valid) {
+                        if (elect_one()) {
+                            tc_mma_f16(d_tmem, ah, bh, idesc, acc);
                             tc_mma_f16(d_tmem, ah, bl, idesc, 1);
                             tc_mma_f16(d_tmem, al, bh, idesc, 1);
+                            tc_mma_f16(d_tmem, ah + 2, bh + 2, idesc, 1);      // second k-step: +32 bytes along K
+                            tc_mma_f16(d_tmem, ah + 2, bl + 2, idesc, 1);
+                            tc_mma_f16(d_tmem, al + 2, bh + 2, idesc, 1);
                         }
+                        __syncwarp();
+                        acc = 1;
                     }
-                    __syncwarp();
-                    first = false;
                 }
                 if (elect_one()) {
                     tc_commit(&dfull[buf]);
-                    // conv row cy was the last user of pair cy-2; the image's last row also retires pairs 126 and 127
-                    if (cy >= 2) tc_commit(&xempty[(it * 128 + cy - 2) % TS_RING]);
+                    // conv row cy was the last user of pair cy-2 (slot s0); the image's last row also retires pairs 126, 127
+                    if (cy >= 2) tc_commit(&xempty[s0]);
                     if (cy == 127) {
-                        tc_commit(&xempty[(it * 128 + 126) % TS_RING]);
-                        tc_commit(&xempty[(it * 128 + 127) % TS_RING]);
+                        const int s1 = (s0 + 1 >= TS_RING) ? s0 + 1 - TS_RING : s0 + 1;
+                        const int s2 = (s0 + 2 >= TS_RING) ? s0 + 2 - TS_RING : s0 + 2;
+                        tc_commit(&xempty[s1]);
+                        tc_commit(&xempty[s2]);
                     }
                 }
                 __syncwarp();
+                if (++s0 == TS_RING) s0 = 0;
+                if (++buf == TS_DBUF) { buf = 0; d_phase ^= 1; }
             }
         }
     }

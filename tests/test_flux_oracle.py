@@ -96,3 +96,58 @@ def test_product_and_oracle_layouts_agree():
     order = F.param_order(F.FluxConfig())
     assert len(order) == 20 + 20 * 19 + 8 * 38 and len(set(order)) == len(order)
     assert F.flow_match_sigmas(50, 4096) == pytest.approx(OF.flow_match_sigmas(50, 4096).tolist())
+
+
+def test_sampler_glue_matches_torchtitan_sampling():
+    """Second statement of the sampler glue (oracle/pipelines.py and the schedule had no independent check):
+    torchtitan's BFL-style sampling.py - get_schedule (time_shift of linspace(1, 0, T+1), mu from the token count),
+    position encodings, 2x2 latent packing and the Euler update `latents + (t_prev - t_curr) * pred` (:38-66, :195-209) -
+    against oracle.flux.sample / flow_match_sigmas / image_ids / pack_latents on the same model and noise."""
+    from torchtitan.experiments.flux import sampling as TS
+    from torchtitan.experiments.flux import utils as TU
+    cfg, p, m = build_pair(seed=3)
+    T, H, W, s_txt = 5, 64, 96, 12
+    h, w = H // 8, W // 8
+    seq = (h // 2) * (w // 2)
+    sched = TS.get_schedule(T, seq, shift=True)
+    assert OF.flow_match_sigmas(T, seq).tolist() == pytest.approx(sched, rel=1e-6, abs=1e-7)
+    assert torch.equal(TU.create_position_encoding_for_latents(1, h, w)[0], OF.image_ids(h // 2, w // 2))
+    g = torch.Generator().manual_seed(9)
+    z = torch.randn(2, 16, h, w, generator=g)
+    ctx, pooled = torch.randn(2, s_txt, 48, generator=g), torch.randn(2, 32, generator=g)
+    assert torch.equal(TU.pack_latents(z), OF.pack_latents(z))
+    lat = TU.pack_latents(z)
+    pos = TU.create_position_encoding_for_latents(2, h, w)
+    with torch.no_grad():
+        for t_curr, t_prev in zip(sched[:-1], sched[1:]):
+            pred = m(img=lat, img_ids=pos, txt=ctx, txt_ids=torch.zeros(2, s_txt, 3), y=pooled,
+                     timesteps=torch.full((2,), t_curr))
+            lat = lat + (t_prev - t_curr) * pred
+        want = TU.unpack_latents(lat, h, w)
+        got = OF.unpack_latents(OF.sample(p, cfg, OF.pack_latents(z), ctx, pooled, 0.0, T, h // 2, w // 2), h, w)
+    torch.testing.assert_close(got, want, rtol=1e-3, atol=1e-3)
+
+
+def test_guidance_embedder_is_the_timestep_embedder_applied_to_the_guidance_scale():
+    """The guidance branch has no second implementation offline (torchtitan's FluxModel is the schnell variant). What can be
+    pinned: diffusers' CombinedTimestepGuidanceTextProjEmbeddings adds THREE terms - timestep MLP(sinusoid(1000 t)), guidance
+    MLP(sinusoid(1000 g)) with the same sinusoid, pooled-text MLP - so with g_in := t_in and g := t the conditioning vector must
+    equal 2 * t_emb + p_emb, and a model without the branch must equal the same model with a zeroed guidance MLP."""
+    cfg = OF.FluxConfig(in_channels=64, d=256, heads=2, n_double=1, n_single=1, txt_dim=48, pooled_dim=32, guidance=True)
+    p = OF.init_params(cfg, seed=4)
+    for k in ("w1", "b1", "w2", "b2"):
+        p[f"g_in.{k}"] = p[f"t_in.{k}"].clone()
+    t = torch.tensor([0.7, 0.2])
+    pooled = torch.randn(2, 32, generator=torch.Generator().manual_seed(1))
+    vec = OF.temb_vector(p, cfg, t, t, pooled)
+    t_emb = OF._mlp_embed(p, "t_in", OF.timestep_embedding(t))
+    p_emb = OF._mlp_embed(p, "p_in", pooled)
+    torch.testing.assert_close(vec, 2 * t_emb + p_emb, rtol=1e-6, atol=1e-6)
+    emb = OF.timestep_embedding(torch.tensor([0.03]))            # diffusers: guidance * 1000 -> sinusoid, cos first
+    assert emb.shape == (1, 256) and float(emb[0, 0]) == pytest.approx(__import__("math").cos(30.0), abs=1e-5)
+    assert float(emb[0, 128]) == pytest.approx(__import__("math").sin(30.0), abs=1e-5)
+    cfg0 = OF.FluxConfig(in_channels=64, d=256, heads=2, n_double=1, n_single=1, txt_dim=48, pooled_dim=32, guidance=False)
+    pz = dict(p)
+    pz["g_in.w2"], pz["g_in.b2"] = torch.zeros_like(p["g_in.w2"]), torch.zeros_like(p["g_in.b2"])
+    torch.testing.assert_close(OF.temb_vector(pz, cfg, t, torch.tensor([30.0, 2.5]), pooled),
+                               OF.temb_vector(p, cfg0, t, None, pooled), rtol=1e-6, atol=1e-6)
