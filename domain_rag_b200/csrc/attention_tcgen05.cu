@@ -441,6 +441,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 // through shared memory (one 256-thread named barrier per key tile, which also orders the partner's S reads before this
 // thread's in-place P writes); keys [0,64) are exactly half 0's work, so `p_half` / `p_full` are simply "half 0 done" /
 // "half 1 done" and the MMA issuer is unchanged. O is rescaled and stored in halves. 20 warps: {TMA, MMA, 2 idle} + 4 x 4.
+// MEASURED (profiles/r02_attention_split_ab.txt): correct (same parity bar) but 13 % slower than one thread per row - 1115 vs
+// 1285 TFLOP/s at B = 4, S = 5337: the exchange barrier couples the two halves and the 104-register budget spills. Kept
+// behind drag_debug_set key 7 as a documented negative result; the default path is the one-thread-per-row kernel.
 constexpr int AT_SPLIT_THREADS = 640;
 template <int HD>
 // Register re-balancing: setmaxnreg.inc can only take what setmaxnreg.dec of the same CTA has released (registers of the SM
@@ -806,8 +809,8 @@ static int launch_attention_split(const __nv_bfloat16* q, const __nv_bfloat16* k
 // Debug knobs kept for ABI stability (drag_debug_set keys 1/2); unused by the current kernel.
 uint32_t g_attn_v_lbo = 0, g_attn_v_sbo = 1024;
 int g_attn_force_pp = 0;      // drag_debug_set key 5: 1 = always the two-tile ping-pong kernel (A/B comparisons)
-int g_attn_split = 1;         // drag_debug_set key 7: head dim 128: 1 = split-row kernel (two softmax warpgroups per query tile),
-                              // 0 = one thread per row (A/B comparisons)
+int g_attn_split = 0;         // drag_debug_set key 7: head dim 128: 1 = split-row kernel (two softmax warpgroups per query tile),
+                              // 0 = one thread per row (default: the split kernel measured 13 % SLOWER, see the kernel)
 
 int attention_bf16(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int B, int H, int S,
                    int head_dim, int split, __nv_bfloat16* out0, int ld0, __nv_bfloat16* out1, int ld1,

@@ -35,6 +35,7 @@ extern int g_gemm_group_m;
 extern int g_attn_force_pp;
 extern int g_stem_force_ffma;
 extern int g_attn_split;
+extern int g_gemm_no_wide_st;
 int stem_stats_any_device(const void* img, int img_kind, int B, int H, int W, const float* w_fold, const float* b_fold,
                           float eps, float* out, cudaStream_t st);
 extern int g_gemm_group_n;
@@ -485,6 +486,7 @@ int drag_debug_set(int key, int value) {
     else if (key == 6) g_gemm_group_n = value;
     else if (key == 7) g_attn_split = value;
     else if (key == 8) g_stem_force_ffma = value;
+    else if (key == 9) g_gemm_no_wide_st = value;
     else return fail(DRAG_ERR_INVALID, "drag_debug_set: unknown key");
     return DRAG_OK;
 }

@@ -56,6 +56,8 @@ struct GemmEpi {
     const float* ln_s = nullptr;          // [N] fp32
     const float* ln_c = nullptr;          // [N] fp32
     float ln_eps = 1e-5f;
+    int wide_st = 0;                      // set by the launcher: 32-byte (STG.256) row stores are legal for this output
+    int wide_ld = 0;                      //                      32-byte (LDG.256) loads of the residual rows
 };
 
 // C[M,N] = A[M,K] (bf16 row-major, lda) x W[N,K]^T (bf16 row-major, ldw), fp32 accumulate in TMEM.

@@ -155,12 +155,52 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
     *reinterpret_cast<uint4*>(dst) = u;
 }
 
+// 16 bf16 = one full 32-byte sector per lane in ONE store (STG.256, sm_100). In the row-per-thread epilogue a warp store
+// touches 32 different rows: with 16-byte stores every instruction writes 32 HALF sectors and the K = 1024 GEMMs of the ViT
+// towers (output bytes large next to their 64 k-steps) were bound by the store path at 41-71 % tensor-pipe utilisation.
+__device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const float* v) {
+    uint32_t u[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        __nv_bfloat162 p = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        u[i] = *reinterpret_cast<uint32_t*>(&p);
+    }
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(u[0]), "r"(u[1]), "r"(u[2]),
+                 "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+                 : "memory");
+}
+// store 32 consecutive bf16 of one row: 2 x 32 B when the destination allows it, else 4 x 16 B
+__device__ __forceinline__ void store_row32(__nv_bfloat16* dst, const float* v, bool wide) {
+    if (wide) {
+        store_bf16x16(dst, v);
+        store_bf16x16(dst + 16, v + 16);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) store_bf16x8(dst + j, v + j);
+    }
+}
+
 __device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* src, float* v) {
     uint4 u = *reinterpret_cast<const uint4*>(src);
     const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         float2 f = __bfloat1622float2(p[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+
+// 16 bf16 (one 32-byte sector) per lane in one load (LDG.256): the residual rows of the gate*x+residual epilogue.
+__device__ __forceinline__ void load_bf16x16(const __nv_bfloat16* src, float* v) {
+    uint32_t u[8];
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                 : "l"(src)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[i]));
         v[2 * i] = f.x;
         v[2 * i + 1] = f.y;
     }
@@ -200,10 +240,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, float (&v)[32],
         for (int j = 0; j < 32; ++j) v[j] = v[j] * sigmoid_f(v[j]);
     } else if (e.mode == EPI_GATE_RESID) {
         const int b = row / e.rows_per_batch;
+        float rr[32];
+        if (e.wide_ld) {
+            load_bf16x16(e.resid + static_cast<size_t>(row) * e.ldr + col0, rr);
+            load_bf16x16(e.resid + static_cast<size_t>(row) * e.ldr + col0 + 16, rr + 16);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) load_bf16x8(e.resid + static_cast<size_t>(row) * e.ldr + col0 + j, rr + j);
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-            float r[8];
-            load_bf16x8(e.resid + static_cast<size_t>(row) * e.ldr + col0 + j, r);
+            const float* r = rr + j;
             if (e.gate) {
                 float g[8];
                 load_bf16x8(e.gate + static_cast<size_t>(b) * e.gate_ld + col0 + j, g);
@@ -225,8 +272,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, float (&v)[32],
         const int pos = e.tok_offset + (row - b * e.rows_per_batch);
         __nv_bfloat16* base = which == 0 ? e.q_out : (which == 1 ? e.k_out : e.v_out);
         __nv_bfloat16* dst = base + ((static_cast<size_t>(b) * e.heads + head) * e.s_total + pos) * e.head_dim + c;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) store_bf16x8(dst + j, &v[j]);
+        store_row32(dst, v, e.wide_st != 0);
     } else if (e.mode == EPI_BIAS_F32) {
         float* dst = e.out_f32 + static_cast<size_t>(row) * e.ldo + col0;
 #pragma unroll
@@ -234,8 +280,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, float (&v)[32],
             *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     } else {
         __nv_bfloat16* dst = e.out + static_cast<size_t>(row) * e.ldo + col0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) store_bf16x8(dst + j, &v[j]);
+        store_row32(dst, v, e.wide_st != 0);
         if (e.stats_out) {      // moments of the values as stored (bf16), for the LayerNorm folded into the next GEMM
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -776,6 +821,7 @@ static int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 }
 
 
+int g_gemm_no_wide_st = 0;   // drag_debug_set key 9: 1 = 16-byte epilogue stores only (A/B comparisons)
 int g_gemm_force_1cta = 0;   // drag_debug_set key 3: 1 = always use the single-CTA kernel (A/B comparisons)
 int g_gemm_group_n = 0;      // drag_debug_set key 6: > 0 = column-group raster with this many column tiles per group
 int g_gemm_group_m = 0;      // drag_debug_set key 4: > 0 = force the raster group size (1 << 20 = plain row-fastest order)
@@ -783,9 +829,18 @@ int g_gemm_group_m = 0;      // drag_debug_set key 4: > 0 = force the raster gro
 // Shared launch logic: builds the operand tensor maps (A from a row-major matrix unless a ready map is given) and
 // picks the CTA-pair kernel whenever there is more than one 128-row tile of work and N tiles evenly.
 static int dispatch_gemm(const __nv_bfloat16* A, const CUtensorMap* tmA_ready, int M, int K, int lda,
-                         const __nv_bfloat16* W, int ldw, GemmShape sh, int bn, int m_tiles, const GemmEpi& epi,
+                         const __nv_bfloat16* W, int ldw, GemmShape sh, int bn, int m_tiles, const GemmEpi& epi_in,
                          cudaStream_t st) {
     const int N = sh.N;
+    GemmEpi epi = epi_in;
+    // 32-byte stores need 32-byte aligned row segments: base pointers and row pitches (32-column chunks start at multiples of 64 B)
+    if (epi.mode == EPI_QKV_SPLIT)
+        epi.wide_st = ((reinterpret_cast<uintptr_t>(epi.q_out) | reinterpret_cast<uintptr_t>(epi.k_out) |
+                        reinterpret_cast<uintptr_t>(epi.v_out)) & 31) == 0 && (epi.head_dim % 16) == 0;
+    else if (epi.out)
+        epi.wide_st = (reinterpret_cast<uintptr_t>(epi.out) & 31) == 0 && (epi.ldo % 16) == 0;
+    epi.wide_ld = epi.resid && (reinterpret_cast<uintptr_t>(epi.resid) & 31) == 0 && (epi.ldr % 16) == 0;
+    if (g_gemm_no_wide_st) epi.wide_st = epi.wide_ld = 0;
     const bool pair_ok = !g_gemm_force_1cta && m_tiles > 1 && (bn == 256 || bn == 128) && N % bn == 0;
     CUtensorMap tmA, tmB;
     int rc;

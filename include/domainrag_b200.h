@@ -229,8 +229,8 @@ int drag_launch_count(int64_t* count, int reset);
  * instead of the CTA-pair cta_group::2 kernel; key 4: > 0 = force the GEMM tile-raster group size, 1 << 20 = plain
  * row-fastest order; key 5: 1 = head-dim-64 attention always on the two-tile ping-pong kernel; key 6: > 0 = force the
  * column-group raster with that many column tiles per group; key 7: head-dim-128 attention:
- * 1 = split-row kernel, two softmax warpgroups per query tile (default), 0 = one thread per row; key 8: 1 = stem statistics on the FP32 CUDA-core kernel instead of
- * the tensor-core kernel). */
+ * 1 = split-row kernel, two softmax warpgroups per query tile (measured slower), 0 = one thread per row (default); key 8: 1 = stem statistics on the FP32 CUDA-core kernel instead of
+ * the tensor-core kernel; key 9: 1 = GEMM epilogues store 16 bytes per lane instead of 32). */
 int drag_debug_set(int key, int value);
 
 #ifdef __cplusplus

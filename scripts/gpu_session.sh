@@ -15,6 +15,9 @@ for stage in "$@"; do
     tests_x)      run 1500 tests python -m pytest tests -m gpu -x -q --durations=10 ;;
     tests_new)    run 900 tests_new python -m pytest tests/test_full_depth_gpu.py tests/test_cli_gpu.py tests/test_pipelines_gpu.py tests/test_retrieval_cli_gpu.py tests/test_topk_gpu.py -m gpu -q -s --durations=10 ;;
     tests_attn)   run 600 tests_attn python -m pytest tests/test_flux_gpu.py tests/test_stem_gpu.py tests/test_vit_gpu.py -m gpu -q -s --durations=5 ;;
+    attn_quick)   run 150 attn_tests python -m pytest tests/test_flux_gpu.py -k "attention" -m gpu -q -x
+                  run 120 attn python scripts/bench_attn.py ;;
+    epilogue)     run 200 epilogue python scripts/bench_epilogue.py ;;
     smoke)        run 300 smoke python -c "import __graft_entry__ as g; g.smoke()" ;;
     bench)        run 1200 bench $(launch) bench.py --gpus $N --steps ${STEPS:-2} --warmup 3 ;;
     bench_fast)   run 900 bench_fast $(launch) bench.py --gpus $N --steps ${STEPS:-2} --warmup 3 --no-secondary --no-gpu-baseline ;;
@@ -30,7 +33,8 @@ for stage in "$@"; do
     ncu_hot)      run 600 ncu_hot ncu --set full --clock-control none --import-source on -k regex:"gemm_bf16|attention_tcgen05" -s 4 -c 4 -o gpurun_out/${tag}_hot python scripts/prof_kernels.py 4 ;;
     ncu_attn)     run 400 ncu_attn ncu --set full --clock-control none --import-source on -k regex:"attention_tcgen05" -s 2 -c 2 -o gpurun_out/${tag}_attn python scripts/prof_kernels.py 4 ;;
     ncu_stem)     run 300 ncu_stem ncu --set full --clock-control none --import-source on -k regex:"stem_stats" -s 1 -c 1 -o gpurun_out/${tag}_stem python scripts/prof_stem.py ;;
-    ncu_vit)      run 600 ncu_vit ncu --set full --clock-control none --import-source on -k regex:"gemm_bf16|attention_tcgen05|layernorm" -s 30 -c 8 -o gpurun_out/${tag}_vit python scripts/prof_vit.py ;;
+    ncu_vit)      run 400 ncu_vit ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:"gemm_bf16|attention_tcgen05|layernorm" -s 14 -c 14 --csv --log-file gpurun_out/${tag}_vit_plain.csv python scripts/prof_vit.py plain
+                  run 400 ncu_vit_fold ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:"gemm_bf16|attention_tcgen05|layernorm" -s 10 -c 10 --csv --log-file gpurun_out/${tag}_vit_fold.csv python scripts/prof_vit.py fold ;;
     *)            echo "unknown stage $stage" ;;
   esac
 done
