@@ -840,6 +840,10 @@ static int dispatch_gemm(const __nv_bfloat16* A, const CUtensorMap* tmA_ready, i
     else if (epi.out)
         epi.wide_st = (reinterpret_cast<uintptr_t>(epi.out) & 31) == 0 && (epi.ldo % 16) == 0;
     epi.wide_ld = epi.resid && (reinterpret_cast<uintptr_t>(epi.resid) & 31) == 0 && (epi.ldr % 16) == 0;
+    // Measured (profiles/r02_gemm_epilogue_store_width.txt): 32-byte stores lift the store-bound K = 1024 shapes of the ViT
+    // blocks by 12-35 % (QKV 1109 -> 1495 TFLOP/s) and do nothing for K >= 3072, where the epilogue hides behind 48+ k-steps
+    // (Flux MLP-up 1486 vs 1405): wide accesses only where the k loop is short.
+    if (K > 2048) epi.wide_st = epi.wide_ld = 0;
     if (g_gemm_no_wide_st) epi.wide_st = epi.wide_ld = 0;
     const bool pair_ok = !g_gemm_force_1cta && m_tiles > 1 && (bn == 256 || bn == 128) && N % bn == 0;
     CUtensorMap tmA, tmB;
