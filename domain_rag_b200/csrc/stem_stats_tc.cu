@@ -11,16 +11,17 @@
 //   with the per-input-row K block k = ci*8 + kx (kx = 7 and ci = 3 are zero padding): the im2col block of an input row is
 //   built ONCE in shared memory (hi and lo tiles) and reused by the up to four conv rows that touch it. Two input rows
 //   share one 128-byte-swizzled [128][64] K-major tile (the layout TMA would write), ring of 5 row pairs.
-//   warps 0-7   two loader groups of 128 threads (thread = pixel), even / odd row pairs: 7-tap windows from global/L1 (all
-//               loads of a pair in flight at once), split to bf16 hi/lo, swizzled 16-byte stores, fence.proxy.async, arrive
-//               on the pair's `xfull` barrier. One group alone exposes a full memory latency per pair and leaves the
-//               tensor core idle three quarters of the time;
-//   warp 8      MMA issuer: 7 x 2 k-steps x 3 split terms = 42 UMMA 128x64x16 per conv row into one of 8 TMEM accumulators,
+//   warps 0-3   loaders (thread = pixel): 7-tap windows from global/L1 (all loads of a row pair in flight at once), split to
+//               bf16 hi/lo, swizzled 16-byte stores, fence.proxy.async, arrive on the pair's `xfull` barrier. The folded
+//               BatchNorm bias rides in the GEMM: the padding tap (kx = 7) of channel 0 is a column of ones in A and holds the
+//               bias in the ky = 3 weight block, so every conv row receives it exactly once;
+//   warp 4      MMA issuer: 7 x 2 k-steps x 3 split terms = 42 UMMA 128x64x16 per conv row into one of 8 TMEM accumulators,
 //               tcgen05.commit -> `dfull`; releases row pairs (`xempty`) as conv rows retire;
-//   warps 12-15 pooling + statistics: thread = pixel. For pooled row py the three conv rows 2py-1..2py+1 are read from
-//               TMEM (vertical max), the horizontal 3-max comes from warp shuffles (+ a 1 KB shared-memory hand-off at
-//               warp edges), bias + ReLU after the max (both monotonic), then running sum / sum of squares per channel:
-//               even lanes own channels 0-31 of their pooled pixel, odd lanes channels 32-63. fp64 for the final moments.
+//   warps 8-15  pooling + statistics, two warpgroups splitting the CHANNELS (0-31 / 32-63; the profile of the one-warpgroup
+//               version showed this stage, not the tensor core, bounding the kernel): thread = pixel. For pooled row py the
+//               three conv rows 2py-1..2py+1 are read from TMEM (vertical max), the horizontal 3-max comes from warp shuffles
+//               (+ a shared-memory hand-off at warp edges), ReLU after the max (monotonic), then shifted running moments per
+//               channel: even lanes own the first 16 channels of their pooled pixel, odd lanes the other 16. fp64 merge.
 // Neither the 64x128x128 conv map nor the 64x64x64 pooled map ever leaves the SM. Input: fp32 [B][3][256][256] in [0,1] (the
 // reference contract) or uint8 pixels (scaled by 1/255 in the loader).
 #include "common.cuh"
@@ -29,8 +30,8 @@
 
 namespace drag {
 
-constexpr int TS_THREADS = 512;                 // 16 warps: 0-3 / 4-7 loader groups (even / odd row pairs), 8 MMA, 9-11 idle,
-                                                // 12-15 pooling
+constexpr int TS_THREADS = 512;                 // 16 warps: 0-3 loaders, 4 MMA, 5-7 idle, 8-11 / 12-15 pooling (channels
+                                                // 0-31 / 32-63)
 constexpr int TS_RING = 5;                      // input-row pairs resident
 constexpr int TS_XTILE = 128 * 128;             // [128 px][64 K] bf16 = 16 KB
 constexpr int TS_WTILE = 64 * 128;              // [64 ch][64 K] bf16 = 8 KB (two ky per tile)
@@ -87,7 +88,7 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
     uint64_t* xfull = bars;                  // [5]  count 128 (loader threads)
     uint64_t* xempty = bars + TS_RING;       // [5]  count 1 (tcgen05.commit)
     uint64_t* dfull = bars + 2 * TS_RING;    // [8]  count 1 (tcgen05.commit)
-    uint64_t* dempty = dfull + TS_DBUF;      // [8]  count 4 (one per pooling warp)
+    uint64_t* dempty = dfull + TS_DBUF;      // [8]  count 8 (one per pooling warp)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + TS_DBUF);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -101,11 +102,11 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
         }
         for (int i = 0; i < TS_DBUF; ++i) {
             mbar_init(&dfull[i], 1);
-            mbar_init(&dempty[i], 4);
+            mbar_init(&dempty[i], 8);                        // every warp of both pooling warpgroups
         }
         fence_mbar_init();
     }
-    if (warp == 8) {
+    if (warp == 4) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
@@ -117,6 +118,7 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
 #pragma unroll
         for (int kx = 0; kx < 8; ++kx)
             x[kx] = (ky < 7 && ci < 3 && kx < 7) ? w_fold[((ch * 3 + ci) * 7 + ky) * 7 + kx] : 0.f;
+        if (ky == 3 && ci == 0) x[7] = b_fold[ch];           // multiplies the column of ones the loaders put at (ci 0, kx 7)
         uint4 hi, lo;
         split_bf16x8(x, hi, lo);
         const uint32_t off = static_cast<uint32_t>(t) * TS_WTILE + sw128_chunk(ch, c);
@@ -129,13 +131,13 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 12) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");      // 256 threads release 32 each; the 256 pooling threads take 32 each
+    if (warp < 4) {
         // ------------------------------------------------------------------ loaders: thread = conv pixel px
-        const int px = tid & 127, grp = tid >> 7;             // group 0: even row pairs, group 1: odd row pairs
+        const int px = tid;
         // the zero chunks (ci = 3 of either row) of every ring slot are written once: no later store touches them
-        for (int slot = grp; slot < TS_RING; slot += 2) {
+        for (int slot = 0; slot < TS_RING; ++slot) {
             uint8_t* t0 = xring + static_cast<size_t>(slot) * 2 * TS_XTILE;
             *reinterpret_cast<uint4*>(t0 + sw128_chunk(px, 3)) = make_uint4(0, 0, 0, 0);
             *reinterpret_cast<uint4*>(t0 + sw128_chunk(px, 7)) = make_uint4(0, 0, 0, 0);
@@ -148,7 +150,7 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
         const bool ok0 = x0 >= 0, ok3 = x0 + 6 < 256;       // pairs 1, 2 are always inside
         for (int it = 0; it < n_img; ++it) {
             const size_t b = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(it) * gridDim.x;
-            for (int p = grp; p < 128; p += 2) {
+            for (int p = 0; p < 128; ++p) {
                 const int P = it * 128 + p, slot = P % TS_RING;
                 // all 24 loads of the pair in flight before the first conversion: ONE memory latency per row pair
                 float w[6][8];
@@ -193,7 +195,7 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
                     float x[8];                               // taps kx = 0..6 are window elements 1..7; kx = 7 is padding
 #pragma unroll
                     for (int kx = 0; kx < 7; ++kx) x[kx] = w[c][kx + 1];
-                    x[7] = 0.f;
+                    x[7] = (ci == 0) ? 1.f : 0.f;             // the ones column that carries the bias (weights: ky 3, ci 0, kx 7)
                     uint4 hi, lo;
                     split_bf16x8(x, hi, lo);
                     const uint32_t off = sw128_chunk(px, h * 4 + ci);
@@ -204,7 +206,7 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
                 mbar_arrive(&xfull[slot]);
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == 4) {
         // ------------------------------------------------------------------ MMA issuer
         // Everything the issue loop needs is kept in running counters updated with add / compare / select only (no % or /),
         // and the tap loop is fully unrolled, so that ring slots, phases and UMMA descriptors live in UNIFORM registers:
@@ -269,28 +271,30 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
         }
     }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
         // ------------------------------------------------------------------ pooling + statistics: thread = conv pixel px
-        const int w = warp - 12;                              // TMEM lane quarter (warp % 4 == w)
-        const int px = w * 32 + lane;
-        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(w * 32) << 16);
+        const int g = (warp - 8) >> 2;                        // channel half: 32 g .. 32 g + 31
+        const int w = warp & 3;                               // TMEM lane quarter
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(w * 32) << 16) + g * 32;
         const bool odd = lane & 1;
-        const float* bias = b_fold + (odd ? 32 : 0);           // 32 L1-resident loads per pooled row: cheaper than 32 registers
+        float* edge_g = edge + g * (2 * 4 * 32);              // [2 parity][4 warps][32] of this warpgroup
+        float* red_g = edge_g;                                // end of image: [4 warps][mean | M2][32] aliases it
+        const int t = tid - 256 - g * 128;                    // thread index inside the warpgroup
         for (int it = 0; it < n_img; ++it) {
             const size_t b = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(it) * gridDim.x;
             // Moments of the thread's 64 pooled values per channel, accumulated around a per-thread SHIFT (its first pooled
             // value): sum of (x - shift) and of (x - shift)^2 stay small for smooth maps, so fp32 accumulation does not
             // cancel when the variance is formed (a constant image has var ~ 1e-6 next to mean^2 ~ 1).
-            float shift[32], sum[32], sq[32];
+            float shift[16], sum[16], sq[16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) shift[i] = sum[i] = sq[i] = 0.f;
+            for (int i = 0; i < 16; ++i) shift[i] = sum[i] = sq[i] = 0.f;
             for (int py = 0; py < 64; ++py) {
                 const int R2 = it * 128 + 2 * py + 1, R1 = R2 - 1, R0 = R2 - 2;
                 mbar_wait(&dfull[R2 % TS_DBUF], (R2 / TS_DBUF) & 1);   // MMAs retire in order: rows R1, R0 are complete too
                 tc_fence_after();
-                float vm[64];
+                float vm[32];
 #pragma unroll
-                for (int c = 0; c < 64; c += 16) {
+                for (int c = 0; c < 32; c += 16) {
                     uint32_t r1[16], r2[16], r0[16];
                     tmem_ld_32x16(t_lane + (R1 % TS_DBUF) * 64 + c, r1);
                     tmem_ld_32x16(t_lane + (R2 % TS_DBUF) * 64 + c, r2);
@@ -312,32 +316,32 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
                     if (py == 63) mbar_arrive(&dempty[R2 % TS_DBUF]);
                 }
                 // hand the last pixel of this warp to the next warp (its lanes 0 / 1 need px - 1 / px - 2)
-                float* e = edge + ((py & 1) * 4 + w) * 64;
+                float* e = edge_g + ((py & 1) * 4 + w) * 32;
                 if (lane == 31) {
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) e[i] = vm[i];
+                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(e + i) = make_float4(vm[i], vm[i + 1], vm[i + 2], vm[i + 3]);
                 }
-                named_bar_sync(1, 128);
-                const float* ep = edge + ((py & 1) * 4 + (w > 0 ? w - 1 : 0)) * 64;
+                named_bar_sync(1 + g, 128);
+                const float* ep = edge_g + ((py & 1) * 4 + (w > 0 ? w - 1 : 0)) * 32;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    // even lane (pooled pixel centre px): channels i      from lanes l-1, l, l+1
-                    // odd lane  (px = centre + 1):        channels 32 + i from lanes l-2, l-1, l
+                for (int i = 0; i < 16; ++i) {
+                    // even lane (pooled pixel centre px): channel i      from lanes l-1, l, l+1
+                    // odd lane  (px = centre + 1):        channel 16 + i from lanes l-2, l-1, l
                     const float a_e = __shfl_up_sync(0xffffffffu, vm[i], 1);
                     const float c_e = __shfl_down_sync(0xffffffffu, vm[i], 1);
-                    const float a_o = __shfl_up_sync(0xffffffffu, vm[32 + i], 2);
-                    const float b_o = __shfl_up_sync(0xffffffffu, vm[32 + i], 1);
+                    const float a_o = __shfl_up_sync(0xffffffffu, vm[16 + i], 2);
+                    const float b_o = __shfl_up_sync(0xffffffffu, vm[16 + i], 1);
                     float left, mid, right;
                     if (!odd) {
                         left = (lane == 0) ? (w > 0 ? ep[i] : -INFINITY) : a_e;
                         mid = vm[i];
                         right = c_e;
                     } else {
-                        left = (lane == 1) ? (w > 0 ? ep[32 + i] : -INFINITY) : a_o;
+                        left = (lane == 1) ? (w > 0 ? ep[16 + i] : -INFINITY) : a_o;
                         mid = b_o;
-                        right = vm[32 + i];
+                        right = vm[16 + i];
                     }
-                    const float pooled = fmaxf(fmaxf(fmaxf(left, mid), right) + __ldg(bias + i), 0.f);   // bias + ReLU commute with max
+                    const float pooled = fmaxf(fmaxf(fmaxf(left, mid), right), 0.f);   // ReLU commutes with max; bias is in the GEMM
                     if (py == 0) shift[i] = pooled;
                     const float dlt = pooled - shift[i];
                     sum[i] += dlt;
@@ -348,9 +352,9 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
             // merged pairwise (Chan et al.): equal counts at every level -> mean' = (ma + mb) / 2, M2' = M2a + M2b +
             // (mb - ma)^2 * n / 2: first across the 16 same-parity lanes of the warp (butterfly), then across the 4 warps.
             double cnt = 64.0;
-            float mean_f[32], m2_f[32];
+            float mean_f[16], m2_f[16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 16; ++i) {
                 double mean = static_cast<double>(shift[i]) + static_cast<double>(sum[i]) / 64.0;
                 double m2 = static_cast<double>(sq[i]) - static_cast<double>(sum[i]) * static_cast<double>(sum[i]) / 64.0;
                 double n = 64.0;
@@ -367,21 +371,20 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
                 mean_f[i] = static_cast<float>(mean);
                 m2_f[i] = static_cast<float>(m2);
             }
-            named_bar_sync(1, 128);                            // the last pooled row's readers of the edge buffer are done
+            named_bar_sync(1 + g, 128);                        // the last pooled row's readers of the edge buffer are done
             if (lane < 2) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    red[(w * 2 + 0) * 64 + lane * 32 + i] = mean_f[i];
-                    red[(w * 2 + 1) * 64 + lane * 32 + i] = m2_f[i];
+                for (int i = 0; i < 16; ++i) {
+                    red_g[(w * 2 + 0) * 32 + lane * 16 + i] = mean_f[i];
+                    red_g[(w * 2 + 1) * 32 + lane * 16 + i] = m2_f[i];
                 }
             }
-            named_bar_sync(1, 128);
-            const int t = tid - 384;
-            if (t < 64) {
-                double mean = static_cast<double>(red[(0 * 2 + 0) * 64 + t]), m2 = static_cast<double>(red[(0 * 2 + 1) * 64 + t]);
+            named_bar_sync(1 + g, 128);
+            if (t < 32) {
+                double mean = static_cast<double>(red_g[(0 * 2 + 0) * 32 + t]), m2 = static_cast<double>(red_g[(0 * 2 + 1) * 32 + t]);
                 double n = cnt;                                // 1024 values per warp partial
                 for (int ww = 1; ww < 4; ++ww) {
-                    const double mb = static_cast<double>(red[(ww * 2 + 0) * 64 + t]), qb = static_cast<double>(red[(ww * 2 + 1) * 64 + t]);
+                    const double mb = static_cast<double>(red_g[(ww * 2 + 0) * 32 + t]), qb = static_cast<double>(red_g[(ww * 2 + 1) * 32 + t]);
                     const double dl = mb - mean, nt = n + cnt;
                     m2 = m2 + qb + dl * dl * (n * cnt / nt);
                     mean = mean + dl * (cnt / nt);
@@ -389,15 +392,15 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
                 }
                 double var = m2 / (n - 1.0);
                 if (var < 0.0) var = 0.0;
-                out[b * 128 + t] = static_cast<float>(mean);
-                out[b * 128 + 64 + t] = static_cast<float>(sqrt(var + static_cast<double>(eps)));
+                out[b * 128 + g * 32 + t] = static_cast<float>(mean);
+                out[b * 128 + 64 + g * 32 + t] = static_cast<float>(sqrt(var + static_cast<double>(eps)));
             }
-            named_bar_sync(1, 128);                            // `red` aliases the edge buffer the next image writes
+            named_bar_sync(1 + g, 128);                        // `red` aliases the edge buffer the next image writes
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 4) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
