@@ -32,16 +32,17 @@ namespace drag {
 
 constexpr int TS_THREADS = 512;                 // 16 warps: 0-3 loaders, 4 MMA, 5-7 idle, 8-11 / 12-15 pooling (channels
                                                 // 0-31 / 32-63)
-constexpr int TS_RING = 5;                      // input-row pairs resident
+constexpr int TS_RING_MAX = 10;                 // input-row pairs resident: 5 (fp32 input: hi + lo tile per pair) or 10 (uint8 input:
+                                                // the pixel VALUES 0..255 are exact in bf16 - one tile per pair, 1/255 folded into W)
 constexpr int TS_XTILE = 128 * 128;             // [128 px][64 K] bf16 = 16 KB
 constexpr int TS_WTILE = 64 * 128;              // [64 ch][64 K] bf16 = 8 KB (two ky per tile)
 constexpr int TS_DBUF = 8;                      // TMEM accumulators (64 columns each)
 constexpr int TS_X_OFF = 0;                                         // ring: [slot][hi|lo]
-constexpr int TS_W_OFF = TS_X_OFF + TS_RING * 2 * TS_XTILE;         // [hi|lo][4 ky pairs]
+constexpr int TS_W_OFF = TS_X_OFF + 5 * 2 * TS_XTILE;               // [hi|lo][4 ky pairs]
 constexpr int TS_EDGE_OFF = TS_W_OFF + 2 * 4 * TS_WTILE;            // [2 parity][4 warps][64] fp32 warp-edge hand-off; the
                                                                     // end-of-image reduction buffer [4 warps][2][64] aliases it
 constexpr int TS_BAR_OFF = TS_EDGE_OFF + 2 * 4 * 64 * 4;
-constexpr int TS_SMEM = TS_BAR_OFF + 256;                           // 231 680 B of the 232 448 B a CTA may own
+constexpr int TS_SMEM = TS_BAR_OFF + 320;                           // 231 744 B of the 232 448 B a CTA may own
 static_assert(TS_SMEM <= 232448, "stem_stats_tc: shared memory budget");
 
 // byte offset of element (row r, k) of a K-major SWIZZLE_128B tile (rows of 64 bf16 = 128 B, 8-row atoms of 1024 B)
@@ -85,9 +86,11 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
     float* edge = reinterpret_cast<float*>(smem + TS_EDGE_OFF);        // [2][4][64]
     float* red = edge;                                                 // [4 warps][sum | sumsq][64 ch], end of image only
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TS_BAR_OFF);
-    uint64_t* xfull = bars;                  // [5]  count 128 (loader threads)
-    uint64_t* xempty = bars + TS_RING;       // [5]  count 1 (tcgen05.commit)
-    uint64_t* dfull = bars + 2 * TS_RING;    // [8]  count 1 (tcgen05.commit)
+    constexpr int TS_RING = U8 ? 10 : 5;     // ring slots
+    constexpr int TS_TILES = U8 ? 1 : 2;     // operand tiles per slot (hi [, lo])
+    uint64_t* xfull = bars;                      // [ring]  count 128 (loader threads)
+    uint64_t* xempty = bars + TS_RING_MAX;       // [ring]  count 1 (tcgen05.commit)
+    uint64_t* dfull = bars + 2 * TS_RING_MAX;    // [8]  count 1 (tcgen05.commit)
     uint64_t* dempty = dfull + TS_DBUF;      // [8]  count 8 (one per pooling warp)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + TS_DBUF);
 
@@ -116,8 +119,10 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
         const int ky = 2 * t + (c >> 2), ci = c & 3;
         float x[8];
 #pragma unroll
-        for (int kx = 0; kx < 8; ++kx)
+        for (int kx = 0; kx < 8; ++kx) {
             x[kx] = (ky < 7 && ci < 3 && kx < 7) ? w_fold[((ch * 3 + ci) * 7 + ky) * 7 + kx] : 0.f;
+            if (U8) x[kx] = __fdiv_rn(x[kx], 255.f);          // uint8 input: A holds the pixel values, the / 255 of :193 lives here
+        }
         if (ky == 3 && ci == 0) x[7] = b_fold[ch];           // multiplies the column of ones the loaders put at (ci 0, kx 7)
         uint4 hi, lo;
         split_bf16x8(x, hi, lo);
@@ -137,12 +142,10 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
         // ------------------------------------------------------------------ loaders: thread = conv pixel px
         const int px = tid;
         // the zero chunks (ci = 3 of either row) of every ring slot are written once: no later store touches them
-        for (int slot = 0; slot < TS_RING; ++slot) {
-            uint8_t* t0 = xring + static_cast<size_t>(slot) * 2 * TS_XTILE;
+        for (int slot = 0; slot < TS_RING * TS_TILES; ++slot) {
+            uint8_t* t0 = xring + static_cast<size_t>(slot) * TS_XTILE;
             *reinterpret_cast<uint4*>(t0 + sw128_chunk(px, 3)) = make_uint4(0, 0, 0, 0);
             *reinterpret_cast<uint4*>(t0 + sw128_chunk(px, 7)) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(t0 + TS_XTILE + sw128_chunk(px, 3)) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(t0 + TS_XTILE + sw128_chunk(px, 7)) = make_uint4(0, 0, 0, 0);
         }
         // window of conv pixel px: input columns 2px-3 .. 2px+3, fetched as the 4 aligned pairs covering 2px-4 .. 2px+3
         // (rows have 256 columns, so a pair is either wholly inside the row or wholly padding)
@@ -153,38 +156,53 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
             for (int p = 0; p < 128; ++p) {
                 const int P = it * 128 + p, slot = P % TS_RING;
                 // all 24 loads of the pair in flight before the first conversion: ONE memory latency per row pair
+                if (U8) {
+                    // uint8 pixels: 4 x 16-bit loads per (row, channel) window; the VALUES go to the tensor core as exact bf16
+                    unsigned short q[6][4];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        const int h = c / 3, ci = c - h * 3;
+                        const uint8_t* src = static_cast<const uint8_t*>(img_v) + ((b * 3 + ci) * 256 + (2 * p + h)) * 256;
+                        q[c][0] = ok0 ? __ldg(reinterpret_cast<const unsigned short*>(src + x0)) : static_cast<unsigned short>(0);
+                        q[c][1] = (x0 + 2 >= 0) ? __ldg(reinterpret_cast<const unsigned short*>(src + x0 + 2)) : static_cast<unsigned short>(0);
+                        q[c][2] = __ldg(reinterpret_cast<const unsigned short*>(src + x0 + 4));
+                        q[c][3] = ok3 ? __ldg(reinterpret_cast<const unsigned short*>(src + x0 + 6)) : static_cast<unsigned short>(0);
+                    }
+                    mbar_wait(&xempty[slot], ((P / TS_RING) & 1) ^ 1);
+                    uint8_t* thi = xring + static_cast<size_t>(slot) * TS_XTILE;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        const int h = c / 3, ci = c - h * 3;
+                        // window bytes 1..7 are taps kx = 0..6; integers 0..255 convert to bf16 exactly
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            f[2 * j] = static_cast<float>(q[c][j] & 0xff);
+                            f[2 * j + 1] = static_cast<float>(q[c][j] >> 8);
+                        }
+                        uint32_t u[4];
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            __nv_bfloat162 pk = __floats2bfloat162_rn(f[2 * j + 1], f[2 * j + 2]);
+                            u[j] = *reinterpret_cast<uint32_t*>(&pk);
+                        }
+                        __nv_bfloat162 pl = __floats2bfloat162_rn(f[7], ci == 0 ? 1.f : 0.f);   // tap 6 | the ones column (bias)
+                        u[3] = *reinterpret_cast<uint32_t*>(&pl);
+                        *reinterpret_cast<uint4*>(thi + sw128_chunk(px, h * 4 + ci)) = make_uint4(u[0], u[1], u[2], u[3]);
+                    }
+                } else {
                 float w[6][8];
 #pragma unroll
                 for (int c = 0; c < 6; ++c) {                 // (row of the pair, channel)
                     const int h = c / 3, ci = c - h * 3;
-                    const size_t row = ((b * 3 + ci) * 256 + (2 * p + h)) * 256;
-                    if (U8) {
-                        const uint8_t* src = static_cast<const uint8_t*>(img_v) + row;
-                        unsigned short q[4];
-                        q[0] = ok0 ? __ldg(reinterpret_cast<const unsigned short*>(src + x0)) : static_cast<unsigned short>(0);
-                        q[1] = (x0 + 2 >= 0) ? __ldg(reinterpret_cast<const unsigned short*>(src + x0 + 2)) : static_cast<unsigned short>(0);
-                        q[2] = __ldg(reinterpret_cast<const unsigned short*>(src + x0 + 4));
-                        q[3] = ok3 ? __ldg(reinterpret_cast<const unsigned short*>(src + x0 + 6)) : static_cast<unsigned short>(0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            // u8 / 255 exactly as IEEE division rounds it, without the division sequence: q = u * r,
-                            // one Newton correction with the exact remainder (verified for all 256 values)
-                            const float r = 1.0f / 255.0f;
-                            const float u0 = static_cast<float>(q[j] & 0xff), u1 = static_cast<float>(q[j] >> 8);
-                            const float q0 = u0 * r, q1 = u1 * r;
-                            w[c][2 * j] = fmaf(fmaf(-q0, 255.f, u0), r, q0);
-                            w[c][2 * j + 1] = fmaf(fmaf(-q1, 255.f, u1), r, q1);
-                        }
-                    } else {
-                        const float* src = static_cast<const float*>(img_v) + row;
-                        const float2 z = make_float2(0.f, 0.f);
-                        const float2 a0 = ok0 ? __ldg(reinterpret_cast<const float2*>(src + x0)) : z;
-                        const float2 a1 = (x0 + 2 >= 0) ? __ldg(reinterpret_cast<const float2*>(src + x0 + 2)) : z;
-                        const float2 a2 = __ldg(reinterpret_cast<const float2*>(src + x0 + 4));
-                        const float2 a3 = ok3 ? __ldg(reinterpret_cast<const float2*>(src + x0 + 6)) : z;
-                        w[c][0] = a0.x; w[c][1] = a0.y; w[c][2] = a1.x; w[c][3] = a1.y;
-                        w[c][4] = a2.x; w[c][5] = a2.y; w[c][6] = a3.x; w[c][7] = a3.y;
-                    }
+                    const float* src = static_cast<const float*>(img_v) + ((b * 3 + ci) * 256 + (2 * p + h)) * 256;
+                    const float2 z = make_float2(0.f, 0.f);
+                    const float2 a0 = ok0 ? __ldg(reinterpret_cast<const float2*>(src + x0)) : z;
+                    const float2 a1 = (x0 + 2 >= 0) ? __ldg(reinterpret_cast<const float2*>(src + x0 + 2)) : z;
+                    const float2 a2 = __ldg(reinterpret_cast<const float2*>(src + x0 + 4));
+                    const float2 a3 = ok3 ? __ldg(reinterpret_cast<const float2*>(src + x0 + 6)) : z;
+                    w[c][0] = a0.x; w[c][1] = a0.y; w[c][2] = a1.x; w[c][3] = a1.y;
+                    w[c][4] = a2.x; w[c][5] = a2.y; w[c][6] = a3.x; w[c][7] = a3.y;
                 }
                 mbar_wait(&xempty[slot], ((P / TS_RING) & 1) ^ 1);
                 uint8_t* thi = xring + static_cast<size_t>(slot) * 2 * TS_XTILE;
@@ -202,6 +220,7 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
                     *reinterpret_cast<uint4*>(thi + off) = hi;
                     *reinterpret_cast<uint4*>(tlo + off) = lo;
                 }
+                }
                 fence_proxy_async();                          // generic-proxy stores -> visible to the tensor core's async proxy
                 mbar_arrive(&xfull[slot]);
             }
@@ -214,7 +233,8 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
         // bottleneck (148 cycles per 32-cycle MMA in the first version).
         constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
         const uint64_t x_desc0 = umma_desc_k_sw128(smem_u32(xring)), w_desc0 = umma_desc_k_sw128(smem_u32(wt));
-        int s0 = TS_RING - 2;                                  // ring slot of pair (cy - 2); pairs run on across images
+        int s0 = TS_RING - 2;                                  // ring slot of pair (cy - 2); pairs run on across images (128 % ring
+                                                               // != 0 is fine: slots are just a running counter mod ring)
         int w_slot = 0, w_phase = 0;                           // next pair to wait for: its slot and barrier phase
         int buf = 0, d_phase = 0;                              // accumulator of the current conv row and its phase
         for (int it = 0; it < n_img; ++it) {
@@ -236,18 +256,18 @@ stem_stats_tc_kernel(const void* __restrict__ img_v, const float* __restrict__ w
                     const bool valid = (2 * cy - 3 + ky >= 0) && (2 * cy - 3 + ky <= 255);   // padding rows contribute nothing
                     int slot = s0 + ((ky + 1) >> 1);
                     slot = slot >= TS_RING ? slot - TS_RING : slot;
-                    const uint64_t ah = x_desc0 + static_cast<uint64_t>((slot * 2 * TS_XTILE + ((ky + 1) & 1) * 64) >> 4);
-                    const uint64_t al = ah + (TS_XTILE >> 4);
+                    const uint64_t ah = x_desc0 + static_cast<uint64_t>((slot * TS_TILES * TS_XTILE + ((ky + 1) & 1) * 64) >> 4);
+                    const uint64_t al = ah + (TS_XTILE >> 4);     // lo tile: fp32 input only
                     const uint64_t bh = w_desc0 + (((ky >> 1) * TS_WTILE + (ky & 1) * 64) >> 4);
                     const uint64_t bl = bh + ((4 * TS_WTILE) >> 4);
                     if (valid) {
                         if (elect_one()) {
                             tc_mma_f16(d_tmem, ah, bh, idesc, acc);
                             tc_mma_f16(d_tmem, ah, bl, idesc, 1);
-                            tc_mma_f16(d_tmem, al, bh, idesc, 1);
+                            if (!U8) tc_mma_f16(d_tmem, al, bh, idesc, 1);     // uint8 pixels are exact in bf16: no lo operand
                             tc_mma_f16(d_tmem, ah + 2, bh + 2, idesc, 1);      // second k-step: +32 bytes along K
                             tc_mma_f16(d_tmem, ah + 2, bl + 2, idesc, 1);
-                            tc_mma_f16(d_tmem, al + 2, bh + 2, idesc, 1);
+                            if (!U8) tc_mma_f16(d_tmem, al + 2, bh + 2, idesc, 1);
                         }
                         __syncwarp();
                         acc = 1;
