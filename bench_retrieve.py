@@ -167,7 +167,8 @@ def stem_roofline(m, peaks):
     gbs = m["stem_bytes"] / (m["stem_ms"] * 1e-3) / 1e9
     return {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": round(gbs / peaks["hbm_gbs"], 4), "kernel": "stem_stats_tc_kernel (707 images of 256^2, one launch; split-bf16 implicit GEMM on tcgen05)",
-            "tensor_tflops": round(3 * 2.0 * 128 * 128 * 64 * 224 * 707 / (m["stem_ms"] * 1e-3) / 1e12, 1),
+            "tensor_tflops": round(2 * 2.0 * 128 * 128 * 64 * 224 * 707 / (m["stem_ms"] * 1e-3) / 1e12, 1),
+            "tensor_note": "uint8 pixels are exact bf16 operands: 2 split terms (x.wh + x.wl) x 14 k-steps of 16 per conv row",
             "kernel_ms": round(m["stem_ms"], 4), "traffic": None}
 
 
