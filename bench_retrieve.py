@@ -34,7 +34,7 @@ def c2_workload(model: str, embed_batch: int) -> str:
     """config.workload of the retrieve line - shared by the b200 arm and the reference arm."""
     return (f"C2 per GPU: {N_CORPUS} synthetic 224^2 images (uint8 pixels, normalised on the GPU) -> CLIP {model} embed (batches of {embed_batch}) + "
             f"L2 normalise -> resident fp32 index shard; {N_QUERY} queries -> exact top-{TOP_K} "
-            f"(sharded: all-gather of per-shard top-k) -> ResNet-50-stem style statistics of "
+            f"(sharded: per-shard top-k exchanged and merged) -> ResNet-50-stem style statistics of "
             f"{N_QUERY}x(1+{TOP_K}) 256^2 images; random-init weights")
 
 

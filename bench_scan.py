@@ -191,8 +191,8 @@ def measure(rank, world, local, n, d, nq, k, steps, warmup, flush_l2=False, e2e=
 def _line(pt, world, steps, warmup, clocks, peaks, extra_cfg=None):
     n, d, nq, k = pt["n_per_gpu"], pt["d"], pt["nq"], pt["k"]
     alg = scan_algorithmic_bytes(n, d, nq, k)
-    cfg = {"workload": f"C5 scan: {n} x {d} fp32 embeddings per GPU, nq={nq}, top-{k}; index row-sharded, all-gather of "
-                       f"per-shard top-k", "l2_policy": pt["l2"] + f" ({alg / 1e6:.0f} MB per GPU vs 126 MB)",
+    cfg = {"workload": f"C5 scan: {n} x {d} fp32 embeddings per GPU, nq={nq}, top-{k}; index row-sharded, per-shard top-k "
+                       f"exchanged and merged on every rank", "l2_policy": pt["l2"] + f" ({alg / 1e6:.0f} MB per GPU vs 126 MB)",
            "grid": pt["grid"], "ring_stages": pt["ring_stages"], "rows_per_stage": pt["rows_per_stage"],
            "exchange": pt["exchange"], "nccl_ms_per_search": pt["nccl_ms_per_search"],
            "verified_sharded_equals_single": pt["verified_sharded_equals_single"]}
@@ -288,6 +288,6 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C5 scan: {n} x {d} fp32 embeddings per GPU, nq={nq}, top-{k}; index row-sharded, "
-                                   f"all-gather of per-shard top-k", "sample": sample},
+                                   f"per-shard top-k exchanged and merged on every rank", "sample": sample},
             "cpu_baseline": {"value": val, "unit": "GB/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

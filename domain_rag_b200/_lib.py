@@ -61,6 +61,8 @@ SIGNATURES = {
     "drag_topk_exchange_buffer_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, c_i64_p]),
     "drag_topk_exchange_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                            C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "drag_index_search_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "drag_vit_create": (C.c_int, [C.c_void_p, c_void_pp]),
     "drag_vit_destroy": (C.c_int, [C.c_void_p]),
     "drag_vit_set_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
@@ -84,6 +86,10 @@ SIGNATURES = {
                                         C.c_float, C.c_float, C.c_void_p]),
     "drag_image_postprocess_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "drag_image_preprocess_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "drag_pack_latents": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "drag_unpack_latents": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "drag_pack_fill_inputs": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_int64, C.c_void_p]),
     "drag_axpby_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
     "drag_prof_enable": (C.c_int, [C.c_int]),
     "drag_prof_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

@@ -309,6 +309,16 @@ int drag_timestep_embed(const float* t_dev, void* out, int B, void* stream) {
 int drag_euler_step(void* x, int ldx, const void* v, int ldv, int rows, int cols, float dsigma, void* stream) {
     return euler_step(BFM(x), ldx, BF(v), ldv, rows, cols, dsigma, ST(stream));
 }
+int drag_pack_latents(const void* z, int B, int C, int h, int w, void* out, int64_t ldo, int ch_off, void* stream) {
+    return pack_latents(BF(z), B, C, h, w, BFM(out), ldo, ch_off, ST(stream));
+}
+int drag_unpack_latents(const void* x, int64_t ldx, int B, int C, int h, int w, void* z, void* stream) {
+    return unpack_latents(BF(x), ldx, B, C, h, w, BFM(z), ST(stream));
+}
+int drag_pack_fill_inputs(const void* latents, int64_t ld_lat, const void* masked_latents, const uint8_t* mask, int B, int h,
+                          int w, void* x, int64_t ldx, void* stream) {
+    return pack_fill_inputs(BF(latents), ld_lat, BF(masked_latents), mask, B, h, w, BFM(x), ldx, ST(stream));
+}
 int drag_redux_blend(const void* txt, const void* img, const void* pooled, const float* s_embed_dev,
                      const float* s_pool_dev, void* out_embeds, void* out_pooled, int B, int n_txt, int n_img, int dim,
                      int pooled_dim, void* stream) {
@@ -349,6 +359,14 @@ int drag_topk_exchange_buffer_bytes(int world, int nq_cap, int k_cap, int64_t* b
 int drag_topk_exchange_merge(const float* D_loc, const int64_t* I_loc, int nq, int k, void* const* peer_bufs, int world,
                              int rank, int nq_cap, int k_cap, uint32_t epoch, float* D_dev, int64_t* I_dev, void* stream) {
     return topk_exchange_merge(D_loc, I_loc, nq, k, peer_bufs, world, rank, nq_cap, k_cap, epoch, D_dev, I_dev, ST(stream));
+}
+int drag_index_search_sharded(drag_index_t* h, const float* q_dev, int nq, int k, void* const* peer_bufs, int world, int rank,
+                              int nq_cap, int k_cap, uint32_t epoch, float* D_ws, int64_t* I_ws, float* D_dev,
+                              int64_t* I_dev, void* stream) {
+    DRAG_REQUIRE(h && D_ws && I_ws, "drag_index_search_sharded: null pointer");
+    const int rc = index_search_device(reinterpret_cast<Index*>(h), q_dev, nq, k, D_ws, I_ws, ST(stream));
+    if (rc != DRAG_OK) return rc;
+    return topk_exchange_merge(D_ws, I_ws, nq, k, peer_bufs, world, rank, nq_cap, k_cap, epoch, D_dev, I_dev, ST(stream));
 }
 
 // ------------------------------------------------------------------------------------ CLIP ViT engine

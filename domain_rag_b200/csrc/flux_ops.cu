@@ -236,6 +236,105 @@ int euler_step(__nv_bfloat16* x, int ldx, const __nv_bfloat16* v, int ldv, int r
     return DRAG_OK;
 }
 
+// Flux 2x2 latent packing (diffusers _pack_latents / _unpack_latents): z [B][C][h][w] <-> token s = (y/2)(w/2) + x/2,
+// channel c*4 + (y%2)*2 + (x%2). One thread moves the four values of one (token, c): an 8-byte store on the packed side.
+__global__ void pack_latents_kernel(const __nv_bfloat16* __restrict__ z, int C, int h, int w, __nv_bfloat16* __restrict__ out,
+                                    int64_t ldo, int ch_off, int64_t total) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int w2 = w / 2, S = (h / 2) * w2;
+    const int c = static_cast<int>(i % C);
+    const int64_t bs = i / C;
+    const int s = static_cast<int>(bs % S), b = static_cast<int>(bs / S);
+    const int sy = s / w2, sx = s - sy * w2;
+    const __nv_bfloat16* src = z + ((static_cast<size_t>(b) * C + c) * h + 2 * sy) * w + 2 * sx;
+    const __nv_bfloat162 r0 = *reinterpret_cast<const __nv_bfloat162*>(src);
+    const __nv_bfloat162 r1 = *reinterpret_cast<const __nv_bfloat162*>(src + w);
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(out + static_cast<size_t>(bs) * ldo + ch_off + c * 4);
+    dst[0] = r0;
+    dst[1] = r1;
+}
+__global__ void unpack_latents_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int C, int h, int w,
+                                      __nv_bfloat16* __restrict__ z, int64_t total) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int w2 = w / 2, h2 = h / 2;
+    const int sx = static_cast<int>(i % w2);
+    int64_t r = i / w2;
+    const int sy = static_cast<int>(r % h2);
+    r /= h2;
+    const int c = static_cast<int>(r % C), b = static_cast<int>(r / C);
+    const __nv_bfloat162* src = reinterpret_cast<const __nv_bfloat162*>(
+        x + (static_cast<size_t>(b) * h2 * w2 + static_cast<size_t>(sy) * w2 + sx) * ldx + c * 4);
+    __nv_bfloat16* dst = z + ((static_cast<size_t>(b) * C + c) * h + 2 * sy) * w + 2 * sx;
+    *reinterpret_cast<__nv_bfloat162*>(dst) = src[0];
+    *reinterpret_cast<__nv_bfloat162*>(dst + w) = src[1];
+}
+int pack_latents(const __nv_bfloat16* z, int B, int C, int h, int w, __nv_bfloat16* out, int64_t ldo, int ch_off,
+                 cudaStream_t st) {
+    DRAG_REQUIRE(z && out && B >= 1 && C >= 1 && h >= 2 && w >= 2 && h % 2 == 0 && w % 2 == 0 && ldo % 4 == 0 &&
+                     ch_off % 4 == 0 && ch_off + 4 * C <= ldo, "pack_latents: bad arguments");
+    const int64_t total = static_cast<int64_t>(B) * (h / 2) * (w / 2) * C;
+    pack_latents_kernel<<<ceil_div(total, 256), 256, 0, st>>>(z, C, h, w, out, ldo, ch_off, total); count_launch();
+    DRAG_CUDA(cudaGetLastError());
+    return DRAG_OK;
+}
+int unpack_latents(const __nv_bfloat16* x, int64_t ldx, int B, int C, int h, int w, __nv_bfloat16* z, cudaStream_t st) {
+    DRAG_REQUIRE(x && z && B >= 1 && C >= 1 && h >= 2 && w >= 2 && h % 2 == 0 && w % 2 == 0 && ldx % 4 == 0 && 4 * C <= ldx,
+                 "unpack_latents: bad arguments");
+    const int64_t total = static_cast<int64_t>(B) * C * (h / 2) * (w / 2);
+    unpack_latents_kernel<<<ceil_div(total, 256), 256, 0, st>>>(x, ldx, C, h, w, z, total); count_launch();
+    DRAG_CUDA(cudaGetLastError());
+    return DRAG_OK;
+}
+
+// Flux-Fill transformer input (FluxFillPipeline.prepare_mask_latents + the channel concat of its denoising loop):
+// x[b][s][0:64] = packed latents (copied when given), [64:128] = 2x2-packed masked-image latents, [128:384] = the 8x8 block
+// of mask pixels under each latent pixel as 64 channels, 2x2-packed. 96 work items per token, four channels each.
+__global__ void pack_fill_inputs_kernel(const __nv_bfloat16* __restrict__ latents, int64_t ld_lat,
+                                        const __nv_bfloat16* __restrict__ masked, const uint8_t* __restrict__ mask, int h,
+                                        int w, __nv_bfloat16* __restrict__ x, int64_t ldx, int64_t total) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int w2 = w / 2, S = (h / 2) * w2;
+    const int q = static_cast<int>(i % 96);
+    const int64_t bs = i / 96;
+    const int s = static_cast<int>(bs % S), b = static_cast<int>(bs / S);
+    const int sy = s / w2, sx = s - sy * w2;
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(x + static_cast<size_t>(bs) * ldx + q * 4);
+    if (q < 16) {
+        if (latents == nullptr) return;
+        const __nv_bfloat162* src = reinterpret_cast<const __nv_bfloat162*>(latents + static_cast<size_t>(bs) * ld_lat + q * 4);
+        dst[0] = src[0];
+        dst[1] = src[1];
+    } else if (q < 32) {
+        const int c = q - 16;
+        const __nv_bfloat16* src = masked + ((static_cast<size_t>(b) * 16 + c) * h + 2 * sy) * w + 2 * sx;
+        dst[0] = *reinterpret_cast<const __nv_bfloat162*>(src);
+        dst[1] = *reinterpret_cast<const __nv_bfloat162*>(src + w);
+    } else {
+        const int m = q - 32, my = m >> 3, mx = m & 7;
+        const size_t W = static_cast<size_t>(w) * 8;
+        const uint8_t* src = mask + (static_cast<size_t>(b) * h * 8 + static_cast<size_t>(2 * sy) * 8 + my) * W +
+                             static_cast<size_t>(2 * sx) * 8 + mx;
+        const float v00 = src[0] ? 1.f : 0.f, v01 = src[8] ? 1.f : 0.f;
+        const float v10 = src[8 * W] ? 1.f : 0.f, v11 = src[8 * W + 8] ? 1.f : 0.f;
+        dst[0] = __floats2bfloat162_rn(v00, v01);
+        dst[1] = __floats2bfloat162_rn(v10, v11);
+    }
+}
+int pack_fill_inputs(const __nv_bfloat16* latents, int64_t ld_lat, const __nv_bfloat16* masked, const uint8_t* mask, int B,
+                     int h, int w, __nv_bfloat16* x, int64_t ldx, cudaStream_t st) {
+    DRAG_REQUIRE(masked && mask && x && B >= 1 && h >= 2 && w >= 2 && h % 2 == 0 && w % 2 == 0 && ldx >= 384 &&
+                     ldx % 4 == 0 && (latents == nullptr || (ld_lat >= 64 && ld_lat % 4 == 0)),
+                 "pack_fill_inputs: bad arguments");
+    const int64_t total = static_cast<int64_t>(B) * (h / 2) * (w / 2) * 96;
+    pack_fill_inputs_kernel<<<ceil_div(total, 256), 256, 0, st>>>(latents, ld_lat, masked, mask, h, w, x, ldx, total);
+    count_launch();
+    DRAG_CUDA(cudaGetLastError());
+    return DRAG_OK;
+}
+
 // Redux prompt blend: out_embeds[t][c] = sum_b s_embed[b] * (t < n_txt ? txt[b][t][c] : img[b][t-n_txt][c]);
 // out_pooled[c] = sum_b s_pool[b] * pooled[b][c]. Products and the running sum round to bf16 like
 // the reference's bf16 tensor ops.

@@ -15,6 +15,11 @@ int sum_silu(const __nv_bfloat16* a, const __nv_bfloat16* b, const __nv_bfloat16
              int apply_silu, cudaStream_t st);
 int euler_step(__nv_bfloat16* x, int ldx, const __nv_bfloat16* v, int ldv, int rows, int cols, float dsigma,
                cudaStream_t st);
+int pack_latents(const __nv_bfloat16* z, int B, int C, int h, int w, __nv_bfloat16* out, int64_t ldo, int ch_off,
+                 cudaStream_t st);
+int unpack_latents(const __nv_bfloat16* x, int64_t ldx, int B, int C, int h, int w, __nv_bfloat16* z, cudaStream_t st);
+int pack_fill_inputs(const __nv_bfloat16* latents, int64_t ld_lat, const __nv_bfloat16* masked, const uint8_t* mask, int B,
+                     int h, int w, __nv_bfloat16* x, int64_t ldx, cudaStream_t st);
 int redux_blend(const __nv_bfloat16* txt, const __nv_bfloat16* img, const __nv_bfloat16* pooled, const float* s_embed,
                 const float* s_pool, __nv_bfloat16* out_embeds, __nv_bfloat16* out_pooled, int B, int n_txt, int n_img,
                 int dim, int pooled_dim, cudaStream_t st);

@@ -147,6 +147,44 @@ def unpack_latents(x: torch.Tensor, h: int, w: int) -> torch.Tensor:
     return x.view(B, h // 2, w // 2, Cc, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(B, Cc, h, w)
 
 
+def pack_latents_device(z: torch.Tensor, out: Optional[torch.Tensor] = None, ch_off: int = 0) -> torch.Tensor:
+    """pack_latents of a bf16 CUDA tensor [B,C,h,w] as one kernel (drag_pack_latents); with `out` [B,S,ld] the packed
+    channels land at out[..., ch_off : ch_off + 4C]."""
+    B, Cc, h, w = z.shape
+    z = z.contiguous()
+    if out is None:
+        out = torch.empty((B, (h // 2) * (w // 2), 4 * Cc), dtype=torch.bfloat16, device=z.device)
+    assert z.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and out.stride(2) == 1
+    assert out.stride(0) == out.shape[1] * out.stride(1)
+    _lib.check(_lib.load().drag_pack_latents(_lib.ptr(z), B, Cc, h, w, _lib.ptr(out), out.stride(1), ch_off,
+                                             _lib.current_stream_ptr(z.device)), "drag_pack_latents")
+    return out
+
+
+def unpack_latents_device(x: torch.Tensor, h: int, w: int, channels: int = 16) -> torch.Tensor:
+    """unpack_latents of bf16 CUDA [B,S,ld >= 4*channels] (a channel-strided view is fine) -> [B,channels,h,w]."""
+    B = x.shape[0]
+    assert x.dtype == torch.bfloat16 and x.stride(2) == 1 and x.stride(0) == x.shape[1] * x.stride(1)
+    z = torch.empty((B, channels, h, w), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().drag_unpack_latents(_lib.ptr(x), x.stride(1), B, channels, h, w, _lib.ptr(z),
+                                               _lib.current_stream_ptr(x.device)), "drag_unpack_latents")
+    return z
+
+
+def pack_fill_inputs(latents: Optional[torch.Tensor], masked_latents: torch.Tensor, mask_u8: torch.Tensor) -> torch.Tensor:
+    """The Flux-Fill transformer input [B,S,384] in one launch (drag_pack_fill_inputs): packed `latents` [B,S,64] (or None:
+    channels 0:64 left for the caller), masked-image latents bf16 [B,16,h,w], mask uint8 [B,8h,8w] (non-zero = repaint)."""
+    B, _, h, w = masked_latents.shape
+    assert mask_u8.dtype == torch.uint8 and tuple(mask_u8.shape) == (B, 8 * h, 8 * w)
+    x = torch.empty((B, (h // 2) * (w // 2), 384), dtype=torch.bfloat16, device=masked_latents.device)
+    lat = latents.contiguous() if latents is not None else None
+    _lib.check(_lib.load().drag_pack_fill_inputs(_lib.ptr(lat) if lat is not None else None, 64 if lat is not None else 0,
+                                                 _lib.ptr(masked_latents.contiguous()), _lib.ptr(mask_u8.contiguous()), B, h, w,
+                                                 _lib.ptr(x), 384, _lib.current_stream_ptr(x.device)),
+               "drag_pack_fill_inputs")
+    return x
+
+
 class FluxTransformer:
     """FluxTransformer2DModel stand-in: owns bf16 device weights and one C++ engine."""
 
@@ -268,17 +306,22 @@ class FluxPipeline:
         return pack_latents(z).contiguous().pin_memory().to(device, non_blocking=True), h, w
 
     def _denoise(self, latents, h, w, prompt_embeds, pooled_prompt_embeds, guidance_scale, num_inference_steps, start,
-                 extra_cond):
-        """Steps [start, T) of the flow-match Euler loop on packed latents [B,S,64]; returns packed latents."""
+                 extra_cond, buf=None):
+        """Steps [start, T) of the flow-match Euler loop on packed latents [B,S,64]; returns the packed latents as a view
+        of the working buffer. `buf` (Fill: [B,S,384] from pack_fill_inputs, latents already in channels 0:64) is used as
+        is; otherwise it is built from `latents` (+ `extra_cond`)."""
         tr = self.transformer
         dev = tr.device
-        B, S_img, c_lat = latents.shape
+        if buf is not None:
+            B, S_img, c_lat = buf.shape[0], buf.shape[1], tr.cfg.out_channels
+        else:
+            B, S_img, c_lat = latents.shape
+            if extra_cond is not None:   # x lives in the first 64 channels of a persistent [B,S,64+cond] buffer
+                buf = torch.cat([latents, extra_cond.to(latents.dtype)], dim=-1).contiguous()
+            else:
+                buf = latents.contiguous()
         sig = flow_match_sigmas(num_inference_steps, S_img)
         cos, sin = self._rope(h // 2, w // 2, prompt_embeds.shape[1], dev)
-        if extra_cond is not None:       # Fill: x lives in the first 64 channels of a persistent [B,S,384] buffer
-            buf = torch.cat([latents, extra_cond.to(latents.dtype)], dim=-1).contiguous()
-        else:
-            buf = latents.contiguous()
         x_view = buf[:, :, :c_lat]
         ctx = prompt_embeds.to(dev, torch.bfloat16).contiguous()
         if ctx.shape[0] != B:
@@ -292,10 +335,10 @@ class FluxPipeline:
         for i in range(start, num_inference_steps):
             tr.forward(buf, ctx, pooled, t_all[i], g, cos, sin, out=v)
             euler_step_(x_view, v, sig[i + 1] - sig[i])
-        return x_view.contiguous(), sig
+        return x_view, sig
 
     def _finish(self, packed, h, w, steps_run, output_type):
-        lat = unpack_latents(packed, h, w)
+        lat = unpack_latents_device(packed, h, w, packed.shape[2] // 4)
         if output_type == "latent":
             return PipelineOutput(latents=lat, images=None, steps_run=steps_run)
         if self.vae is None:
@@ -393,15 +436,15 @@ class FluxFillPipeline(FluxPipeline):
             raise ValueError(f"After adjusting the num_inference_steps by strength parameter: {strength}, the number of "
                              "pipeline steps is 0 which is < 1")
         h, w = H // 8, W // 8
-        image_latents = pack_latents(self.vae.encode(img_u8, generator=generator)).contiguous()
+        image_latents = pack_latents_device(self.vae.encode(img_u8, generator=generator))
         if noise is None:
             noise, _, _ = self.prepare_latents(B, H, W, generator, dev)
         s0 = flow_match_sigmas(num_inference_steps, noise.shape[1])[start]
         latents = axpby_(noise.contiguous(), image_latents, s0, 1.0 - s0)
-        masked = pack_latents(self.vae.encode(img_u8, generator=generator, mask=mask_u8))
-        cond = torch.cat([masked, pack_mask(mask_u8).to(torch.bfloat16)], dim=-1).contiguous()      # [B,S,320]
-        packed, _ = self._denoise(latents, h, w, prompt_embeds, pooled_prompt_embeds, guidance_scale, num_inference_steps,
-                                  start, cond)
+        masked = self.vae.encode(img_u8, generator=generator, mask=mask_u8)                          # [B,16,h,w]
+        buf = pack_fill_inputs(latents, masked, mask_u8)                                             # [B,S,384]
+        packed, _ = self._denoise(None, h, w, prompt_embeds, pooled_prompt_embeds, guidance_scale, num_inference_steps,
+                                  start, None, buf=buf)
         return self._finish(packed, h, w, num_inference_steps - start, output_type)
 
 

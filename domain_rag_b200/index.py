@@ -236,21 +236,29 @@ class ShardedIndexFlatIP:
     def search(self, q, k: int):
         import torch
         import torch.distributed as dist
+        p2p = (self.world > 1 and self._index is not None and self._p2p is not None and self.exchange == "p2p"
+               and q.shape[0] <= self._p2p[3] and k <= self._p2p[4] and self.world * k <= 8192)
+        if p2p:                                   # local scan + fused NVLink exchange + merge behind ONE C call
+            _, _, ptrs, nq_cap, k_cap = self._p2p
+            if not (isinstance(q, torch.Tensor) and q.is_cuda and q.dtype == torch.float32):
+                raise TypeError("search: need a float32 CUDA tensor")
+            q = q.contiguous()
+            nq = q.shape[0]
+            self._epoch += 1
+            D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+            I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+            Do, Io = torch.empty_like(D), torch.empty_like(I)
+            _lib.check(_lib.load().drag_index_search_sharded(self._index._h, _lib.ptr(q), nq, int(k), ptrs, self.world,
+                                                             self.rank, nq_cap, k_cap, self._epoch, _lib.ptr(D), _lib.ptr(I),
+                                                             _lib.ptr(Do), _lib.ptr(Io), _lib.current_stream_ptr(q.device)),
+                       "drag_index_search_sharded")
+            return Do, Io
         if self._index is not None:
             D, I = self._index.search_device(q, k)
         else:
             D, I = self._local_search(self._rows, q, k, self.lo)
         if self.world == 1:
             return D, I
-        if (self._p2p is not None and self.exchange == "p2p" and q.shape[0] <= self._p2p[3] and k <= self._p2p[4]
-                and self.world * k <= 8192):
-            _, _, ptrs, nq_cap, k_cap = self._p2p
-            self._epoch += 1
-            Do, Io = torch.empty_like(D), torch.empty_like(I)
-            _lib.check(_lib.load().drag_topk_exchange_merge(_lib.ptr(D), _lib.ptr(I), q.shape[0], int(k), ptrs, self.world,
-                                                            self.rank, nq_cap, k_cap, self._epoch, _lib.ptr(Do), _lib.ptr(Io),
-                                                            _lib.current_stream_ptr(D.device)), "drag_topk_exchange_merge")
-            return Do, Io
         if self._all_gather is not None:
             Dg, Ig = self._all_gather(D), self._all_gather(I)
         else:

@@ -75,6 +75,12 @@ int drag_topk_merge_device(const float* scores, const int64_t* ids, int nq, int 
 int drag_topk_exchange_buffer_bytes(int world, int nq_cap, int k_cap, int64_t* bytes);
 int drag_topk_exchange_merge(const float* D_loc, const int64_t* I_loc, int nq, int k, void* const* peer_bufs, int world,
                              int rank, int nq_cap, int k_cap, uint32_t epoch, float* D_dev, int64_t* I_dev, void* stream);
+/* The whole sharded search of one rank in one call: drag_index_search_device over this rank's rows into the caller's
+ * workspace D_ws / I_ws [nq][k], then drag_topk_exchange_merge. Collective over the ranks that own `peer_bufs`; replaces
+ * index.search(q, k) of retrieval/clip100_resnet_style_all_shots.py:431-434 when the corpus is row-sharded. */
+int drag_index_search_sharded(drag_index_t* h, const float* q_dev, int nq, int k, void* const* peer_bufs, int world, int rank,
+                              int nq_cap, int k_cap, uint32_t epoch, float* D_ws, int64_t* I_ws, float* D_dev,
+                              int64_t* I_dev, void* stream);
 
 /* ---- ResNet-50 stem + style statistics --------------------------------------------------------
  * Replaces ResNetEncoder()(x) + calc_mean_std (retrieval/clip100_resnet_style_all_shots.py:51-74,
@@ -123,6 +129,17 @@ int drag_layernorm_bf16(const void* x, int ldx, void* out, int ldo, int M, int d
 int drag_timestep_embed(const float* t_dev, void* out, int B, void* stream);
 /* Flow-match Euler update on a strided bf16 view: x += dsigma * v (fp32 arithmetic). */
 int drag_euler_step(void* x, int ldx, const void* v, int ldv, int rows, int cols, float dsigma, void* stream);
+/* Flux 2x2 latent packing (diffusers FluxPipeline._pack_latents / _unpack_latents, inside the pipe(...) calls of
+ * batch_generate_flux_kshot.py:467-474 and outpainting_updown_sampling_redux.py:1246-1257): z bf16 [B][C][h][w] <->
+ * token s = (y/2)(w/2) + x/2, channel ch_off + c*4 + (y%2)*2 + (x%2) of a row with leading dim ldo / ldx. */
+int drag_pack_latents(const void* z, int B, int C, int h, int w, void* out, int64_t ldo, int ch_off, void* stream);
+int drag_unpack_latents(const void* x, int64_t ldx, int B, int C, int h, int w, void* z, void* stream);
+/* Flux-Fill transformer input (FluxFillPipeline.prepare_mask_latents + the per-step channel concat; outpainting...:1246-1257):
+ * x bf16 [B][(h/2)(w/2)][ldx >= 384]: channels 0:64 = `latents` (already packed, leading dim ld_lat; NULL leaves them
+ * untouched), 64:128 = packed `masked_latents` bf16 [B][16][h][w], 128:384 = the 8x8 block of `mask` (uint8 [B][8h][8w],
+ * non-zero = repaint) under every latent pixel as 64 channels, packed the same way. One launch. */
+int drag_pack_fill_inputs(const void* latents, int64_t ld_lat, const void* masked_latents, const uint8_t* mask, int B, int h,
+                          int w, void* x, int64_t ldx, void* stream);
 /* FluxPriorReduxPipeline output blend (batch_generate_flux_kshot.py:459-465, outpainting...:1237-1243):
  * out_embeds[1][n_txt+n_img][dim] = sum_b s_embed[b] * cat(txt[b], img[b]); out_pooled = sum_b s_pool[b]*pooled[b]. */
 int drag_redux_blend(const void* txt, const void* img, const void* pooled, const float* s_embed_dev,

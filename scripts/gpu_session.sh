@@ -14,6 +14,7 @@ for stage in "$@"; do
     tests)        run 1500 tests python -m pytest tests -m gpu -q --durations=10 -s ;;
     tests_x)      run 1500 tests python -m pytest tests -m gpu -x -q --durations=10 ;;
     tests_new)    run 900 tests_new python -m pytest tests/test_full_depth_gpu.py tests/test_cli_gpu.py tests/test_pipelines_gpu.py tests/test_retrieval_cli_gpu.py tests/test_topk_gpu.py -m gpu -q -s --durations=10 ;;
+    tests_pack)   run 600 tests_pack python -m pytest tests/test_pipelines_gpu.py tests/test_sharded_nccl_gpu.py tests/test_topk_gpu.py -m gpu -q --durations=5 ;;
     tests_attn)   run 600 tests_attn python -m pytest tests/test_flux_gpu.py tests/test_stem_gpu.py tests/test_vit_gpu.py -m gpu -q -s --durations=5 ;;
     attn_quick)   run 150 attn_tests python -m pytest tests/test_flux_gpu.py -k "attention" -m gpu -q -x
                   run 120 attn python scripts/bench_attn.py ;;

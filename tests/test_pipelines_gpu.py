@@ -185,3 +185,31 @@ def test_generate_batch_with_generator_list_equals_sequential_calls(lib):
         assert rel_l2(batch.latents[i:i + 1], one.latents) < 2e-3
         d = np.abs(np.asarray(batch.images[i]).astype(np.int32) - np.asarray(one.images[0]).astype(np.int32))
         assert d.max() <= 2, d.max()
+
+
+@pytest.mark.parametrize("B,h,w", [(1, 8, 12), (3, 16, 16), (2, 64, 96)])
+def test_pack_kernels_match_oracle_bit_exact(lib, B, h, w):
+    """drag_pack_latents / drag_unpack_latents / drag_pack_fill_inputs against the oracle's view/permute statements of
+    diffusers' _pack_latents and prepare_mask_latents (oracle/flux.py, oracle/pipelines.py): data movement, so bit-exact."""
+    from domain_rag_b200 import flux as F
+    g = torch.Generator().manual_seed(100 + B * h)
+    z = torch.randn((B, 16, h, w), generator=g).to(torch.bfloat16)
+    zm = torch.randn((B, 16, h, w), generator=g).to(torch.bfloat16)
+    mask = (torch.rand((B, 8 * h, 8 * w), generator=g) > 0.6).to(torch.uint8)
+    mask[:, :: 7, :: 5] *= 3                                    # any non-zero value means "repaint"
+    lat = torch.randn((B, (h // 2) * (w // 2), 64), generator=g).to(torch.bfloat16)
+
+    packed = F.pack_latents_device(z.cuda())
+    assert torch.equal(packed.cpu(), OF.pack_latents(z))
+    assert torch.equal(F.unpack_latents_device(packed, h, w).cpu(), z)
+    wide = torch.zeros((B, (h // 2) * (w // 2), 96), dtype=torch.bfloat16, device="cuda")
+    F.pack_latents_device(zm.cuda(), out=wide, ch_off=32)       # into a channel window of a wider row
+    assert torch.equal(wide[:, :, 32:].cpu(), OF.pack_latents(zm)) and not wide[:, :, :32].any()
+    assert torch.equal(F.unpack_latents_device(wide[:, :, 32:], h, w).cpu(), zm)    # strided view in
+
+    want = torch.cat([lat, OF.pack_latents(zm), OP.pack_mask((mask > 0).float()).to(torch.bfloat16)], dim=-1)
+    got = F.pack_fill_inputs(lat.cuda(), zm.cuda(), mask.cuda())
+    assert got.shape == (B, (h // 2) * (w // 2), 384)
+    assert torch.equal(got.cpu(), want)
+    keep = F.pack_fill_inputs(None, zm.cuda(), mask.cuda())     # latents = NULL: only the 320 conditioning channels
+    assert torch.equal(keep[:, :, 64:].cpu(), want[:, :, 64:])
