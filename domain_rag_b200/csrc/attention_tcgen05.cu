@@ -157,6 +157,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     const int bh = blockIdx.y;
     const int n_tiles = (a.S + AT_TILE - 1) / AT_TILE;
     const bool has_b = PP && (q0 + AT_TILE) < a.S;     // second query tile holds at least one row
+    // Short sequences (!PP: CLIP ViT, 50 / 197 / 257 tokens) pay for every padded key: ViT-L/14's 257 = 2 x 128 + 1 made the
+    // third key tile a full 128-column tile with ONE live column. There the last tile is narrow: Q K^T with N = the valid
+    // keys rounded up to 16, exponentials for the valid keys rounded up to 32, P V over the same 16-key steps.
+    const int tail = a.S - (n_tiles - 1) * AT_TILE;                     // valid keys of the last tile, 1..128
+    const int tail_ks = PP ? AT_TILE / 16 : (tail + 15) / 16;           // 16-key MMA steps of the last tile
+    const int tail_cols = PP ? AT_TILE : ((tail + 31) & ~31);           // score columns the softmax touches there
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmQ);
@@ -233,13 +239,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const uint64_t q_desc0 = umma_desc_k_sw128(smem_u32(smem + Cfg::Q_OFF));
         const uint64_t k_desc0 = umma_desc_k_sw128(smem_u32(smem + Cfg::K_OFF));
         const uint64_t v_desc0 = umma_desc_mn_sw128(smem_u32(smem + Cfg::V_OFF), Cfg::NH > 1 ? AT_HALF_BYTES : 0, 1024);
-        auto issue_qk = [&](int x, int st) {     // S_x = Q_x K^T  (K tile already waited for)
+        const uint32_t idesc_qk_tail = umma_idesc_bf16(128, static_cast<uint32_t>(tail_ks) * 16, 0, 0);
+        auto issue_qk = [&](int x, int st, bool last_tile) {     // S_x = Q_x K^T  (K tile already waited for)
             const uint64_t qd = q_desc0 + ((x * TILE_BYTES) >> 4), kd = k_desc0 + ((st * TILE_BYTES) >> 4);
+            const uint32_t idesc = (!PP && last_tile) ? idesc_qk_tail : idesc_qk;
             if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < HD / 16; ++ks) {
                     const uint32_t off = ((ks >> 2) * AT_HALF_BYTES + (ks & 3) * 32) >> 4;
-                    tc_mma_f16(tmem_base + x * 128, qd + off, kd + off, idesc_qk, ks != 0);
+                    tc_mma_f16(tmem_base + x * 128, qd + off, kd + off, idesc, ks != 0);
                 }
                 tc_commit(&s_full[x]);
             }
@@ -248,12 +256,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         // O_x += P_x V, keys [half*64, half*64+64) of the tile   (P_x: packed bf16 in S_x columns [0,64))
         auto issue_pv = [&](int x, int st, int j, int half, bool last) {
             const uint64_t vd = v_desc0 + ((st * TILE_BYTES) >> 4);
+            const int nks = (!PP && j == n_tiles - 1) ? tail_ks : AT_TILE / 16;     // 16-key steps of this tile
             if (elect_one()) {
 #pragma unroll
                 for (int kk = 0; kk < AT_TILE / 32; ++kk) {    // 16 kv rows per k-step = 2048 B inside each half
                     const int ks = half * (AT_TILE / 32) + kk;
-                    tc_mma_f16_ts(tmem_base + Cfg::O_COL + x * 128, tmem_base + x * 128 + ks * 8, vd + ((ks * 2048) >> 4), idesc_pv,
-                                  (j | ks) != 0);
+                    if (PP || ks < nks)
+                        tc_mma_f16_ts(tmem_base + Cfg::O_COL + x * 128, tmem_base + x * 128 + ks * 8, vd + ((ks * 2048) >> 4),
+                                      idesc_pv, (j | ks) != 0);
                 }
                 if (last) tc_commit(&pv_done[x]);
             }
@@ -262,8 +272,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         mbar_wait(q_full, 0);
         mbar_wait(&k_full[0], 0);
         tc_fence_after();
-        issue_qk(0, 0);
-        if (has_b) issue_qk(1, 0);
+        issue_qk(0, 0, n_tiles == 1);
+        if (has_b) issue_qk(1, 0, n_tiles == 1);
         if (elect_one()) tc_commit(&k_empty[0]);
         __syncwarp();
         for (int j = 0; j < n_tiles; ++j) {
@@ -280,7 +290,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             if (more) {
                 mbar_wait(&k_full[nst], npar);
                 tc_fence_after();
-                issue_qk(0, nst);
+                issue_qk(0, nst, j + 2 == n_tiles);
             }
             if (has_b) {
                 mbar_wait(&p_half[1], j & 1);
@@ -289,7 +299,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 mbar_wait(&p_full[1], j & 1);
                 tc_fence_after();
                 issue_pv(1, st, j, 1, true);
-                if (more) issue_qk(1, nst);
+                if (more) issue_qk(1, nst, j + 2 == n_tiles);
             }
             if (elect_one()) {
                 tc_commit(&v_empty[st]);
@@ -309,14 +319,30 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const uint32_t t_s = t_lane + x * 128;             // S / P
         const uint32_t t_o = t_lane + Cfg::O_COL + x * 128;  // O
         float m = -INFINITY, l = 0.f;
-        for (int j = 0; j < n_tiles; ++j) {
+        // !PP: a warp whose 32 query rows all lie past the sequence end (ViT-L/14: 127 of the 128 rows of the third query
+        // tile) only keeps the barrier protocol going - its rows of P and O are never stored, so they may hold anything.
+        // It paces itself on s_full so that its arrivals land in the right barrier phase.
+        const bool warp_dead = !PP && (q0 + quarter * 32) >= a.S;
+        if (warp_dead) {
+            for (int j = 0; j < n_tiles; ++j) {
+                mbar_wait(&s_full[x], j & 1);
+                if (lane == 0) {
+                    mbar_arrive(&p_half[x]);
+                    mbar_arrive(&p_full[x]);
+                }
+            }
+        }
+        for (int j = 0; j < (warp_dead ? 0 : n_tiles); ++j) {
             mbar_wait(&s_full[x], j & 1);
             tc_fence_after();
             const int kv_valid = a.S - j * AT_TILE;        // columns >= kv_valid are past the sequence end
+            const int ncol = (!PP && j == n_tiles - 1) ? tail_cols : AT_TILE;     // score columns in use (warp-uniform)
             // the whole 128-wide score row of this thread in registers: ONE TMEM pass per key tile
             uint32_t v[AT_TILE];
 #pragma unroll
-            for (int c = 0; c < AT_TILE; c += 32) tmem_ld_32x32_ptr(t_s + c, &v[c]);
+            for (int c = 0; c < AT_TILE; c += 32) {
+                if (PP || c < ncol) tmem_ld_32x32_ptr(t_s + c, &v[c]);
+            }
             tmem_ld_wait();
             if (kv_valid < AT_TILE) {
 #pragma unroll
@@ -365,6 +391,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             // half is still being exponentiated.
 #pragma unroll
             for (int c = 0; c < AT_TILE; c += 32) {
+                if (!PP && c >= ncol) break;                 // narrow last tile: nothing but padding from here on
                 uint32_t packed[16];
 #pragma unroll
                 for (int pr = 0; pr < 16; ++pr) {            // pairs of row elements
@@ -390,8 +417,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[x]);
+            if (lane == 0) {
+                if (!PP && ncol < 64) mbar_arrive(&p_half[x]);     // the c == 32 checkpoint above was never reached
+                mbar_arrive(&p_full[x]);
+            }
         }
+        if (!warp_dead) {
         mbar_wait(&pv_done[x], (n_tiles - 1) & 1);
         tc_fence_after();
         const float inv = 1.f / l;
@@ -420,6 +451,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     *reinterpret_cast<uint4*>(orow + c * 32 + i) = u;
                 }
             }
+        }
         }
     }
     }
@@ -749,6 +781,352 @@ attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __
     }
 }
 
+// ---------------------------------------------------------------------------------------------- whole-row kernel (head dim 64)
+// CLIP ViT sequences are 50 / 197 / 257 tokens. The tiled kernels above walk 128-key tiles with an online softmax: per
+// query tile three QK -> softmax -> PV round trips through mbarriers plus prologue and epilogue - a LATENCY chain of ~13 k
+// cycles per CTA in which the tensor core is busy 25 % of the time, and ViT-L/14's 257 = 2 x 128 + 1 pays a whole third key
+// tile for one key (measured: trimming that tile's arithmetic alone changed nothing - the chain, not the math, is the cost).
+// Here the whole score row lives in TMEM at once: ONE UMMA sequence S = Q K^T with N = up to 256 keys, a two-pass softmax
+// (exact row maximum, no running rescale), ONE sequence O = P V, one barrier round trip per query tile. Keys 256.. (at most
+// AR_TAIL = 4 of them: the 257th token of ViT-L/14) never touch the tensor core: their scores are 64-term dot products on the
+// CUDA cores, their P V contribution is added to O in the epilogue in fp32.
+// TMEM (256 columns, two CTAs per SM): S [0,256) -> P packed bf16 [0,128) in place; O [128,192) reuses dead S columns.
+constexpr int AR_MAIN = 256;
+constexpr int AR_TAIL = 4;
+struct AttnRowCfg {
+    static constexpr int Q_OFF = 0;                           // 128 rows x 128 B
+    static constexpr int K_OFF = AT_HALF_BYTES;               // 256 rows x 128 B (two TMA boxes back to back)
+    static constexpr int V_OFF = K_OFF + 2 * AT_HALF_BYTES;
+    static constexpr int BAR_OFF = V_OFF + 2 * AT_HALF_BYTES;
+    static constexpr int KT_OFF = BAR_OFF + 256;              // tail keys: AR_TAIL rows x 128 B, unswizzled
+    static constexpr int VT_OFF = KT_OFF + AR_TAIL * 128;
+    static constexpr int SMEM = VT_OFF + AR_TAIL * 128 + 1024;
+    static constexpr int TMEM_COLS = 256;
+    static constexpr int O_COL = 128;
+};
+struct AttnRowArgs {
+    AttnArgs a;
+    const __nv_bfloat16 *k, *v;        // [B*H][S][64]: rows 256.. are bulk-copied next to the TMA tiles
+    int prefetch_stride;               // this CTA warms L2 for the CTA `prefetch_stride` positions later in launch order
+};
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4& u, float* f) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(p[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+
+__global__ void __launch_bounds__(256, 2)
+attention_row_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, AttnRowArgs ar) {
+    using Cfg = AttnRowCfg;
+    constexpr int HD = 64;
+    const AttnArgs& a = ar.a;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+    uint64_t* qk_full = bars + 0;
+    uint64_t* v_full = bars + 1;
+    uint64_t* s_full = bars + 2;
+    uint64_t* p_full = bars + 3;
+    uint64_t* pv_done = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * AT_TILE;
+    const int bh = blockIdx.y;
+    const int n_main = min(a.S, AR_MAIN);                 // keys on the tensor core
+    const int n_tail = a.S - n_main;                      // keys on the CUDA cores (0..AR_TAIL)
+    const int n_mma = (n_main + 15) & ~15;                // N of Q K^T, K extent of P V
+    const int k_boxes = (n_main + AT_TILE - 1) / AT_TILE;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        mbar_init(qk_full, 1);
+        mbar_init(v_full, 1);
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 4);
+        mbar_init(pv_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        setmaxnreg_dec<56>();
+        if (warp == 0) {
+            // ------------------------------------------------------------------ TMA producer: everything at once
+            if (elect_one()) {
+                const size_t tail_off = (static_cast<size_t>(bh) * a.S + n_main) * HD;
+                mbar_arrive_expect_tx(qk_full, (1 + k_boxes) * AT_HALF_BYTES + n_tail * 128);
+                tma_load_3d(smem + Cfg::Q_OFF, &tmQ, 0, q0, bh, qk_full);
+                for (int i = 0; i < k_boxes; ++i)
+                    tma_load_3d(smem + Cfg::K_OFF + i * AT_HALF_BYTES, &tmK, 0, i * AT_TILE, bh, qk_full);
+                if (n_tail > 0) bulk_g2s(smem + Cfg::KT_OFF, ar.k + tail_off, n_tail * 128, qk_full);
+                mbar_arrive_expect_tx(v_full, k_boxes * AT_HALF_BYTES + n_tail * 128);
+                for (int i = 0; i < k_boxes; ++i)
+                    tma_load_3d(smem + Cfg::V_OFF + i * AT_HALF_BYTES, &tmV, 0, i * AT_TILE, bh, v_full);
+                if (n_tail > 0) bulk_g2s(smem + Cfg::VT_OFF, ar.v + tail_off, n_tail * 128, v_full);
+                // A CTA lives ~7 us, of which the first ~2.5 were spent waiting for these tiles to come from HBM (ncu: 37 %
+                // of the softmax warps' samples). Two CTAs per SM cannot hide that, so every CTA pulls the tiles of the CTA
+                // that will take over a slot about one CTA lifetime from now into L2: its loads then cost an L2 hit.
+                const long long tgt = static_cast<long long>(bh) * gridDim.x + blockIdx.x + ar.prefetch_stride;
+                const int tbh = static_cast<int>(tgt / gridDim.x), tx = static_cast<int>(tgt - static_cast<long long>(tbh) * gridDim.x);
+                if (ar.prefetch_stride > 0 && tbh < static_cast<int>(gridDim.y)) {
+                    tma_prefetch_l2_3d(&tmQ, 0, tx * AT_TILE, tbh);
+                    if (tx == 0) {                         // K / V are shared by the query tiles of one (batch, head)
+                        for (int i = 0; i < k_boxes; ++i) {
+                            tma_prefetch_l2_3d(&tmK, 0, i * AT_TILE, tbh);
+                            tma_prefetch_l2_3d(&tmV, 0, i * AT_TILE, tbh);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            // ------------------------------------------------------------------ MMA issuer
+            const uint32_t idesc_qk = umma_idesc_bf16(128, static_cast<uint32_t>(n_mma), 0, 0);
+            constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD, 0, 1);
+            const uint64_t qd = umma_desc_k_sw128(smem_u32(smem + Cfg::Q_OFF));
+            const uint64_t kd = umma_desc_k_sw128(smem_u32(smem + Cfg::K_OFF));
+            const uint64_t vd = umma_desc_mn_sw128(smem_u32(smem + Cfg::V_OFF), 0, 1024);
+            mbar_wait(qk_full, 0);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < HD / 16; ++ks)
+                    tc_mma_f16(tmem_base, qd + ((ks * 32) >> 4), kd + ((ks * 32) >> 4), idesc_qk, ks != 0);
+                tc_commit(s_full);
+            }
+            __syncwarp();
+            mbar_wait(v_full, 0);
+            mbar_wait(p_full, 0);
+            tc_fence_after();
+            if (elect_one()) {
+                const int nks = n_mma / 16;
+                for (int ks = 0; ks < nks; ++ks)          // 16 keys per step: 8 packed P columns, 2048 B of V
+                    tc_mma_f16_ts(tmem_base + Cfg::O_COL, tmem_base + ks * 8, vd + ((ks * 2048) >> 4), idesc_pv, ks != 0);
+                tc_commit(pv_done);
+            }
+            __syncwarp();
+        }
+    } else {
+        setmaxnreg_inc<200>();
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const int srow = q0 + r;
+        if (q0 + quarter * 32 >= a.S) {
+            // no live query row in this warp: its rows of P and O are never stored and may hold anything
+            if (lane == 0) mbar_arrive(p_full);
+        } else {
+            const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+            const uint32_t t_s = t_lane;
+            const uint32_t t_o = t_lane + Cfg::O_COL;
+            // scores of the tail keys on the CUDA cores, before the tensor core has anything to show
+            float st[AR_TAIL];
+#pragma unroll
+            for (int t = 0; t < AR_TAIL; ++t) st[t] = -INFINITY;
+            if (n_tail > 0) {
+                // q row r of the SWIZZLE_128B tile: 16-byte chunk j sits at chunk position j ^ (r & 7) of its 128-byte row
+                mbar_wait(qk_full, 0);
+                const uint8_t* qrow = smem + Cfg::Q_OFF + r * 128;
+                uint4 qv[HD / 8];
+#pragma unroll
+                for (int i = 0; i < HD / 8; ++i) qv[i] = *reinterpret_cast<const uint4*>(qrow + ((i ^ (r & 7)) << 4));
+#pragma unroll
+                for (int t = 0; t < AR_TAIL; ++t) {
+                    if (t < n_tail) {
+                        const uint4* kp = reinterpret_cast<const uint4*>(smem + Cfg::KT_OFF + t * 128);
+                        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < HD / 8; ++i) {
+                            float qf[8], kf[8];
+                            bf16x8_to_float(qv[i], qf);
+                            bf16x8_to_float(kp[i], kf);
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                acc0 = fmaf(qf[e], kf[e], acc0);
+                                acc1 = fmaf(qf[e + 1], kf[e + 1], acc1);
+                            }
+                        }
+                        st[t] = acc0 + acc1;
+                    }
+                }
+            }
+            const int ncol = (n_main + 31) & ~31;          // score columns read (warp-uniform)
+            mbar_wait(s_full, 0);
+            tc_fence_after();
+            // pass 1: the exact row maximum
+            static_assert(AR_TAIL == 4, "the four maximum chains start from the four tail scores");
+            float m0 = st[0], m1 = st[1], m2 = st[2], m3 = st[3];
+#pragma unroll
+            for (int c = 0; c < AR_MAIN; c += 64) {
+                if (c < ncol) {
+                    uint32_t v[64];
+                    tmem_ld_32x32_ptr(t_s + c, &v[0]);
+                    tmem_ld_32x32_ptr(t_s + c + 32, &v[32]);
+                    tmem_ld_wait();
+                    if (c + 64 > n_main) {
+#pragma unroll
+                        for (int i = 0; i < 64; ++i)
+                            if (c + i >= n_main) v[i] = 0xff800000u;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 64; i += 8) {
+                        m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                        m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                        m2 = fmax3(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+                        m3 = fmax3(m3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+                    }
+                }
+            }
+            const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * a.scale_log2;
+            // pass 2: P = exp2(s * scale - m) as packed bf16 IN PLACE (columns [c/2, c/2 + 16) were read in an earlier step)
+            const float2 sc2 = splat2(a.scale_log2), nm2 = splat2(-m);
+            float2 sum_a = splat2(0.f), sum_b = splat2(0.f);
+#pragma unroll
+            for (int c = 0; c < AR_MAIN; c += 32) {
+                if (c < ncol) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_s + c, v);
+                    tmem_ld_wait();
+                    if (c + 32 > n_main) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c + i >= n_main) v[i] = 0xff800000u;
+                    }
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int pr = 0; pr < 16; ++pr) {
+                        const float2 x = ffma2(make_float2(__uint_as_float(v[2 * pr]), __uint_as_float(v[2 * pr + 1])), sc2, nm2);
+                        const float2 e = ((AT_POLY_MASK >> (pr & 7)) & 1) ? ex2_poly2(x)
+                                                                          : make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                        if (pr & 1) sum_b = fadd2(sum_b, e);
+                        else sum_a = fadd2(sum_a, e);
+                        packed[pr] = pack_bf16x2(e);
+                    }
+                    tmem_st_32x16(t_s + (c >> 1), packed);
+                }
+            }
+            const float2 sum2 = fadd2(sum_a, sum_b);
+            float l = sum2.x + sum2.y;
+            float pt[AR_TAIL];
+#pragma unroll
+            for (int t = 0; t < AR_TAIL; ++t) {
+                pt[t] = (t < n_tail) ? ex2_approx(fmaf(st[t], a.scale_log2, -m)) : 0.f;
+                l += pt[t];
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+
+            mbar_wait(pv_done, 0);
+            tc_fence_after();
+            if (n_tail > 0) mbar_wait(v_full, 0);            // long complete; makes the bulk-copied tail rows visible here
+            const float inv = 1.f / l;
+            const int b = bh / a.H, h = bh - b * a.H;
+            __nv_bfloat16* orow = (srow < a.split)
+                ? a.out0 + (static_cast<size_t>(b) * a.split + srow) * a.ld0 + h * HD
+                : a.out1 + (static_cast<size_t>(b) * (a.S - a.split) + (srow - a.split)) * a.ld1 + h * HD;
+#pragma unroll 1
+            for (int c = 0; c < HD / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_o + c * 32, v);
+                tmem_ld_wait();
+                float o[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]);
+#pragma unroll
+                for (int t = 0; t < AR_TAIL; ++t) {          // the tail keys' share of P V, fp32
+                    if (t < n_tail) {
+                        const uint4* vp = reinterpret_cast<const uint4*>(smem + Cfg::VT_OFF + t * 128 + c * 64);
+                        const float p = pt[t];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float vf[8];
+                            bf16x8_to_float(vp[i], vf);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) o[i * 8 + e] = fmaf(p, vf[e], o[i * 8 + e]);
+                        }
+                    }
+                }
+                if (srow < a.S) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        __nv_bfloat162 p0 = __floats2bfloat162_rn(o[i] * inv, o[i + 1] * inv);
+                        __nv_bfloat162 p1 = __floats2bfloat162_rn(o[i + 2] * inv, o[i + 3] * inv);
+                        __nv_bfloat162 p2 = __floats2bfloat162_rn(o[i + 4] * inv, o[i + 5] * inv);
+                        __nv_bfloat162 p3 = __floats2bfloat162_rn(o[i + 6] * inv, o[i + 7] * inv);
+                        uint4 u;
+                        u.x = *reinterpret_cast<uint32_t*>(&p0);
+                        u.y = *reinterpret_cast<uint32_t*>(&p1);
+                        u.z = *reinterpret_cast<uint32_t*>(&p2);
+                        u.w = *reinterpret_cast<uint32_t*>(&p3);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + i) = u;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+int g_attn_row_prefetch = 1;   // drag_debug_set key 11: 0 = the whole-row kernel does not warm L2 for later CTAs (A/B comparisons)
+static int launch_attention_row(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int B, int H, int S,
+                                AttnArgs a, cudaStream_t st) {
+    using Cfg = AttnRowCfg;
+    constexpr int HD = 64;
+    CUtensorMap tq, tk, tv;
+    const uint64_t bh = static_cast<uint64_t>(B) * H;
+    int rc = make_tmap_bf16_3d(&tq, q, HD, S, bh, HD, static_cast<uint64_t>(S) * HD, 64, AT_TILE);
+    if (rc) return rc;
+    rc = make_tmap_bf16_3d(&tk, k, HD, S, bh, HD, static_cast<uint64_t>(S) * HD, 64, AT_TILE);
+    if (rc) return rc;
+    rc = make_tmap_bf16_3d(&tv, v, HD, S, bh, HD, static_cast<uint64_t>(S) * HD, 64, AT_TILE);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DRAG_CUDA(cudaFuncSetAttribute(attention_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        DRAG_CUDA(cudaFuncSetAttribute(attention_row_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set = true;
+    }
+    a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+    AttnRowArgs ar;
+    ar.a = a; ar.k = k; ar.v = v;
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        DRAG_CUDA(cudaGetDevice(&dev));
+        DRAG_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    ar.prefetch_stride = g_attn_row_prefetch ? 2 * sm_count : 0;       // two resident CTAs per SM
+    dim3 grid((S + AT_TILE - 1) / AT_TILE, static_cast<unsigned>(bh));
+    const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * H * static_cast<double>(S) * S * HD, st);
+    attention_row_kernel<<<grid, 256, Cfg::SMEM, st>>>(tq, tk, tv, ar); count_launch();
+    prof_end(slot, st);
+    DRAG_CUDA(cudaGetLastError());
+    return DRAG_OK;
+}
+
 template <int HD, bool PP>
 static int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int B, int H, int S,
                             AttnArgs a, cudaStream_t st) {
@@ -809,6 +1187,7 @@ static int launch_attention_split(const __nv_bfloat16* q, const __nv_bfloat16* k
 // Debug knobs kept for ABI stability (drag_debug_set keys 1/2); unused by the current kernel.
 uint32_t g_attn_v_lbo = 0, g_attn_v_sbo = 1024;
 int g_attn_force_pp = 0;      // drag_debug_set key 5: 1 = always the two-tile ping-pong kernel (A/B comparisons)
+int g_attn_no_row = 0;        // drag_debug_set key 10: 1 = head dim 64 never takes the whole-row kernel (A/B comparisons)
 int g_attn_split = 0;         // drag_debug_set key 7: head dim 128: 1 = split-row kernel (two softmax warpgroups per query tile),
                               // 0 = one thread per row (default: the split kernel measured 13 % SLOWER, see the kernel)
 
@@ -828,7 +1207,9 @@ int attention_bf16(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bf
     if (head_dim == 128)
         return g_attn_split ? launch_attention_split<128>(q, k, v, B, H, S, a, st)
                             : launch_attention<128, true>(q, k, v, B, H, S, a, st);
-    // head dim 64 = the CLIP ViT towers: short sequences -> two single-tile CTAs per SM; long ones keep the ping-pong
+    // head dim 64 = the CLIP ViT towers: up to 256 (+ AR_TAIL) keys -> the whole-row kernel; longer sequences the tiled ones
+    // (two single-tile CTAs per SM up to 512 keys, the ping-pong beyond)
+    if (S <= AR_MAIN + AR_TAIL && !g_attn_force_pp && !g_attn_no_row) return launch_attention_row(q, k, v, B, H, S, a, st);
     if (S <= 4 * AT_TILE && !g_attn_force_pp) return launch_attention<64, false>(q, k, v, B, H, S, a, st);
     return launch_attention<64, true>(q, k, v, B, H, S, a, st);
 }

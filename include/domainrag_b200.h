@@ -247,7 +247,9 @@ int drag_launch_count(int64_t* count, int reset);
  * row-fastest order; key 5: 1 = head-dim-64 attention always on the two-tile ping-pong kernel; key 6: > 0 = force the
  * column-group raster with that many column tiles per group; key 7: head-dim-128 attention:
  * 1 = split-row kernel, two softmax warpgroups per query tile (measured slower), 0 = one thread per row (default); key 8: 1 = stem statistics on the FP32 CUDA-core kernel instead of
- * the tensor-core kernel; key 9: 1 = GEMM epilogues store 16 bytes per lane instead of 32). */
+ * the tensor-core kernel; key 9: 1 = GEMM epilogues store 16 bytes per lane instead of 32; key 10: 1 = head-dim-64
+ * attention never takes the whole-row kernel, i.e. the tiled online-softmax kernels also for <= 260 keys; key 11: 0 = the whole-row kernel
+ * does not prefetch the tiles of later CTAs into L2). */
 int drag_debug_set(int key, int value);
 
 #ifdef __cplusplus

@@ -39,23 +39,44 @@ def test_attention_matches_sdpa(ops, B, H, S, split):
         assert (got.float() - ref[:, split:]).abs().max().item() < 2e-2
 
 
-@pytest.mark.parametrize("force_pp", [0, 1])
-@pytest.mark.parametrize("B,H,S", [(3, 4, 50), (2, 16, 257), (1, 12, 197), (2, 2, 128), (1, 3, 512), (1, 2, 700)])
-def test_attention_head_dim_64_both_variants(ops, B, H, S, force_pp):
-    """CLIP ViT shapes: short sequences run the single-tile kernel (two CTAs per SM), S > 512 or drag_debug_set(5, 1)
-    the two-tile ping-pong kernel; both must agree with fp32 SDPA."""
+@pytest.mark.parametrize("variant", ["default", "force_pp", "no_row"])
+@pytest.mark.parametrize("B,H,S", [(3, 4, 50), (2, 16, 257), (1, 12, 197), (2, 2, 128), (1, 3, 512), (1, 2, 700), (2, 3, 1),
+                                   (1, 2, 17), (2, 2, 256), (1, 5, 258), (2, 2, 260), (1, 2, 261)])
+def test_attention_head_dim_64_all_variants(ops, B, H, S, variant):
+    """CLIP ViT shapes. Default: up to 256 (+4) keys take the whole-row kernel (one Q K^T, exact two-pass softmax, one P V; keys
+    past 256 on the CUDA cores), longer sequences the tiled online-softmax kernels (single-tile CTAs up to 512 keys, the
+    two-tile ping-pong beyond). drag_debug_set(5, 1) forces the ping-pong, (10, 1) the tiled kernels for every length. All
+    must agree with fp32 SDPA."""
     q, k, v = rnd((B, H, S, 64), 21), rnd((B, H, S, 64), 22), rnd((B, H, S, 64), 23)
-    ops.debug_set(5, force_pp)
+    key = {"default": None, "force_pp": 5, "no_row": 10}[variant]
+    if key is not None:
+        ops.debug_set(key, 1)
     try:
         _, o = ops.attention(q, k, v, 0)
         torch.cuda.synchronize()
     finally:
-        ops.debug_set(5, 0)
+        if key is not None:
+            ops.debug_set(key, 0)
     ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
     ref = ref.permute(0, 2, 1, 3).reshape(B, S, H * 64)
     got = o.view(B, S, -1)
     assert rel_l2(got, ref) < 1e-2
     assert (got.float() - ref).abs().max().item() < 2e-2
+
+
+def test_attention_whole_row_kernel_tail_keys_dominate(ops):
+    """S = 257..260: the keys past 256 are scored on the CUDA cores and enter max, sum and P V outside the tensor core.
+    Make exactly those keys carry the row maximum and most of the probability mass."""
+    for S in (257, 259, 260):
+        B, H = 2, 3
+        q, k, v = rnd((B, H, S, 64), 31), rnd((B, H, S, 64), 32), rnd((B, H, S, 64), 33)
+        k[:, :, 256:] = q[:, :, 5:5 + S - 256] * 1.5                 # large positive logits for some rows
+        _, o = ops.attention(q, k, v, 0)
+        ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+        ref = ref.permute(0, 2, 1, 3).reshape(B, S, H * 64)
+        got = o.view(B, S, -1)
+        assert rel_l2(got, ref) < 1e-2
+        assert (got.float() - ref).abs().max().item() < 3e-2
 
 
 def test_attention_large_logits(ops):
