@@ -249,7 +249,8 @@ int drag_launch_count(int64_t* count, int reset);
  * 1 = split-row kernel, two softmax warpgroups per query tile (measured slower), 0 = one thread per row (default); key 8: 1 = stem statistics on the FP32 CUDA-core kernel instead of
  * the tensor-core kernel; key 9: 1 = GEMM epilogues store 16 bytes per lane instead of 32; key 10: 1 = head-dim-64
  * attention never takes the whole-row kernel, i.e. the tiled online-softmax kernels also for <= 260 keys; key 11: 0 = the whole-row kernel
- * does not prefetch the tiles of later CTAs into L2). */
+ * does not prefetch the tiles of later CTAs into L2; key 12: 0 = 129..260 keys take the one-tile-per-CTA whole-row kernel
+ * instead of the persistent one). */
 int drag_debug_set(int key, int value);
 
 #ifdef __cplusplus

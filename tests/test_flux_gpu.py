@@ -43,7 +43,7 @@ def test_attention_matches_sdpa(ops, B, H, S, split):
 @pytest.mark.parametrize("B,H,S", [(3, 4, 50), (2, 16, 257), (1, 12, 197), (2, 2, 128), (1, 3, 512), (1, 2, 700), (2, 3, 1),
                                    (1, 2, 17), (2, 2, 256), (1, 5, 258), (2, 2, 260), (1, 2, 261)])
 def test_attention_head_dim_64_all_variants(ops, B, H, S, variant):
-    """CLIP ViT shapes. Default: up to 256 (+4) keys take the whole-row kernel (one Q K^T, exact two-pass softmax, one P V; keys
+    """CLIP ViT shapes. Default: up to 257 keys take the whole-row kernels (one Q K^T, exact two-pass softmax, one P V; keys
     past 256 on the CUDA cores), longer sequences the tiled online-softmax kernels (single-tile CTAs up to 512 keys, the
     two-tile ping-pong beyond). drag_debug_set(5, 1) forces the ping-pong, (10, 1) the tiled kernels for every length. All
     must agree with fp32 SDPA."""
@@ -64,11 +64,27 @@ def test_attention_head_dim_64_all_variants(ops, B, H, S, variant):
     assert (got.float() - ref).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("S", [129, 197, 256, 257])
+def test_attention_head_dim_64_persistent_kernel_many_items(ops, S):
+    """129..257 keys run the persistent whole-row kernel: one CTA per SM walks several (batch, head) items through two
+    shared-memory slots and the two TMEM halves, so the barrier phases wrap around. 47 x 16 = 752 items = 5-6 per CTA."""
+    B, H = 47, 16
+    q, k, v = rnd((B, H, S, 64), 41), rnd((B, H, S, 64), 42), rnd((B, H, S, 64), 43)
+    _, o = ops.attention(q, k, v, 0)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    ref = ref.permute(0, 2, 1, 3).reshape(B, S, H * 64)
+    got = o.view(B, S, -1)
+    assert rel_l2(got, ref) < 1e-2
+    assert (got.float() - ref).abs().max().item() < 2e-2
+    _, o2 = ops.attention(q, k, v, 0)                      # deterministic: no atomics, fixed item -> CTA mapping
+    assert torch.equal(o, o2)
+
+
 def test_attention_whole_row_kernel_tail_keys_dominate(ops):
-    """S = 257..260: the keys past 256 are scored on the CUDA cores and enter max, sum and P V outside the tensor core.
-    Make exactly those keys carry the row maximum and most of the probability mass."""
-    for S in (257, 259, 260):
-        B, H = 2, 3
+    """S = 257: key 256 is scored on the CUDA cores and enters max, sum and P V outside the tensor core, and query row 256 is
+    computed entirely on the CUDA cores. Make exactly that key carry the row maximum and most of the probability mass
+    (259 / 260 keys: the same planted keys through the tiled kernels)."""
+    for S, B, H in ((257, 2, 3), (257, 30, 16), (259, 2, 3), (260, 2, 3)):
         q, k, v = rnd((B, H, S, 64), 31), rnd((B, H, S, 64), 32), rnd((B, H, S, 64), 33)
         k[:, :, 256:] = q[:, :, 5:5 + S - 256] * 1.5                 # large positive logits for some rows
         _, o = ops.attention(q, k, v, 0)
