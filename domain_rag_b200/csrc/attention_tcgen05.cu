@@ -1161,8 +1161,10 @@ struct AttnRow2Args {
     AttnArgs a;
     const __nv_bfloat16 *q, *k, *v;
     int n_items;                       // B * H
+    int stagger;                       // 1 = hold query tile 1 back by half an item (see the MMA warp)
 };
 
+template <uint32_t POLY_MASK>
 __global__ void __launch_bounds__(AttnRow2Cfg::THREADS, 1)
 attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, AttnRow2Args ar) {
@@ -1246,37 +1248,52 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             const uint32_t idesc_qk = umma_idesc_bf16(128, static_cast<uint32_t>(n_mma), 0, 0);
             constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD, 0, 1);
             const int nks = n_mma / 16;
-            for (int k = 0; k < n_my; ++k) {
-                const int s = k & 1, ph = (k >> 1) & 1, kp = k & 1;
-                const uint32_t slot = smem_u32(smem + s * Cfg::SLOT_BYTES);
-                const uint64_t kd = umma_desc_k_sw128(slot + Cfg::SLOT_K);
-                const uint64_t vd = umma_desc_mn_sw128(slot + Cfg::SLOT_V, 0, 1024);
-                mbar_wait(&qk_full[s], ph);
+            // Event-driven: each query tile is a two-state machine (Q K^T wanted / P V wanted) served as soon as its
+            // barriers allow, so the two softmax warpgroups need not run in lockstep. With ar.stagger tile 1 is held back
+            // until tile 0's first P V is issued: from then on one warpgroup computes while the other waits for the
+            // tensor core and for its barriers, instead of both doing the same thing at the same time.
+            int kx[2] = {0, 0};
+            int stage[2] = {0, 0};
+            bool b_enabled = ar.stagger == 0;
+            while (kx[0] < n_my || kx[1] < n_my) {
 #pragma unroll
                 for (int x = 0; x < 2; ++x) {
-                    const uint64_t qd = umma_desc_k_sw128(slot + Cfg::SLOT_Q + x * AT_HALF_BYTES);
-                    mbar_wait(&tmem_free[x], kp ^ 1);          // the epilogue of the previous item has read O_x
-                    tc_fence_after();
-                    if (elect_one()) {
+                    const int k = kx[x];
+                    if (k >= n_my || (x == 1 && !b_enabled)) continue;
+                    const int s = k & 1, ph = (k >> 1) & 1, kp = k & 1;
+                    const uint32_t slot = smem_u32(smem + s * Cfg::SLOT_BYTES);
+                    if (stage[x] == 0) {
+                        uint32_t ok = mbar_try_wait(&qk_full[s], ph) && mbar_try_wait(&tmem_free[x], kp ^ 1);
+                        ok = __shfl_sync(0xffffffffu, ok, 0);
+                        if (!ok) continue;
+                        tc_fence_after();
+                        const uint64_t kd = umma_desc_k_sw128(slot + Cfg::SLOT_K);
+                        const uint64_t qd = umma_desc_k_sw128(slot + Cfg::SLOT_Q + x * AT_HALF_BYTES);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < HD / 16; ++ks)
-                            tc_mma_f16(tmem_base + x * 256, qd + ((ks * 32) >> 4), kd + ((ks * 32) >> 4), idesc_qk, ks != 0);
-                        tc_commit(&s_full[x]);
+                            for (int ks = 0; ks < HD / 16; ++ks)
+                                tc_mma_f16(tmem_base + x * 256, qd + ((ks * 32) >> 4), kd + ((ks * 32) >> 4), idesc_qk, ks != 0);
+                            tc_commit(&s_full[x]);
+                        }
+                        __syncwarp();
+                        stage[x] = 1;
+                    } else {
+                        uint32_t ok = mbar_try_wait(&v_full[s], ph) && mbar_try_wait(&p_full[x], kp);
+                        ok = __shfl_sync(0xffffffffu, ok, 0);
+                        if (!ok) continue;
+                        tc_fence_after();
+                        const uint64_t vd = umma_desc_mn_sw128(slot + Cfg::SLOT_V, 0, 1024);
+                        if (elect_one()) {
+                            for (int ks = 0; ks < nks; ++ks)
+                                tc_mma_f16_ts(tmem_base + x * 256 + 128, tmem_base + x * 256 + ks * 8, vd + ((ks * 2048) >> 4),
+                                              idesc_pv, ks != 0);
+                            tc_commit(&pv_done[x]);
+                        }
+                        __syncwarp();
+                        stage[x] = 0;
+                        kx[x] = k + 1;
+                        b_enabled = true;
                     }
-                    __syncwarp();
-                }
-                mbar_wait(&v_full[s], ph);
-#pragma unroll
-                for (int x = 0; x < 2; ++x) {
-                    mbar_wait(&p_full[x], kp);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        for (int ks = 0; ks < nks; ++ks)
-                            tc_mma_f16_ts(tmem_base + x * 256 + 128, tmem_base + x * 256 + ks * 8, vd + ((ks * 2048) >> 4),
-                                          idesc_pv, ks != 0);
-                        tc_commit(&pv_done[x]);
-                    }
-                    __syncwarp();
                 }
             }
         } else if (n_tail > 0) {
@@ -1484,7 +1501,7 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                         for (int pr = 0; pr < 16; ++pr) {
                             const float2 xx = ffma2(make_float2(__uint_as_float(v[hh * 32 + 2 * pr]),
                                                                 __uint_as_float(v[hh * 32 + 2 * pr + 1])), sc2, nm2);
-                            const float2 e = ((AT_POLY_MASK >> (pr & 7)) & 1) ? ex2_poly2(xx)
+                            const float2 e = ((POLY_MASK >> (pr & 7)) & 1) ? ex2_poly2(xx)
                                                                               : make_float2(ex2_approx(xx.x), ex2_approx(xx.y));
                             if (pr & 1) sum_b = fadd2(sum_b, e);
                             else sum_a = fadd2(sum_a, e);
@@ -1568,6 +1585,8 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
 }
 
+int g_attn_row_stagger = 1;     // drag_debug_set key 13: 0 = both query tiles of the persistent kernel start together
+int g_attn_row_poly = 0;        // drag_debug_set key 14: 1 = the persistent kernel takes 2 of 8 exponentials from the FMA-pipe polynomial
 int g_attn_row_persistent = 1;  // drag_debug_set key 12: 0 = 129..260 keys take the one-tile-per-CTA whole-row kernel (A/B comparisons)
 static int launch_attention_row2(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int B, int H, int S,
                                  AttnArgs a, cudaStream_t st) {
@@ -1587,16 +1606,22 @@ static int launch_attention_row2(const __nv_bfloat16* q, const __nv_bfloat16* k,
         int dev = 0;
         DRAG_CUDA(cudaGetDevice(&dev));
         DRAG_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        DRAG_CUDA(cudaFuncSetAttribute(attention_row2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        DRAG_CUDA(cudaFuncSetAttribute(attention_row2_kernel<0u>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        DRAG_CUDA(cudaFuncSetAttribute(attention_row2_kernel<AT_POLY_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         attr_set = true;
     }
     a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
     AttnRow2Args ar;
     ar.a = a; ar.q = q; ar.k = k; ar.v = v;
     ar.n_items = static_cast<int>(bh);
+    ar.stagger = g_attn_row_stagger;
     const unsigned grid = static_cast<unsigned>(bh < static_cast<uint64_t>(sm_count) ? bh : sm_count);
     const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * H * static_cast<double>(S) * S * HD, st);
-    attention_row2_kernel<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tq, tk, tv, ar); count_launch();
+    // The softmax warps of this kernel are issue- / latency-bound, not MUFU-bound (ncu: XU pipe 28 %, issue slots 45 %): every
+    // exponential on MUFU.EX2 is fewer instructions than the polynomial mix of the head-dim-128 kernel.
+    if (g_attn_row_poly) attention_row2_kernel<AT_POLY_MASK><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tq, tk, tv, ar);
+    else attention_row2_kernel<0u><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tq, tk, tv, ar);
+    count_launch();
     DRAG_CUDA(cudaGetLastError());
     prof_end(slot, st);
     return DRAG_OK;

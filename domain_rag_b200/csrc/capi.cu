@@ -38,6 +38,8 @@ extern int g_attn_split;
 extern int g_attn_no_row;
 extern int g_attn_row_prefetch;
 extern int g_attn_row_persistent;
+extern int g_attn_row_stagger;
+extern int g_attn_row_poly;
 extern int g_gemm_no_wide_st;
 int stem_stats_any_device(const void* img, int img_kind, int B, int H, int W, const float* w_fold, const float* b_fold,
                           float eps, float* out, cudaStream_t st);
@@ -511,6 +513,8 @@ int drag_debug_set(int key, int value) {
     else if (key == 10) g_attn_no_row = value;
     else if (key == 11) g_attn_row_prefetch = value;
     else if (key == 12) g_attn_row_persistent = value;
+    else if (key == 13) g_attn_row_stagger = value;
+    else if (key == 14) g_attn_row_poly = value;
     else return fail(DRAG_ERR_INVALID, "drag_debug_set: unknown key");
     return DRAG_OK;
 }

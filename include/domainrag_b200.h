@@ -250,7 +250,8 @@ int drag_launch_count(int64_t* count, int reset);
  * the tensor-core kernel; key 9: 1 = GEMM epilogues store 16 bytes per lane instead of 32; key 10: 1 = head-dim-64
  * attention never takes the whole-row kernel, i.e. the tiled online-softmax kernels also for <= 260 keys; key 11: 0 = the whole-row kernel
  * does not prefetch the tiles of later CTAs into L2; key 12: 0 = 129..260 keys take the one-tile-per-CTA whole-row kernel
- * instead of the persistent one). */
+ * instead of the persistent one; key 13: 0 = its two query tiles start together instead of half an item apart; key 14: 1 = it
+ * takes 2 of 8 exponentials from the FMA-pipe polynomial like the head-dim-128 kernel). */
 int drag_debug_set(int key, int value);
 
 #ifdef __cplusplus

@@ -21,7 +21,14 @@ for (B, H, S, hd) in [(1, 24, 5337, 128), (4, 24, 5337, 128), (1, 24, 2265, 128)
         ops.debug_set(11, 0)
         ms_np = t_ms(lambda: ops.attention(q, k, v, 0, out1=out))
         ops.debug_set(11, 1)
-        print(f"   whole-row kernel without the L2 prefetch of later CTAs: {ms_np:.3f} ms", flush=True)
+        ops.debug_set(13, 0)
+        ms_ns = t_ms(lambda: ops.attention(q, k, v, 0, out1=out))
+        ops.debug_set(13, 1); ops.debug_set(14, 1)
+        ms_poly = t_ms(lambda: ops.attention(q, k, v, 0, out1=out))
+        ops.debug_set(14, 0); ops.debug_set(12, 0)
+        ms_row1 = t_ms(lambda: ops.attention(q, k, v, 0, out1=out))
+        ops.debug_set(12, 1)
+        print(f"   variants: no L2 prefetch (one-tile kernel) {ms_np:.3f} | persistent without stagger {ms_ns:.3f} | persistent with 2/8 poly exp2 {ms_poly:.3f} | one-tile-per-CTA whole-row kernel {ms_row1:.3f} ms", flush=True)
     ms_t = t_ms(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))
     fl = 4.0 * B * H * S * S * hd
     print(f"B={B} H={H} S={S} hd={hd}: ours {ms:.3f} ms {fl/ms/1e9:.0f} TFLOP/s (hd 64 tiled kernels: {ms_one:.3f} ms {fl/ms_one/1e9:.0f}) | torch sdpa {ms_t:.3f} ms {fl/ms_t/1e9:.0f} TFLOP/s", flush=True)
