@@ -6,6 +6,7 @@ is raised. The CPU oracle under oracle/ is test infrastructure and is never impo
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
@@ -123,6 +124,9 @@ def load() -> C.CDLL:
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    for item in filter(None, os.environ.get("DRAG_DEBUG_SET", "").split(",")):      # A/B knobs, see drag_debug_set
+        key, _, value = item.partition("=")
+        check(lib.drag_debug_set(int(key), int(value)), f"DRAG_DEBUG_SET={item}")
     return lib
 
 

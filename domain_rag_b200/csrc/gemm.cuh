@@ -56,6 +56,7 @@ struct GemmEpi {
     const float* ln_s = nullptr;          // [N] fp32
     const float* ln_c = nullptr;          // [N] fp32
     float ln_eps = 1e-5f;
+    int rcp_mufu = 0;                     // set by the launcher: QuickGELU takes its reciprocal from MUFU.RCP (drag_debug_set key 15)
     int wide_st = 0;                      // set by the launcher: 32-byte (STG.256) row stores are legal for this output
     int wide_ld = 0;                      //                      32-byte (LDG.256) loads of the residual rows
 };

@@ -140,6 +140,21 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
     return fmaf(-x, rcp_approx(e + 1.f), x);
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx(1.f + ex2_approx_f(-1.4426950408889634f * x)); }
+// QuickGELU x * sigmoid(1.702 x) = x / (1 + 2^(-1.702 log2(e) x)) with ONE MUFU op per element. The fc GEMM of a ViT block has
+// K = 1024: a 128 x 256 tile is 4096 tensor-core cycles, and two MUFU ops per output element (ex2 + rcp, 16 lanes / clock / SM)
+// are 4096 cycles as well - the epilogue could not hide behind the next tile's MMAs (ncu: tensor pipe 68 %). The reciprocal of
+// d = 1 + 2^t in [1, 2^126] therefore runs on the FMA pipe: exponent-flip seed (5 % off) and two Newton steps, relative error
+// 7e-6 - three orders below the bf16 rounding of the stored value. t is clamped so that d stays finite (x < -50: result 0).
+__device__ __forceinline__ float rcp_fma(float d) {
+    float r = __uint_as_float(0x7EF311C7u - __float_as_uint(d));
+    r = r * fmaf(-d, r, 2.f);
+    r = r * fmaf(-d, r, 2.f);
+    return r;
+}
+__device__ __forceinline__ float quick_gelu_f(float x) {
+    const float e = ex2_approx_f(fminf(-2.4554669595930157f * x, 125.f));     // 1.702 * log2(e)
+    return x * rcp_fma(1.f + e);
+}
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
@@ -234,7 +249,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, float (&v)[32],
         for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
     } else if (e.mode == EPI_QUICK_GELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = v[j] * sigmoid_f(1.702f * v[j]);
+        for (int j = 0; j < 32; ++j) {
+            const bool mufu = e.rcp_mufu == 1 || (e.rcp_mufu == 2 && (j & 3) != 3);      // 2: three of four on MUFU
+            v[j] = mufu ? v[j] * sigmoid_f(1.702f * v[j]) : quick_gelu_f(v[j]);
+        }
     } else if (e.mode == EPI_SILU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = v[j] * sigmoid_f(v[j]);
@@ -821,6 +839,10 @@ static int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 }
 
 
+// drag_debug_set key 15: QuickGELU reciprocal: 1 = MUFU.RCP (default), 0 = FMA-pipe Newton iteration, 2 = one of four on the
+// FMA pipe. MEASURED in the C2 job on one box: 0 -> 5342 images/s, 1 -> 5573: the epilogue warps are issue-bound before they
+// are MUFU-bound, and the extra FMA-pipe instructions cost more than the MUFU slots they free.
+int g_gemm_quick_gelu_mufu = 1;
 int g_gemm_no_wide_st = 0;   // drag_debug_set key 9: 1 = 16-byte epilogue stores only (A/B comparisons)
 int g_gemm_force_1cta = 0;   // drag_debug_set key 3: 1 = always use the single-CTA kernel (A/B comparisons)
 int g_gemm_group_n = 0;      // drag_debug_set key 6: > 0 = column-group raster with this many column tiles per group
@@ -845,6 +867,7 @@ static int dispatch_gemm(const __nv_bfloat16* A, const CUtensorMap* tmA_ready, i
     // (Flux MLP-up 1486 vs 1405): wide accesses only where the k loop is short.
     if (K > 2048) epi.wide_st = epi.wide_ld = 0;
     if (g_gemm_no_wide_st) epi.wide_st = epi.wide_ld = 0;
+    epi.rcp_mufu = g_gemm_quick_gelu_mufu;
     const bool pair_ok = !g_gemm_force_1cta && m_tiles > 1 && (bn == 256 || bn == 128) && N % bn == 0;
     CUtensorMap tmA, tmB;
     int rc;

@@ -26,6 +26,7 @@ for stage in "$@"; do
     scan)         run 300 scan $(launch) bench.py --gpus $N --workload scan ;;
     sweep)        run 600 sweep $(launch) bench.py --gpus $N --workload scan --sweep --steps 10 ;;
     retrieve)     run 400 retrieve $(launch) bench.py --gpus $N --workload retrieve ;;
+    retrieve_ab)  for kv in ${ABSET:-"15=1" "15=2" "15=1" "15=2"}; do DRAG_DEBUG_SET=$kv run 400 retrieve_ab_${kv}_$SECONDS $(launch) bench.py --gpus $N --workload retrieve; done ;;
     retrieve_b32) run 400 retrieve_b32 $(launch) bench.py --gpus $N --workload retrieve --clip-model ViT-B/32 ;;
     ref)          run 400 ref python bench.py --impl reference --steps 1 --warmup 0 ;;
     attn)         run 300 attn python scripts/bench_attn.py ;;
