@@ -248,10 +248,23 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, float (&v)[32],
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
     } else if (e.mode == EPI_QUICK_GELU) {
+        if (e.rcp_mufu == 3) {
+            // one MUFU.RCP for two elements: 1 / (d0 d1), then s0 = r d1, s1 = r d0 (d = 1 + 2^t, t clamped to 60 so that
+            // the product stays finite; x < -24 gives x * 2^-60 instead of x * 2^-2.46|x|: both vanish next to any other term of the next GEMM)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const bool mufu = e.rcp_mufu == 1 || (e.rcp_mufu == 2 && (j & 3) != 3);      // 2: three of four on MUFU
-            v[j] = mufu ? v[j] * sigmoid_f(1.702f * v[j]) : quick_gelu_f(v[j]);
+            for (int j = 0; j < 32; j += 2) {
+                const float d0 = 1.f + ex2_approx_f(fminf(-2.4554669595930157f * v[j], 60.f));
+                const float d1 = 1.f + ex2_approx_f(fminf(-2.4554669595930157f * v[j + 1], 60.f));
+                const float r = rcp_approx(d0 * d1);
+                v[j] = v[j] * (r * d1);
+                v[j + 1] = v[j + 1] * (r * d0);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const bool mufu = e.rcp_mufu == 1 || (e.rcp_mufu == 2 && (j & 3) != 3);      // 2: three of four on MUFU
+                v[j] = mufu ? v[j] * sigmoid_f(1.702f * v[j]) : quick_gelu_f(v[j]);
+            }
         }
     } else if (e.mode == EPI_SILU) {
 #pragma unroll

@@ -31,7 +31,7 @@ for stage in "$@"; do
     ref)          run 400 ref python bench.py --impl reference --steps 1 --warmup 0 ;;
     attn)         run 300 attn python scripts/bench_attn.py ;;
     gemm)         run 300 gemm python scripts/bench_raster2.py ;;
-    launches)     DRAG_BENCH_LAUNCH_LIST_ONLY=1 run 900 launches ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 1 --warmup 3 --no-secondary --no-gpu-baseline ;;
+    launches)     DRAG_BENCH_LAUNCH_LIST_ONLY=1 run 900 launches ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 6000 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 1 --warmup 3 --no-secondary --no-gpu-baseline ;;
     ncu_hot)      run 600 ncu_hot ncu --set full --clock-control none --import-source on -k regex:"gemm_bf16|attention_tcgen05" -s 4 -c 4 -o gpurun_out/${tag}_hot python scripts/prof_kernels.py 4 ;;
     ncu_attn)     run 400 ncu_attn ncu --set full --clock-control none --import-source on -k regex:"attention_tcgen05" -s 2 -c 2 -o gpurun_out/${tag}_attn python scripts/prof_kernels.py 4 ;;
     ncu_stem)     run 300 ncu_stem ncu --set full --clock-control none --import-source on -k regex:"stem_stats" -s 1 -c 1 -o gpurun_out/${tag}_stem python scripts/prof_stem.py ;;

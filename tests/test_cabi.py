@@ -57,6 +57,10 @@ def test_hot_kernels_are_blackwell_native_sass(lib):
         assert c["HMMA"] == 0, (name, "legacy mma.sync in a tcgen05 kernel")
     for name, c in attn.items():
         assert c["STTM"] >= 1 and c["FFMA2"] >= 32, (name, dict(c))          # P written back to TMEM; packed fp32x2 softmax
+    row = {k: c for k, c in counts.items() if "attention_row" in k}          # whole-row kernels of the CLIP ViT path
+    assert len(row) >= 2
+    for name, c in row.items():
+        assert c["UTCHMMA"] >= 2 and c["LDTM"] >= 3 and c["STTM"] >= 1 and c["UTMALDG"] >= 3 and c["HMMA"] == 0, (name, dict(c))
     pair = [c for k, c in gemm.items() if "2cta" in k]
     assert pair and all(c["UTCHMMA.2CTA"] >= 4 and c["UTCBAR.2CTA.MULTICAST"] >= 1 for c in pair)
     summary = (REPO / "profiles" / "r02_sass_summary.txt").read_text()
