@@ -259,6 +259,22 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, float (&v)[32],
                 v[j] = v[j] * (r * d1);
                 v[j + 1] = v[j + 1] * (r * d0);
             }
+        } else if (e.rcp_mufu == 4) {
+            // one MUFU.RCP for four elements (t clamped to 30)
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float d0 = 1.f + ex2_approx_f(fminf(-2.4554669595930157f * v[j], 30.f));
+                const float d1 = 1.f + ex2_approx_f(fminf(-2.4554669595930157f * v[j + 1], 30.f));
+                const float d2 = 1.f + ex2_approx_f(fminf(-2.4554669595930157f * v[j + 2], 30.f));
+                const float d3 = 1.f + ex2_approx_f(fminf(-2.4554669595930157f * v[j + 3], 30.f));
+                const float d01 = d0 * d1, d23 = d2 * d3;
+                const float r = rcp_approx(d01 * d23);
+                const float r01 = r * d23, r23 = r * d01;          // 1 / (d0 d1), 1 / (d2 d3)
+                v[j] = v[j] * (r01 * d1);
+                v[j + 1] = v[j + 1] * (r01 * d0);
+                v[j + 2] = v[j + 2] * (r23 * d3);
+                v[j + 3] = v[j + 3] * (r23 * d2);
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -852,10 +868,12 @@ static int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 }
 
 
-// drag_debug_set key 15: QuickGELU reciprocal: 1 = MUFU.RCP (default), 0 = FMA-pipe Newton iteration, 2 = one of four on the
-// FMA pipe. MEASURED in the C2 job on one box: 0 -> 5342 images/s, 1 -> 5573: the epilogue warps are issue-bound before they
-// are MUFU-bound, and the extra FMA-pipe instructions cost more than the MUFU slots they free.
-int g_gemm_quick_gelu_mufu = 1;
+// drag_debug_set key 15: QuickGELU reciprocal: 3 = one MUFU.RCP shared by two elements (default), 4 = by four, 1 = one per
+// element, 0 = FMA-pipe Newton iteration, 2 = one element of four on the FMA pipe. The fc GEMM of a ViT block (K = 1024) has a
+// 4096-cycle main loop per tile and, at two MUFU ops per element, a 4096-cycle epilogue. MEASURED in the C2 job, same box:
+// 0 -> 5342 images/s, 2 -> 5516-5535, 1 -> 5554-5573 (Newton costs more issue slots than the MUFU slots it frees); on another
+// box 1 -> 5470-5501, 3 -> 5786-5795: sharing the reciprocal removes a quarter of the MUFU work for two multiplies.
+int g_gemm_quick_gelu_mufu = 3;
 int g_gemm_no_wide_st = 0;   // drag_debug_set key 9: 1 = 16-byte epilogue stores only (A/B comparisons)
 int g_gemm_force_1cta = 0;   // drag_debug_set key 3: 1 = always use the single-CTA kernel (A/B comparisons)
 int g_gemm_group_n = 0;      // drag_debug_set key 6: > 0 = column-group raster with this many column tiles per group

@@ -251,8 +251,8 @@ int drag_launch_count(int64_t* count, int reset);
  * attention never takes the whole-row kernel, i.e. the tiled online-softmax kernels also for <= 260 keys; key 11: 0 = the whole-row kernel
  * does not prefetch the tiles of later CTAs into L2; key 12: 0 = 129..260 keys take the one-tile-per-CTA whole-row kernel
  * instead of the persistent one; key 13: 0 = its two query tiles start together instead of half an item apart; key 14: 1 = it
- * takes 2 of 8 exponentials from the FMA-pipe polynomial like the head-dim-128 kernel; key 15: QuickGELU reciprocal 1 = MUFU.RCP
- * (default), 0 = FMA-pipe Newton iteration, 2 = one element of four on the FMA pipe).
+ * takes 2 of 8 exponentials from the FMA-pipe polynomial like the head-dim-128 kernel; key 15: QuickGELU reciprocal 3 = one MUFU.RCP
+ * per two elements (default), 4 = per four, 1 = per element, 0 = FMA-pipe Newton iteration, 2 = one element of four on the FMA pipe).
  * The environment variable DRAG_DEBUG_SET="key=value,key=value" applies the same knobs when the Python binding loads the library. */
 int drag_debug_set(int key, int value);
 
