@@ -122,7 +122,7 @@ def test_c1_embed_then_top10_recall(lib):
     assert [int(r[0]) for r in I] == [0, 1, 2, 3]                 # self-retrieval first
     overlap = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(I, Io)])
     print(f"C1 recall@10 overlap vs fp32 oracle embeddings: {overlap:.3f}")
-    assert overlap >= 0.9, overlap            # measured 1.000 (profiles/r02_run11_tests_summary.txt)
+    assert overlap >= 0.9, overlap            # measured 0.975-1.000 (profiles/r02_run1[14]_tests_summary.txt)
     # exactness at the scan boundary: same GPU embeddings through the oracle scan give identical indices
     De, Ie = OT.ip_topk(emb.cpu().numpy(), emb[:4].cpu().numpy(), 10)
     np.testing.assert_array_equal(I, Ie)
