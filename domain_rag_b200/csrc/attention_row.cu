@@ -376,9 +376,11 @@ struct AttnRow2Cfg {
     static constexpr int TAIL_BYTES = 3 * AR_TAIL * 128;
     static constexpr int BAR_OFF = TAIL_OFF + 2 * TAIL_BYTES;
     static constexpr int SCRATCH_OFF = BAR_OFF + 256;              // 2 warps x 264 floats: scores / probabilities of row 256
-    static constexpr int SMEM = SCRATCH_OFF + 2 * 264 * 4 + 1024;
+    static constexpr int XCH_OFF = SCRATCH_OFF + 2 * 264 * 4;      // split form: 2 tiles x 128 rows x {max0, max1, sum0, sum1, p_tail}
+    static constexpr int SMEM = XCH_OFF + 2 * 128 * 5 * 4 + 1024;
     static constexpr int TMEM_COLS = 512;
     static constexpr int THREADS = 384;
+    static constexpr int THREADS_SPLIT = 640;                      // {TMA, MMA, 2 x row 256} + 4 x 4 softmax warps
 };
 struct AttnRow2Args {
     AttnArgs a;
@@ -387,8 +389,13 @@ struct AttnRow2Args {
     int stagger;                       // 1 = hold query tile 1 back by half an item (see the MMA warp)
 };
 
-template <uint32_t POLY_MASK>
-__global__ void __launch_bounds__(AttnRow2Cfg::THREADS, 1)
+// SPLIT: every score row is shared by TWO threads (columns [0,128) and [128,256)), 16 softmax warps instead of 8. The
+// one-thread-per-row form runs its SM sub-partitions at 45 % issue utilisation: two dependent instruction streams per
+// sub-partition cannot cover MUFU / TMEM latency, and when one warpgroup waits for the tensor core only one stream is left.
+// The halves exchange row maximum and row sum through shared memory (one 64-thread named barrier each); half 1 keeps its P in
+// its own S columns ([128,192), so it never overwrites scores half 0 still reads) and O moves to [192,256).
+template <uint32_t POLY_MASK, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? AttnRow2Cfg::THREADS_SPLIT : AttnRow2Cfg::THREADS, 1)
 attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, AttnRow2Args ar) {
     using Cfg = AttnRow2Cfg;
@@ -421,11 +428,11 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         for (int i = 0; i < 2; ++i) {
             mbar_init(&qk_full[i], 1);
             mbar_init(&v_full[i], 1);
-            mbar_init(&slot_free[i], 8 + (n_tail > 0 ? 1 : 0));     // + the warp that computes query row 256
+            mbar_init(&slot_free[i], (SPLIT ? 16 : 8) + (n_tail > 0 ? 1 : 0));     // + the warp that computes query row 256
             mbar_init(&s_full[i], 1);
-            mbar_init(&p_full[i], 4);
+            mbar_init(&p_full[i], SPLIT ? 8 : 4);
             mbar_init(&pv_done[i], 1);
-            mbar_init(&tmem_free[i], 4);
+            mbar_init(&tmem_free[i], SPLIT ? 8 : 4);
         }
         fence_mbar_init();
     }
@@ -439,7 +446,10 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        setmaxnreg_dec<104>();   // 128 x (168 - 104) released = 256 x (200 - 168) taken by the softmax warps
+        // setmaxnreg.inc can only take what .dec of the same CTA released: 384 threads launch with 168 registers, 128 x (168 -
+        // 104) released = 256 x (200 - 168) taken; 640 threads launch with 96: 128 x (96 - 64) released = 512 x (104 - 96) taken
+        if constexpr (SPLIT) setmaxnreg_dec<64>();
+        else setmaxnreg_dec<104>();
         if (warp == 0) {
             // ------------------------------------------------------------------ TMA producer, one item ahead
             for (int k = 0; k < n_my; ++k) {
@@ -507,9 +517,12 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                         tc_fence_after();
                         const uint64_t vd = umma_desc_mn_sw128(slot + Cfg::SLOT_V, 0, 1024);
                         if (elect_one()) {
-                            for (int ks = 0; ks < nks; ++ks)
-                                tc_mma_f16_ts(tmem_base + x * 256 + 128, tmem_base + x * 256 + ks * 8, vd + ((ks * 2048) >> 4),
-                                              idesc_pv, ks != 0);
+                            for (int ks = 0; ks < nks; ++ks) {
+                                // P of keys [128,256) sits at columns [128,192) in the split form, O at [192,256)
+                                const int p_col = (SPLIT && ks >= 8) ? 128 + (ks - 8) * 8 : ks * 8;
+                                tc_mma_f16_ts(tmem_base + x * 256 + (SPLIT ? 192 : 128), tmem_base + x * 256 + p_col,
+                                              vd + ((ks * 2048) >> 4), idesc_pv, ks != 0);
+                            }
                             tc_commit(&pv_done[x]);
                         }
                         __syncwarp();
@@ -535,21 +548,19 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 const uint8_t* slot = smem + s * Cfg::SLOT_BYTES;
                 const uint8_t* tail = smem + Cfg::TAIL_OFF + s * Cfg::TAIL_BYTES;
                 mbar_wait(&qk_full[s], ph);
-                float qf[HD];
-#pragma unroll
-                for (int i = 0; i < HD / 8; ++i)
-                    bf16x8_to_float(*reinterpret_cast<const uint4*>(tail + 2 * AR_TAIL * 128 + i * 16), &qf[i * 8]);
+                const uint8_t* qrow = tail + 2 * AR_TAIL * 128;       // q row 256 is re-read (broadcast) per key: no 64 live registers
                 float mx;
                 {
                     float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
                     for (int c = 0; c < HD / 8; ++c) {
-                        float kf[8];
+                        float kf[8], qf[8];
                         bf16x8_to_float(*reinterpret_cast<const uint4*>(tail + c * 16), kf);
+                        bf16x8_to_float(*reinterpret_cast<const uint4*>(qrow + c * 16), qf);
 #pragma unroll
                         for (int e = 0; e < 8; e += 2) {
-                            acc0 = fmaf(qf[c * 8 + e], kf[e], acc0);
-                            acc1 = fmaf(qf[c * 8 + e + 1], kf[e + 1], acc1);
+                            acc0 = fmaf(qf[e], kf[e], acc0);
+                            acc1 = fmaf(qf[e + 1], kf[e + 1], acc1);
                         }
                     }
                     mx = (acc0 + acc1) * a.scale_log2;          // key 256: the same on every lane
@@ -561,12 +572,13 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
                     for (int c = 0; c < HD / 8; ++c) {
-                        float kf[8];
+                        float kf[8], qf[8];
                         bf16x8_to_float(*reinterpret_cast<const uint4*>(krow + ((c ^ (lane & 7)) << 4)), kf);
+                        bf16x8_to_float(*reinterpret_cast<const uint4*>(qrow + c * 16), qf);
 #pragma unroll
                         for (int e = 0; e < 8; e += 2) {
-                            acc0 = fmaf(qf[c * 8 + e], kf[e], acc0);
-                            acc1 = fmaf(qf[c * 8 + e + 1], kf[e + 1], acc1);
+                            acc0 = fmaf(qf[e], kf[e], acc0);
+                            acc1 = fmaf(qf[e + 1], kf[e + 1], acc1);
                         }
                     }
                     const float sj = (acc0 + acc1) * a.scale_log2;
@@ -619,6 +631,164 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     ? a.out0 + (static_cast<size_t>(b) * a.split + srow) * a.ld0 + h * HD
                     : a.out1 + (static_cast<size_t>(b) * (a.S - a.split) + (srow - a.split)) * a.ld1 + h * HD;
                 *reinterpret_cast<__nv_bfloat162*>(orow + 2 * lane) = __floats2bfloat162_rn((o0 + o2) * inv, (o1 + o3) * inv);
+            }
+        }
+    } else if constexpr (SPLIT) {
+        setmaxnreg_inc<104>();
+        const int w4 = warp - 4;
+        const int x = w4 >> 3, hf = (w4 >> 2) & 1, quarter = w4 & 3;
+        const int r = quarter * 32 + lane;
+        const int srow = x * AT_TILE + r;
+        const int rows_here = min(a.S, 2 * AT_TILE);
+        const bool live = (x * AT_TILE + quarter * 32) < rows_here;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        const uint32_t t_s = t_lane + x * 256;
+        const uint32_t t_p = t_s + hf * 128;                          // this half's P: in place over its own S columns
+        const uint32_t t_o = t_s + 192 + hf * 32;                     // this half's 32 output columns
+        const int ncol = (n_main + 31) & ~31;
+        const int c_lo = hf * 128, c_hi = min(ncol, c_lo + 128);      // this thread's score columns
+        float* xch = reinterpret_cast<float*>(smem + Cfg::XCH_OFF) + (x * AT_TILE + r) * 5;   // max0 max1 sum0 sum1 p_tail
+        const int bar_id = 1 + x * 4 + quarter;                       // the two warps that share these 32 rows
+        for (int k = 0; k < n_my; ++k) {
+            const int s = k & 1, ph = (k >> 1) & 1, kp = k & 1;
+            const int bh = blockIdx.x + k * gridDim.x;
+            if (!live) {
+                mbar_wait(&s_full[x], kp);
+                if (lane == 0) mbar_arrive(&p_full[x]);
+                mbar_wait(&pv_done[x], kp);
+                if (lane == 0) {
+                    mbar_arrive(&tmem_free[x]);
+                    mbar_arrive(&slot_free[s]);
+                }
+                continue;
+            }
+            const uint8_t* slot = smem + s * Cfg::SLOT_BYTES;
+            const uint8_t* tail = smem + Cfg::TAIL_OFF + s * Cfg::TAIL_BYTES;
+            float st = -INFINITY;
+            if (n_tail > 0 && hf == 0) {                              // key 256: half 0 scores it
+                mbar_wait(&qk_full[s], ph);
+                const uint8_t* qrow = slot + Cfg::SLOT_Q + x * AT_HALF_BYTES + r * 128;
+                const uint4* kp4 = reinterpret_cast<const uint4*>(tail);
+                float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < HD / 8; ++i) {
+                    float qf[8], kf[8];
+                    bf16x8_to_float(*reinterpret_cast<const uint4*>(qrow + ((i ^ (r & 7)) << 4)), qf);
+                    bf16x8_to_float(kp4[i], kf);
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        acc0 = fmaf(qf[e], kf[e], acc0);
+                        acc1 = fmaf(qf[e + 1], kf[e + 1], acc1);
+                    }
+                }
+                st = acc0 + acc1;
+            }
+            mbar_wait(&s_full[x], kp);
+            tc_fence_after();
+            float m0 = st, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 1
+            for (int c = c_lo; c < c_hi; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_s + c, v);
+                tmem_ld_wait();
+                if (c + 32 > n_main) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c + i >= n_main) v[i] = 0xff800000u;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                    m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                    m2 = fmax3(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+                    m3 = fmax3(m3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+                }
+            }
+            const float m_mine = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            xch[hf] = m_mine;
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            const float m = fmaxf(m_mine, xch[hf ^ 1]) * a.scale_log2;
+            const float2 sc2 = splat2(a.scale_log2), nm2 = splat2(-m);
+            float2 sum_a = splat2(0.f), sum_b = splat2(0.f);
+#pragma unroll 1
+            for (int c = c_lo; c < c_hi; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_s + c, v);
+                tmem_ld_wait();
+                if (c + 32 > n_main) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c + i >= n_main) v[i] = 0xff800000u;
+                }
+                uint32_t packed[16];
+#pragma unroll
+                for (int pr = 0; pr < 16; ++pr) {
+                    const float2 xx = ffma2(make_float2(__uint_as_float(v[2 * pr]), __uint_as_float(v[2 * pr + 1])), sc2, nm2);
+                    const float2 e = ((POLY_MASK >> (pr & 7)) & 1) ? ex2_poly2(xx)
+                                                                   : make_float2(ex2_approx(xx.x), ex2_approx(xx.y));
+                    if (pr & 1) sum_b = fadd2(sum_b, e);
+                    else sum_a = fadd2(sum_a, e);
+                    packed[pr] = pack_bf16x2(e);
+                }
+                tmem_st_32x16(t_p + ((c - c_lo) >> 1), packed);
+            }
+            const float2 sum2 = fadd2(sum_a, sum_b);
+            float pt = (n_tail > 0 && hf == 0) ? ex2_approx(fmaf(st, a.scale_log2, -m)) : 0.f;
+            const float l_mine = sum2.x + sum2.y + pt;
+            xch[2 + hf] = l_mine;
+            if (hf == 0) xch[4] = pt;
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[x]);
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            const float l = l_mine + xch[2 + (hf ^ 1)];
+            if (hf == 1) pt = xch[4];
+
+            mbar_wait(&pv_done[x], kp);
+            tc_fence_after();
+            if (n_tail > 0) mbar_wait(&v_full[s], ph);
+            const float inv = 1.f / l;
+            const int b = bh / a.H, h = bh - b * a.H;
+            __nv_bfloat16* orow = ((srow < a.split)
+                ? a.out0 + (static_cast<size_t>(b) * a.split + srow) * a.ld0 + h * HD
+                : a.out1 + (static_cast<size_t>(b) * (a.S - a.split) + (srow - a.split)) * a.ld1 + h * HD) + hf * 32;
+            uint32_t ov[32];
+            tmem_ld_32x32(t_o, ov);
+            tmem_ld_wait();
+            float o[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(ov[i]);
+            if (n_tail > 0) {
+                const uint4* vp = reinterpret_cast<const uint4*>(tail + AR_TAIL * 128 + hf * 64);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float vf[8];
+                    bf16x8_to_float(vp[i], vf);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[i * 8 + e] = fmaf(pt, vf[e], o[i * 8 + e]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&tmem_free[x]);
+                mbar_arrive(&slot_free[s]);
+            }
+            if (srow < rows_here) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(o[i] * inv, o[i + 1] * inv);
+                    __nv_bfloat162 p1 = __floats2bfloat162_rn(o[i + 2] * inv, o[i + 3] * inv);
+                    __nv_bfloat162 p2 = __floats2bfloat162_rn(o[i + 4] * inv, o[i + 5] * inv);
+                    __nv_bfloat162 p3 = __floats2bfloat162_rn(o[i + 6] * inv, o[i + 7] * inv);
+                    uint4 u;
+                    u.x = *reinterpret_cast<uint32_t*>(&p0);
+                    u.y = *reinterpret_cast<uint32_t*>(&p1);
+                    u.z = *reinterpret_cast<uint32_t*>(&p2);
+                    u.w = *reinterpret_cast<uint32_t*>(&p3);
+                    *reinterpret_cast<uint4*>(orow + i) = u;
+                }
             }
         }
     } else {
@@ -810,6 +980,11 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
 int g_attn_row_stagger = 1;     // drag_debug_set key 13: 0 = both query tiles of the persistent kernel start together
 int g_attn_row_poly = 0;        // drag_debug_set key 14: 1 = the persistent kernel takes 2 of 8 exponentials from the FMA-pipe polynomial
+// drag_debug_set key 16: 1 = two softmax threads per score row in the persistent kernel (SPLIT). MEASURED at the ViT-L/14 shape:
+// 0.381 ms against 0.326 ms with one thread per row (ViT-B/16 shape: 0.198 vs 0.202) - the second negative result of this
+// kind (see attention_tcgen05_split_kernel): 16 softmax warps at 104 registers, two named barriers and an exchange through
+// shared memory per item cost more than the extra instruction streams hide. Kept for A/B; the default is one thread per row.
+int g_attn_row_split = 0;
 int g_attn_row_persistent = 1;  // drag_debug_set key 12: 0 = 129..260 keys take the one-tile-per-CTA whole-row kernel (A/B comparisons)
 static int launch_attention_row2(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int B, int H, int S,
                                  AttnArgs a, cudaStream_t st) {
@@ -829,8 +1004,9 @@ static int launch_attention_row2(const __nv_bfloat16* q, const __nv_bfloat16* k,
         int dev = 0;
         DRAG_CUDA(cudaGetDevice(&dev));
         DRAG_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        DRAG_CUDA(cudaFuncSetAttribute(attention_row2_kernel<0u>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-        DRAG_CUDA(cudaFuncSetAttribute(attention_row2_kernel<AT_POLY_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        DRAG_CUDA(cudaFuncSetAttribute(attention_row2_kernel<0u, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        DRAG_CUDA(cudaFuncSetAttribute(attention_row2_kernel<AT_POLY_MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        DRAG_CUDA(cudaFuncSetAttribute(attention_row2_kernel<0u, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         attr_set = true;
     }
     a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
@@ -842,8 +1018,9 @@ static int launch_attention_row2(const __nv_bfloat16* q, const __nv_bfloat16* k,
     const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * H * static_cast<double>(S) * S * HD, st);
     // The softmax warps of this kernel are issue- / latency-bound, not MUFU-bound (ncu: XU pipe 28 %, issue slots 45 %): every
     // exponential on MUFU.EX2 is fewer instructions than the polynomial mix of the head-dim-128 kernel.
-    if (g_attn_row_poly) attention_row2_kernel<AT_POLY_MASK><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tq, tk, tv, ar);
-    else attention_row2_kernel<0u><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tq, tk, tv, ar);
+    if (g_attn_row_split) attention_row2_kernel<0u, true><<<grid, Cfg::THREADS_SPLIT, Cfg::SMEM, st>>>(tq, tk, tv, ar);
+    else if (g_attn_row_poly) attention_row2_kernel<AT_POLY_MASK, false><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tq, tk, tv, ar);
+    else attention_row2_kernel<0u, false><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tq, tk, tv, ar);
     count_launch();
     DRAG_CUDA(cudaGetLastError());
     prof_end(slot, st);

@@ -64,19 +64,26 @@ def test_attention_head_dim_64_all_variants(ops, B, H, S, variant):
     assert (got.float() - ref).abs().max().item() < 2e-2
 
 
-@pytest.mark.parametrize("S", [129, 197, 256, 257])
-def test_attention_head_dim_64_persistent_kernel_many_items(ops, S):
+@pytest.mark.parametrize("split_rows", [1, 0])
+@pytest.mark.parametrize("S", [129, 140, 197, 256, 257])
+def test_attention_head_dim_64_persistent_kernel_many_items(ops, S, split_rows):
     """129..257 keys run the persistent whole-row kernel: one CTA per SM walks several (batch, head) items through two
-    shared-memory slots and the two TMEM halves, so the barrier phases wrap around. 47 x 16 = 752 items = 5-6 per CTA."""
+    shared-memory slots and the two TMEM halves, so the barrier phases wrap around. 47 x 16 = 752 items = 5-6 per CTA.
+    split_rows = 0 (default): one softmax thread per score row; 1 (drag_debug_set(16, 1)): two, exchanging maximum and sum."""
     B, H = 47, 16
     q, k, v = rnd((B, H, S, 64), 41), rnd((B, H, S, 64), 42), rnd((B, H, S, 64), 43)
-    _, o = ops.attention(q, k, v, 0)
+    ops.debug_set(16, split_rows)
+    try:
+        _, o = ops.attention(q, k, v, 0)
+        _, o2 = ops.attention(q, k, v, 0)                  # deterministic: no atomics, fixed item -> CTA mapping
+        torch.cuda.synchronize()
+    finally:
+        ops.debug_set(16, 0)
     ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
     ref = ref.permute(0, 2, 1, 3).reshape(B, S, H * 64)
     got = o.view(B, S, -1)
     assert rel_l2(got, ref) < 1e-2
     assert (got.float() - ref).abs().max().item() < 2e-2
-    _, o2 = ops.attention(q, k, v, 0)                      # deterministic: no atomics, fixed item -> CTA mapping
     assert torch.equal(o, o2)
 
 

@@ -115,3 +115,34 @@ def test_full_depth_fill_trajectory_and_image(full_model):
     assert stats["fp32"][2] <= max(1.0, 1.5 * float(dref.mean())), (stats, float(dref.mean()))
     # against the bf16 torch-eager leg two independent bf16 roundings meet: bounded by the sum of both distances to the oracle
     assert stats["bf16"][1] <= stats["fp32"][1] + floor and stats["bf16"][3] <= 6, (stats, floor)
+
+
+def test_c3_shape_batch8_forward_matches_fp32_oracle(lib):
+    """BASELINE config C3 as a SHAPE: batch 8 at 512^2 (S = 1241 + 1024 = 2265 tokens, M = 18 120 rows through every GEMM,
+    attention at B = 8, H = 24, S = 2265) at full width with 3 double + 3 single blocks, against the fp32 oracle on the GPU
+    (TF32 off) and next to the bf16 torch-eager path. `bench.py --workload c3` times the same shape at full depth."""
+    from domain_rag_b200 import flux as F
+    kw = dict(in_channels=384, n_double=3, n_single=3)
+    cfg, ocfg = F.FluxConfig(**kw), OF.FluxConfig(**kw)
+    params = F.init_params_device(cfg, seed=3100, device="cuda")
+    B, h2 = 8, 32
+    tr = F.FluxTransformer(cfg, params, max_batch=B, max_img_tokens=h2 * h2, txt_tokens=S_TXT)
+    x, ctx, pooled = rnd((B, h2 * h2, 384), 51), rnd((B, S_TXT, 4096), 52, 0.3), rnd((B, 768), 53)
+    t = torch.linspace(0.95, 0.15, B, device="cuda")
+    gd = torch.full((B,), 30.0, device="cuda")
+    ids = torch.cat([torch.zeros(S_TXT, 3), F.image_ids(h2, h2)], 0)
+    cos, sin = (a.cuda() for a in F.rope_tables(ids))
+    ours = tr.forward(x, ctx, pooled, t, gd, cos, sin).clone()
+    torch.cuda.synchronize()
+    ref16 = TR.flux_forward(params, ocfg, x, ctx, pooled, t, gd, h2, h2, torch.bfloat16)
+    ref32 = torch.cat([TR.flux_forward(params, ocfg, x[b:b + 1], ctx[b:b + 1], pooled[b:b + 1], t[b:b + 1], gd[b:b + 1],
+                                       h2, h2, torch.float32) for b in range(B)])
+    e_ours, e_ref = rel_l2(ours, ref32), rel_l2(ref16, ref32)
+    print(f"\nC3 shape (B=8, S=2265, 3+3 blocks): rel-L2 ours vs fp32 oracle {e_ours:.3e} | bf16 torch-eager vs fp32 oracle {e_ref:.3e}")
+    assert torch.isfinite(ours.float()).all()
+    assert e_ours <= 1e-2, e_ours                     # reduced depth: the SURVEY 8c bar for a shallow forward
+    assert e_ours <= 1.25 * e_ref + 1e-3, (e_ours, e_ref)
+    for b in range(B):                                # no cross-talk between the eight compositions of a batch
+        assert rel_l2(ours[b], ref32[b]) <= 1.5e-2, b
+    del tr, params
+    torch.cuda.empty_cache()
