@@ -387,6 +387,7 @@ struct AttnRow2Args {
     const __nv_bfloat16 *q, *k, *v;
     int n_items;                       // B * H
     int stagger;                       // 1 = hold query tile 1 back by half an item (see the MMA warp)
+    int pair;                          // 1 (S <= 128): an item is TWO heads, tile x = head 2 * item + x with its own Q / K / V
 };
 
 // SPLIT: every score row is shared by TWO threads (columns [0,128) and [128,256)), 16 softmax warps instead of 8. The
@@ -419,7 +420,11 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int n_tail = a.S - n_main;
     const int n_mma = (n_main + 15) & ~15;
     const int k_boxes = (n_main + AT_TILE - 1) / AT_TILE;
-    const int n_my = (ar.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    // S <= 128 (ViT-B/32: 50 tokens): one 128-row tile per head, so an item is a PAIR of heads - tile x works on head
+    // 2 * item + x with its own Q / K / V boxes in the same slot layout (Q_x, K box x, V box x); nothing is shared.
+    const bool pair = ar.pair != 0;
+    const int n_work = pair ? (ar.n_items + 1) / 2 : ar.n_items;
+    const int n_my = (n_work - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmQ);
@@ -458,7 +463,19 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 uint8_t* slot = smem + s * Cfg::SLOT_BYTES;
                 uint8_t* tail = smem + Cfg::TAIL_OFF + s * Cfg::TAIL_BYTES;
                 mbar_wait(&slot_free[s], ((k >> 1) & 1) ^ 1);
-                if (elect_one()) {
+                if (pair) {
+                    if (elect_one()) {
+                        const int n_heads = (2 * bh + 1 < ar.n_items) ? 2 : 1;
+                        mbar_arrive_expect_tx(&qk_full[s], 2 * n_heads * AT_HALF_BYTES);
+                        for (int x = 0; x < n_heads; ++x) {
+                            tma_load_3d(slot + Cfg::SLOT_Q + x * AT_HALF_BYTES, &tmQ, 0, 0, 2 * bh + x, &qk_full[s]);
+                            tma_load_3d(slot + Cfg::SLOT_K + x * AT_HALF_BYTES, &tmK, 0, 0, 2 * bh + x, &qk_full[s]);
+                        }
+                        mbar_arrive_expect_tx(&v_full[s], n_heads * AT_HALF_BYTES);
+                        for (int x = 0; x < n_heads; ++x)
+                            tma_load_3d(slot + Cfg::SLOT_V + x * AT_HALF_BYTES, &tmV, 0, 0, 2 * bh + x, &v_full[s]);
+                    }
+                } else if (elect_one()) {
                     const size_t tail_off = (static_cast<size_t>(bh) * a.S + n_main) * HD;
                     mbar_arrive_expect_tx(&qk_full[s], (2 + k_boxes) * AT_HALF_BYTES + 2 * n_tail * 128);
                     tma_load_3d(slot + Cfg::SLOT_Q, &tmQ, 0, 0, bh, &qk_full[s]);
@@ -500,7 +517,7 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                         ok = __shfl_sync(0xffffffffu, ok, 0);
                         if (!ok) continue;
                         tc_fence_after();
-                        const uint64_t kd = umma_desc_k_sw128(slot + Cfg::SLOT_K);
+                        const uint64_t kd = umma_desc_k_sw128(slot + Cfg::SLOT_K + (pair ? x * AT_HALF_BYTES : 0));
                         const uint64_t qd = umma_desc_k_sw128(slot + Cfg::SLOT_Q + x * AT_HALF_BYTES);
                         if (elect_one()) {
 #pragma unroll
@@ -515,7 +532,7 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                         ok = __shfl_sync(0xffffffffu, ok, 0);
                         if (!ok) continue;
                         tc_fence_after();
-                        const uint64_t vd = umma_desc_mn_sw128(slot + Cfg::SLOT_V, 0, 1024);
+                        const uint64_t vd = umma_desc_mn_sw128(slot + Cfg::SLOT_V + (pair ? x * AT_HALF_BYTES : 0), 0, 1024);
                         if (elect_one()) {
                             for (int ks = 0; ks < nks; ++ks) {
                                 // P of keys [128,256) sits at columns [128,192) in the split form, O at [192,256)
@@ -638,9 +655,9 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const int w4 = warp - 4;
         const int x = w4 >> 3, hf = (w4 >> 2) & 1, quarter = w4 & 3;
         const int r = quarter * 32 + lane;
-        const int srow = x * AT_TILE + r;
-        const int rows_here = min(a.S, 2 * AT_TILE);
-        const bool live = (x * AT_TILE + quarter * 32) < rows_here;
+        const int srow = pair ? r : x * AT_TILE + r;
+        const int rows_here = pair ? a.S : min(a.S, 2 * AT_TILE);
+        const bool live = (pair ? quarter * 32 : x * AT_TILE + quarter * 32) < rows_here;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         const uint32_t t_s = t_lane + x * 256;
         const uint32_t t_p = t_s + hf * 128;                          // this half's P: in place over its own S columns
@@ -651,8 +668,9 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const int bar_id = 1 + x * 4 + quarter;                       // the two warps that share these 32 rows
         for (int k = 0; k < n_my; ++k) {
             const int s = k & 1, ph = (k >> 1) & 1, kp = k & 1;
-            const int bh = blockIdx.x + k * gridDim.x;
-            if (!live) {
+            const int it = blockIdx.x + k * gridDim.x;
+            const int bh = pair ? 2 * it + x : it;                    // (batch, head) of this tile
+            if (!live || bh >= ar.n_items) {                          // (an odd head count leaves tile 1 of the last item empty)
                 mbar_wait(&s_full[x], kp);
                 if (lane == 0) mbar_arrive(&p_full[x]);
                 mbar_wait(&pv_done[x], kp);
@@ -796,17 +814,18 @@ attention_row2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const int x = (warp >= 8) ? 1 : 0;
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;
-        const int srow = x * AT_TILE + r;
-        const int rows_here = min(a.S, 2 * AT_TILE);                  // query rows this kernel covers
-        const bool live = (x * AT_TILE + quarter * 32) < rows_here;
+        const int srow = pair ? r : x * AT_TILE + r;                  // pair mode: tile x is its own head, rows 0..S-1
+        const int rows_here = pair ? a.S : min(a.S, 2 * AT_TILE);     // query rows this kernel covers
+        const bool live = (pair ? quarter * 32 : x * AT_TILE + quarter * 32) < rows_here;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         const uint32_t t_s = t_lane + x * 256;
         const uint32_t t_o = t_s + 128;
         const int ncol = (n_main + 31) & ~31;
         for (int k = 0; k < n_my; ++k) {
             const int s = k & 1, ph = (k >> 1) & 1, kp = k & 1;
-            const int bh = blockIdx.x + k * gridDim.x;
-            if (!live) {
+            const int it = blockIdx.x + k * gridDim.x;
+            const int bh = pair ? 2 * it + x : it;                    // (batch, head) of this tile
+            if (!live || bh >= ar.n_items) {                          // (an odd head count leaves tile 1 of the last item empty)
                 // no live query row in this warp: keep the barrier phases moving, in step with the MMA warp
                 mbar_wait(&s_full[x], kp);
                 if (lane == 0) mbar_arrive(&p_full[x]);
@@ -985,9 +1004,11 @@ int g_attn_row_poly = 0;        // drag_debug_set key 14: 1 = the persistent ker
 // kind (see attention_tcgen05_split_kernel): 16 softmax warps at 104 registers, two named barriers and an exchange through
 // shared memory per item cost more than the extra instruction streams hide. Kept for A/B; the default is one thread per row.
 int g_attn_row_split = 0;
+int g_attn_row_pair = 1;        // drag_debug_set key 17: 0 = up to 128 keys take the one-tile-per-CTA kernel instead of the persistent
+                                // kernel in pair mode (two heads per item)
 int g_attn_row_persistent = 1;  // drag_debug_set key 12: 0 = 129..260 keys take the one-tile-per-CTA whole-row kernel (A/B comparisons)
 static int launch_attention_row2(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int B, int H, int S,
-                                 AttnArgs a, cudaStream_t st) {
+                                 AttnArgs a, bool pair, cudaStream_t st) {
     using Cfg = AttnRow2Cfg;
     constexpr int HD = 64;
     CUtensorMap tq, tk, tv;
@@ -1014,7 +1035,9 @@ static int launch_attention_row2(const __nv_bfloat16* q, const __nv_bfloat16* k,
     ar.a = a; ar.q = q; ar.k = k; ar.v = v;
     ar.n_items = static_cast<int>(bh);
     ar.stagger = g_attn_row_stagger;
-    const unsigned grid = static_cast<unsigned>(bh < static_cast<uint64_t>(sm_count) ? bh : sm_count);
+    ar.pair = pair ? 1 : 0;
+    const uint64_t n_work = pair ? (bh + 1) / 2 : bh;
+    const unsigned grid = static_cast<unsigned>(n_work < static_cast<uint64_t>(sm_count) ? n_work : sm_count);
     const int slot = prof_begin(PROF_ATTENTION, 4.0 * B * H * static_cast<double>(S) * S * HD, st);
     // The softmax warps of this kernel are issue- / latency-bound, not MUFU-bound (ncu: XU pipe 28 %, issue slots 45 %): every
     // exponential on MUFU.EX2 is fewer instructions than the polynomial mix of the head-dim-128 kernel.
@@ -1031,7 +1054,8 @@ bool attention_row_eligible(int head_dim, int S) { return head_dim == 64 && S <=
 
 int launch_attention_row_any(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int B, int H, int S,
                              AttnArgs a, cudaStream_t st) {
-    if (S > AT_TILE && g_attn_row_persistent) return launch_attention_row2(q, k, v, B, H, S, a, st);
+    if (S > AT_TILE && g_attn_row_persistent) return launch_attention_row2(q, k, v, B, H, S, a, false, st);
+    if (S <= AT_TILE && g_attn_row_persistent && g_attn_row_pair) return launch_attention_row2(q, k, v, B, H, S, a, true, st);
     return launch_attention_row(q, k, v, B, H, S, a, st);
 }
 

@@ -41,6 +41,7 @@ extern int g_attn_row_persistent;
 extern int g_attn_row_stagger;
 extern int g_attn_row_poly;
 extern int g_attn_row_split;
+extern int g_attn_row_pair;
 extern int g_gemm_no_wide_st;
 extern int g_gemm_quick_gelu_mufu;
 int stem_stats_any_device(const void* img, int img_kind, int B, int H, int W, const float* w_fold, const float* b_fold,
@@ -519,6 +520,7 @@ int drag_debug_set(int key, int value) {
     else if (key == 14) g_attn_row_poly = value;
     else if (key == 15) g_gemm_quick_gelu_mufu = value;
     else if (key == 16) g_attn_row_split = value;
+    else if (key == 17) g_attn_row_pair = value;
     else return fail(DRAG_ERR_INVALID, "drag_debug_set: unknown key");
     return DRAG_OK;
 }

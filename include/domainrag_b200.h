@@ -253,7 +253,8 @@ int drag_launch_count(int64_t* count, int reset);
  * instead of the persistent one; key 13: 0 = its two query tiles start together instead of half an item apart; key 14: 1 = it
  * takes 2 of 8 exponentials from the FMA-pipe polynomial like the head-dim-128 kernel; key 15: QuickGELU reciprocal 3 = one MUFU.RCP
  * per two elements (default), 4 = per four, 1 = per element, 0 = FMA-pipe Newton iteration, 2 = one element of four on the FMA pipe; key 16: 1 = the
- * persistent head-dim-64 attention kernel shares every score row between two softmax threads - measured slower).
+ * persistent head-dim-64 attention kernel shares every score row between two softmax threads - measured slower; key 17: 0 = up to 128 keys take
+ * the one-tile-per-CTA whole-row kernel instead of the persistent kernel with two heads per item).
  * The environment variable DRAG_DEBUG_SET="key=value,key=value" applies the same knobs when the Python binding loads the library. */
 int drag_debug_set(int key, int value);
 

@@ -29,9 +29,9 @@ for (B, H, S, hd) in [(1, 24, 5337, 128), (4, 24, 5337, 128), (1, 24, 2265, 128)
         ms_two = t_ms(lambda: ops.attention(q, k, v, 0, out1=out))
         ops.debug_set(16, 0)
         print(f"   persistent, two softmax threads per row: {ms_two:.3f} ms", flush=True)
-        ops.debug_set(12, 0)
+        ops.debug_set(12, 0); ops.debug_set(17, 0)
         ms_row1 = t_ms(lambda: ops.attention(q, k, v, 0, out1=out))
-        ops.debug_set(12, 1)
+        ops.debug_set(12, 1); ops.debug_set(17, 1)
         print(f"   variants: no L2 prefetch (one-tile kernel) {ms_np:.3f} | persistent without stagger {ms_ns:.3f} | persistent with 2/8 poly exp2 {ms_poly:.3f} | one-tile-per-CTA whole-row kernel {ms_row1:.3f} ms", flush=True)
     ms_t = t_ms(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))
     fl = 4.0 * B * H * S * S * hd

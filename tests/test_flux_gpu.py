@@ -39,24 +39,25 @@ def test_attention_matches_sdpa(ops, B, H, S, split):
         assert (got.float() - ref[:, split:]).abs().max().item() < 2e-2
 
 
-@pytest.mark.parametrize("variant", ["default", "force_pp", "no_row"])
+@pytest.mark.parametrize("variant", ["default", "force_pp", "no_row", "no_pair"])
 @pytest.mark.parametrize("B,H,S", [(3, 4, 50), (2, 16, 257), (1, 12, 197), (2, 2, 128), (1, 3, 512), (1, 2, 700), (2, 3, 1),
                                    (1, 2, 17), (2, 2, 256), (1, 5, 258), (2, 2, 260), (1, 2, 261)])
 def test_attention_head_dim_64_all_variants(ops, B, H, S, variant):
     """CLIP ViT shapes. Default: up to 257 keys take the whole-row kernels (one Q K^T, exact two-pass softmax, one P V; keys
     past 256 on the CUDA cores), longer sequences the tiled online-softmax kernels (single-tile CTAs up to 512 keys, the
-    two-tile ping-pong beyond). drag_debug_set(5, 1) forces the ping-pong, (10, 1) the tiled kernels for every length. All
-    must agree with fp32 SDPA."""
+    two-tile ping-pong beyond). drag_debug_set(5, 1) forces the ping-pong, (10, 1) the tiled kernels for every length,
+    (17, 0) the one-tile-per-CTA whole-row kernel for <= 128 keys (default there: persistent, two heads per item). All must
+    agree with fp32 SDPA."""
     q, k, v = rnd((B, H, S, 64), 21), rnd((B, H, S, 64), 22), rnd((B, H, S, 64), 23)
-    key = {"default": None, "force_pp": 5, "no_row": 10}[variant]
+    key, on, off = {"default": (None, 0, 0), "force_pp": (5, 1, 0), "no_row": (10, 1, 0), "no_pair": (17, 0, 1)}[variant]
     if key is not None:
-        ops.debug_set(key, 1)
+        ops.debug_set(key, on)
     try:
         _, o = ops.attention(q, k, v, 0)
         torch.cuda.synchronize()
     finally:
         if key is not None:
-            ops.debug_set(key, 0)
+            ops.debug_set(key, off)
     ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
     ref = ref.permute(0, 2, 1, 3).reshape(B, S, H * 64)
     got = o.view(B, S, -1)
@@ -79,6 +80,23 @@ def test_attention_head_dim_64_persistent_kernel_many_items(ops, S, split_rows):
         torch.cuda.synchronize()
     finally:
         ops.debug_set(16, 0)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    ref = ref.permute(0, 2, 1, 3).reshape(B, S, H * 64)
+    got = o.view(B, S, -1)
+    assert rel_l2(got, ref) < 1e-2
+    assert (got.float() - ref).abs().max().item() < 2e-2
+    assert torch.equal(o, o2)
+
+
+@pytest.mark.parametrize("B,H,S", [(47, 13, 50), (40, 12, 128), (301, 1, 50), (9, 12, 1), (33, 12, 77)])
+def test_attention_head_dim_64_pair_mode_many_items(ops, B, H, S):
+    """<= 128 keys (ViT-B/32: 50 tokens): the persistent kernel takes TWO heads per item, one per query tile, each with its
+    own Q / K / V. Odd head counts (47 x 13 = 611, 301) leave the second tile of the last item empty; several items per
+    CTA wrap the barrier phases."""
+    q, k, v = rnd((B, H, S, 64), 61), rnd((B, H, S, 64), 62), rnd((B, H, S, 64), 63)
+    _, o = ops.attention(q, k, v, 0)
+    _, o2 = ops.attention(q, k, v, 0)
+    torch.cuda.synchronize()
     ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
     ref = ref.permute(0, 2, 1, 3).reshape(B, S, H * 64)
     got = o.view(B, S, -1)
