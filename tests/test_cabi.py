@@ -81,3 +81,17 @@ def test_product_package_never_imports_oracle():
     for p in (REPO / "domain_rag_b200").rglob("*.py"):
         src = p.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), p
+
+
+def test_debug_set_environment_hook():
+    """DRAG_DEBUG_SET="key=value,..." applies drag_debug_set knobs when the binding loads the library (same-box A/B runs of
+    bench.py); an unknown key fails loudly instead of being ignored."""
+    import subprocess
+    import sys
+    code = "from domain_rag_b200 import _lib; _lib.load(); print('loaded')"
+    ok = subprocess.run([sys.executable, "-c", code], cwd=str(REPO), capture_output=True, text=True,
+                        env={**__import__("os").environ, "DRAG_DEBUG_SET": "13=1,15=3"})
+    assert ok.returncode == 0 and "loaded" in ok.stdout, ok.stderr[-400:]
+    bad = subprocess.run([sys.executable, "-c", code], cwd=str(REPO), capture_output=True, text=True,
+                         env={**__import__("os").environ, "DRAG_DEBUG_SET": "999=1"})
+    assert bad.returncode != 0 and "unknown key" in bad.stderr
