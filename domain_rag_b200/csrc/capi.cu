@@ -44,6 +44,7 @@ extern int g_attn_row_split;
 extern int g_attn_row_pair;
 extern int g_gemm_no_wide_st;
 extern int g_gemm_quick_gelu_mufu;
+extern int g_gemm_resid_prefetch;
 int stem_stats_any_device(const void* img, int img_kind, int B, int H, int W, const float* w_fold, const float* b_fold,
                           float eps, float* out, cudaStream_t st);
 extern int g_gemm_group_n;
@@ -521,6 +522,7 @@ int drag_debug_set(int key, int value) {
     else if (key == 15) g_gemm_quick_gelu_mufu = value;
     else if (key == 16) g_attn_row_split = value;
     else if (key == 17) g_attn_row_pair = value;
+    else if (key == 18) g_gemm_resid_prefetch = value;
     else return fail(DRAG_ERR_INVALID, "drag_debug_set: unknown key");
     return DRAG_OK;
 }

@@ -364,9 +364,89 @@ __device__ __forceinline__ void ln_row_moments(const GemmEpi& epi, int row, bool
     ln_rstd = rsqrtf(fmaxf(s2 * inv_k - ln_mean * ln_mean, 0.f) + epi.ln_eps);
 }
 
-template <int BN>
+// RPRE: the instantiation for the residual epilogue of the short-K GEMMs (ViT out-projection / MLP-down: K <= 2048, a main
+// loop of 4096 cycles per tile at K = 1024). Loading the residual where it is used makes that epilogue a chain of BN / 64
+// dependent global round trips per tile - longer than the main loop it has to hide behind (ncu: tensor pipe 57 % on the
+// out-projection). Here every 32-byte load of this thread's row segment is issued up front, before the first TMEM read, and
+// bias + residual (+ gate) is the only epilogue compiled in, which is what makes room for the 16 x BN / 64 extra registers
+// (the same prefetch inside the generic epilogue spilled 184-330 bytes in every instantiation, the Flux ones included).
+template <int BN, bool RPRE = false>
 __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, const GemmShape& sh, uint32_t t_addr, int row,
                                               bool row_ok, int n_blk, int half, float ln_mean, float ln_rstd) {
+    if constexpr (RPRE) {
+        constexpr int NC = BN / 64;
+        const int c0 = half * (BN / 2);
+        const int colbase = n_blk * BN + c0;
+        uint32_t rp[NC][16];
+        if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                if (colbase + i * 32 < sh.N) {
+                    const __nv_bfloat16* src = epi.resid + static_cast<size_t>(row) * epi.ldr + colbase + i * 32;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh)
+                        asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                     : "=r"(rp[i][hh * 8 + 0]), "=r"(rp[i][hh * 8 + 1]), "=r"(rp[i][hh * 8 + 2]),
+                                       "=r"(rp[i][hh * 8 + 3]), "=r"(rp[i][hh * 8 + 4]), "=r"(rp[i][hh * 8 + 5]),
+                                       "=r"(rp[i][hh * 8 + 6]), "=r"(rp[i][hh * 8 + 7])
+                                     : "l"(src + hh * 16)
+                                     : "memory");
+                }
+            }
+        }
+        float st_sum = 0.f, st_sq = 0.f;
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(t_addr + c0, ra);
+        const int b = row / epi.rows_per_batch;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            tmem_ld_wait();
+            uint32_t (&cur)[32] = (i & 1) ? rb : ra;
+            uint32_t (&nxt)[32] = (i & 1) ? ra : rb;
+            if (i + 1 < NC) tmem_ld_32x32(t_addr + c0 + (i + 1) * 32, nxt);
+            const int col0 = colbase + i * 32;
+            if (row_ok && col0 < sh.N) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]);
+                if (epi.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float bb[8];
+                        load_bf16x8(epi.bias + col0 + j, bb);
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) v[j + t] += bb[t];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float g[8];
+                    if (epi.gate) load_bf16x8(epi.gate + static_cast<size_t>(b) * epi.gate_ld + col0 + j, g);
+#pragma unroll
+                    for (int t = 0; t < 8; t += 2) {
+                        const float2 r2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rp[i][(j + t) >> 1]));
+                        v[j + t] = epi.gate ? r2.x + g[t] * bf16_round(v[j + t]) : r2.x + bf16_round(v[j + t]);
+                        v[j + t + 1] = epi.gate ? r2.y + g[t + 1] * bf16_round(v[j + t + 1]) : r2.y + bf16_round(v[j + t + 1]);
+                    }
+                }
+                store_row32(epi.out + static_cast<size_t>(row) * epi.ldo + col0, v, true);
+                if (epi.stats_out) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float r = bf16_round(v[j]);
+                        st_sum += r;
+                        st_sq = fmaf(r, r, st_sq);
+                    }
+                }
+            }
+        }
+        if (epi.stats_out && row_ok && colbase < sh.N) {
+            const int part = colbase / (BN / 2);
+            *reinterpret_cast<float2*>(epi.stats_out + (static_cast<size_t>(row) * epi.stats_parts + part) * 2) =
+                make_float2(st_sum, st_sq);
+        }
+        return;
+    }
     if (epi.mode == EPI_QKV_ROPE) {
         // BN covers BN/128 whole heads (one per warp group at BN = 256); columns [0,H*128) q, [H*128,2H*128) k, rest v.
         // The whole 128-wide head row lives in registers: one TMEM pass for sum of squares, RMSNorm, RoPE and store.
@@ -629,7 +709,7 @@ struct Gemm2Cfg {
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
-template <int BN>
+template <int BN, bool RPRE = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                               GemmShape sh, GemmEpi epi) {
@@ -750,7 +830,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             mbar_wait_cluster(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-            epilogue_tile<BN>(epi, sh, t_addr, base + r_in, r_in < count, n_blk, (warp - G_EPI_WARP0) >> 2, ln_mean, ln_rstd);
+            epilogue_tile<BN, RPRE>(epi, sh, t_addr, base + r_in, r_in < count, n_blk, (warp - G_EPI_WARP0) >> 2, ln_mean, ln_rstd);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
@@ -847,13 +927,13 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 }
 
 
-template <int BN>
+template <int BN, bool RPRE = false>
 static int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& sh, const GemmEpi& epi,
                             cudaStream_t st) {
     using Cfg = Gemm2Cfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        DRAG_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        DRAG_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<BN, RPRE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM));
         attr_set = true;
     }
@@ -862,7 +942,7 @@ static int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     const int pairs_max = sms / 2;
     const int tiles = sh.num_m * sh.num_n;
     const int pairs = tiles < pairs_max ? tiles : pairs_max;
-    gemm_bf16_tcgen05_2cta_kernel<BN><<<2 * pairs, G_THREADS, Cfg::SMEM, st>>>(tmA, tmB, sh, epi); count_launch();
+    gemm_bf16_tcgen05_2cta_kernel<BN, RPRE><<<2 * pairs, G_THREADS, Cfg::SMEM, st>>>(tmA, tmB, sh, epi); count_launch();
     DRAG_CUDA(cudaGetLastError());
     return DRAG_OK;
 }
@@ -874,6 +954,7 @@ static int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 // 0 -> 5342 images/s, 2 -> 5516-5535, 1 -> 5554-5573 (Newton costs more issue slots than the MUFU slots it frees); on another
 // box 1 -> 5470-5501, 3 -> 5786-5795: sharing the reciprocal removes a quarter of the MUFU work for two multiplies.
 int g_gemm_quick_gelu_mufu = 3;
+int g_gemm_resid_prefetch = 1;    // drag_debug_set key 18: 0 = the short-K residual GEMMs use the generic epilogue (A/B comparisons)
 int g_gemm_no_wide_st = 0;   // drag_debug_set key 9: 1 = 16-byte epilogue stores only (A/B comparisons)
 int g_gemm_force_1cta = 0;   // drag_debug_set key 3: 1 = always use the single-CTA kernel (A/B comparisons)
 int g_gemm_group_n = 0;      // drag_debug_set key 6: > 0 = column-group raster with this many column tiles per group
@@ -930,7 +1011,10 @@ static int dispatch_gemm(const __nv_bfloat16* A, const CUtensorMap* tmA_ready, i
         sh.num_m = ceil_div(m_tiles, 2);
         sh.num_n = N / bn;
         if ((rc = make_tmap_bf16_2d(&tmB, W, N, K, ldw, bn / 2))) return rc;
-        rc = (bn == 256) ? launch_gemm_2cta<256>(tmA, tmB, sh, epi, st) : launch_gemm_2cta<128>(tmA, tmB, sh, epi, st);
+        const bool rpre = bn == 256 && epi.mode == EPI_GATE_RESID && epi.wide_ld && epi.wide_st && !epi.ln_stats &&
+                          g_gemm_resid_prefetch;      // (wide accesses are only granted for K <= 2048, see above)
+        rc = rpre ? launch_gemm_2cta<256, true>(tmA, tmB, sh, epi, st)
+                  : (bn == 256) ? launch_gemm_2cta<256>(tmA, tmB, sh, epi, st) : launch_gemm_2cta<128>(tmA, tmB, sh, epi, st);
     } else {
         sh.num_m = m_tiles;
         sh.num_n = ceil_div(N, bn);

@@ -254,7 +254,8 @@ int drag_launch_count(int64_t* count, int reset);
  * takes 2 of 8 exponentials from the FMA-pipe polynomial like the head-dim-128 kernel; key 15: QuickGELU reciprocal 3 = one MUFU.RCP
  * per two elements (default), 4 = per four, 1 = per element, 0 = FMA-pipe Newton iteration, 2 = one element of four on the FMA pipe; key 16: 1 = the
  * persistent head-dim-64 attention kernel shares every score row between two softmax threads - measured slower; key 17: 0 = up to 128 keys take
- * the one-tile-per-CTA whole-row kernel instead of the persistent kernel with two heads per item).
+ * the one-tile-per-CTA whole-row kernel instead of the persistent kernel with two heads per item; key 18: 0 = the residual
+ * GEMMs with K <= 2048 use the generic epilogue instead of the instantiation that requests the residual rows up front).
  * The environment variable DRAG_DEBUG_SET="key=value,key=value" applies the same knobs when the Python binding loads the library. */
 int drag_debug_set(int key, int value);
 
