@@ -2,7 +2,9 @@
 # One parameterised GPU session (replaces the per-run scratch scripts of round 1):
 #   gpurun --timeout T -- 'bash scripts/gpu_session.sh <tag> <stage> [<stage> ...]'
 # Every stage writes gpurun_out/<tag>_<stage>.log and echoes its tail; a failing stage does not stop the session.
-# Stages: tests tests_x smoke bench bench_n bench_c3 scan sweep retrieve retrieve_b32 ref attn gemm launches ncu_hot ncu_vit ncu_stem
+# Stages: tests tests_x tests_new tests_pack tests_attn attn_quick smoke bench bench_fast bench_c3 scan sweep retrieve retrieve_ab
+#         (ABSET="15=1 15=3 ...": same-box A/B through DRAG_DEBUG_SET) retrieve_b32 ref attn gemm epilogue launches ncu_hot ncu_attn ncu_stem ncu_vit
+# Environment: NGPU (torchrun ranks), STEPS, TAIL (lines echoed per stage)
 tag=$1; shift
 mkdir -p gpurun_out
 run() { local t=$1 name=$2; shift 2; local t0=$SECONDS; timeout $t "$@" > gpurun_out/${tag}_$name.log 2>&1; local rc=$?
